@@ -1,0 +1,74 @@
+"""Pins the CPU oracle (oracle/mosaic_oracle.c) against the committed golden fixtures that
+oracle/make_golden.py produced from the real reference classes + cv2, and,
+when cv2 is importable, against live cv2 calls on fresh seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+KNN_TAGS_HAM = ["orb", "ties", "nt1", "nt2", "b64", "realorb"]
+KNN_TAGS_L2 = KNN_TAGS_HAM + ["siftint", "f32", "f32d61", "realsift"]
+
+
+@pytest.mark.parametrize("tag", KNN_TAGS_HAM)
+def test_knn_hamming_golden(golden, tag):
+    g = golden.knn
+    idx, dist = orc.knn2(g[f"{tag}_q"], g[f"{tag}_t"], "hamming")
+    assert np.array_equal(idx, g[f"{tag}_ham_idx"])
+    assert np.array_equal(dist, g[f"{tag}_ham_dist"])
+    assert np.array_equal(orc.ratio_test(idx, dist, 0.7), g[f"{tag}_ham_keep"])
+
+
+@pytest.mark.parametrize("tag", KNN_TAGS_L2)
+def test_knn_l2_golden(golden, tag):
+    g = golden.knn
+    idx, dist = orc.knn2(g[f"{tag}_q"], g[f"{tag}_t"], "l2")
+    assert np.array_equal(idx, g[f"{tag}_l2_idx"])
+    assert np.array_equal(dist, g[f"{tag}_l2_dist"])          # bit-exact, incl. generic fp32
+    assert np.array_equal(orc.ratio_test(idx, dist, 0.7), g[f"{tag}_l2_keep"])
+
+
+def test_warp_golden(golden):
+    g = golden.warp
+    for n in range(int(g["n"])):
+        for tag, interp in (("lin", orc.INTER_LINEAR), ("cub", orc.INTER_CUBIC)):
+            got = orc.warp_perspective(g[f"img{n}"], g[f"H{n}"], tuple(g[f"dsize{n}"]), interp)
+            assert np.array_equal(got, g[f"{tag}{n}"]), (n, tag)
+
+
+def test_mapper_golden(golden):
+    g = golden.mapper
+    for ci, (interp, alpha, use_kp, nupd, Hc, Wc) in enumerate(g["cases"]):
+        canvas = np.zeros((int(Hc), int(Wc), 3), np.uint8)
+        cmask = np.zeros((int(Hc), int(Wc)), np.uint8)
+        for k in range(int(nupd)):
+            roi = g[f"c{ci}_roi{k}"] if use_kp else None
+            orc.mapper_update(canvas, cmask, g[f"c{ci}_img{k}"], g[f"c{ci}_H{k}"], float(alpha), int(interp), roi)
+            assert np.array_equal(canvas, g[f"c{ci}_canvas{k}"]), (ci, k)
+            assert np.array_equal(cmask, g[f"c{ci}_mask{k}"]), (ci, k)
+
+
+def test_ratio_integer_form_equals_float64_form():
+    # mosaic.py:430 on Hamming ints:  d1 < 0.7*d2 (float64)  <=>  10*d1 < 7*d2  for 0 <= d <= 512
+    d1, d2 = np.meshgrid(np.arange(513), np.arange(513), indexing="ij")
+    assert np.array_equal(d1.astype(np.float64) < 0.7 * d2.astype(np.float64), 10 * d1 < 7 * d2)
+
+
+def test_oracle_vs_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (90, 130, 3), dtype=np.uint8)
+    for k in range(6):
+        th = rng.uniform(-1, 1)
+        H = np.array([[np.cos(th), -np.sin(th), rng.uniform(0, 80)], [np.sin(th), np.cos(th), rng.uniform(0, 60)],
+                      [rng.uniform(-1e-3, 1e-3), rng.uniform(-1e-3, 1e-3), 1.0]])
+        for fl, interp in ((cv2.INTER_LINEAR, 1), (cv2.INTER_CUBIC, 2)):
+            ref = cv2.warpPerspective(img, H, (200, 160), None, fl, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+            assert np.array_equal(ref, orc.warp_perspective(img, H, (200, 160), interp))
+    q = rng.integers(0, 256, (100, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (140, 32), dtype=np.uint8)
+    for norm, name in ((cv2.NORM_HAMMING, "hamming"), (cv2.NORM_L2, "l2")):
+        m = cv2.BFMatcher(norm).knnMatch(q, t, k=2)
+        idx, dist = orc.knn2(q, t, name)
+        assert [[mm.trainIdx for mm in r] for r in m] == idx.tolist()
+        assert np.array_equal(np.array([[mm.distance for mm in r] for r in m], np.float32), dist)
