@@ -1,0 +1,147 @@
+/*
+ * mosaic_b200.h -- C ABI of libmosaic_b200.so: the B200 (sm_100a) replacement for the
+ * arithmetic behind mosaic-library's per-frame registration + compositing hot path.
+ *
+ * The reference has no FFI of its own: its hot path is three OpenCV call sites reached
+ * from Python (paths relative to the mosaic-library checkout).  Every entry point below
+ * names the call site it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types.  All data pointers are DEVICE pointers owned by the
+ *     caller; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - every call is asynchronous on `stream`, keeps no global mutable state besides
+ *     read-only tables, and returns MK_OK or a negative mk_status; mk_last_error() gives a
+ *     thread-local message for the last failure on the calling thread.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with MK_ERR_CUDA.
+ */
+#ifndef MOSAIC_B200_H
+#define MOSAIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define MK_ABI_VERSION 1
+
+typedef enum mk_status {
+    MK_OK = 0,
+    MK_ERR_ARG = -1,      /* bad shape / null pointer / unsupported size            */
+    MK_ERR_ALIGN = -2,    /* pointer or pitch alignment requirement not met          */
+    MK_ERR_CUDA = -3,     /* CUDA runtime error (message in mk_last_error)           */
+    MK_ERR_WORKSPACE = -4 /* workspace too small (see mk_knn2_workspace_bytes)       */
+} mk_status;
+
+typedef enum mk_norm {
+    MK_NORM_HAMMING = 0,  /* cv2.NORM_HAMMING on uint8 rows (north-star ORB metric)  */
+    MK_NORM_L2_U8 = 1,    /* cv2.NORM_L2 on uint8 rows  (what registration.py:231 does for ORB) */
+    MK_NORM_L2_F32 = 2    /* cv2.NORM_L2 on float32 rows (SIFT)                      */
+} mk_norm;
+
+typedef enum mk_interp {
+    MK_INTER_LINEAR = 1,  /* cv2.INTER_LINEAR: 1/32-px fixed point, north-star kernel */
+    MK_INTER_CUBIC = 2    /* cv2.INTER_CUBIC: the flag mosaic.py:114,118 passes       */
+} mk_interp;
+
+typedef enum mk_blend {
+    MK_BLEND_ALPHA = 0,   /* Mapper._update_cpu semantics (mosaic.py:115-138)         */
+    MK_BLEND_FEATHER = 1  /* analytic feather weights + fp32 weight plane (extension) */
+} mk_blend;
+
+int mk_abi_version(void);
+const char *mk_version_string(void);
+const char *mk_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
+uint64_t mk_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Brute-force k=2 nearest neighbours + Lowe ratio test.
+ * Replaces  Matcher.knn_match -> cv2.BFMatcher.knnMatch(query, train, k=2)
+ *           (src/mosaicking/registration.py:233-242)  and the ratio test of
+ *           src/mosaicking/mosaic.py:430  (m[0].distance < ratio * m[1].distance, float64).
+ *
+ *   q, t      row-major descriptors, `row_stride` BYTES between rows (multiple of 16; rows
+ *             zero-padded up to a multiple of 16 bytes), `dim` = bytes per row for the uint8
+ *             norms (<= 64) or floats per row for MK_NORM_L2_F32 (<= 512).
+ *   idx       int32 [nq][2] train indices, ascending distance, ties -> lowest train index
+ *             (cv2's strict-< insertion); -1 where fewer than 2 train rows exist.
+ *   dist      float32 [nq][2] distances exactly as cv2 reports them (Hamming count as float,
+ *             sqrtf of the squared L2 sum); FLT_MAX where idx = -1.
+ *   keep      uint8 [nq] ratio-test flag (may be NULL); ratio <= 0 disables the test (keep=0).
+ *   n_keep    int32 [1] device counter of kept rows (may be NULL); overwritten.
+ *   workspace scratch of at least mk_knn2_workspace_bytes(..) bytes, 16-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim);
+
+int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t row_stride,
+            int32_t *idx, float *dist, double ratio, uint8_t *keep, int32_t *n_keep,
+            void *workspace, size_t workspace_bytes, void *stream);
+
+/* Batched form: many (query set, train set) pairs in one launch -- consecutive-frame pairs of
+ * SequentialMosaic.match_features (mosaic.py:402-438) or all-pairs loop closure.
+ *   desc       all descriptor rows of all sets, concatenated (same dim / row_stride)
+ *   set_off    int32 [nsets+1] DEVICE: first row of each set
+ *   pairs      int32 [npairs][2] DEVICE: (query set, train set)
+ *   out_off    int32 [npairs+1] DEVICE: first output row of each pair (prefix sum of nq)
+ *   max_nq / max_nt  upper bounds of the set sizes (host side, sizes the grid)
+ *   idx/dist/keep     outputs over sum(nq) rows;  n_keep int32 [npairs] (may be NULL) */
+size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim);
+
+int mk_knn2_batched(int norm, const void *desc, int dim, size_t row_stride, const int32_t *set_off,
+                    const int32_t *pairs, int npairs, const int32_t *out_off, int max_nq, int max_nt,
+                    int32_t *idx, float *dist, double ratio, uint8_t *keep, int32_t *n_keep,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Inverse-homography warp.  Replaces
+ *   cv2.warpPerspective(src, H, (dst_w, dst_h), None, interp, BORDER_CONSTANT, 0)
+ *   (src/mosaicking/mosaic.py:114,118; transformations.py:116).
+ * H is the 3x3 row-major float64 FORWARD map (frame -> canvas) in HOST memory, as the
+ * reference passes it; it is inverted on the host exactly like cv::invert does.
+ * uint8, channels = 1 or 3.  src/dst 16-byte aligned, pitches multiples of 16 (dst) / 4 (src);
+ * src dims <= 32767 (cv2's own limit, short source coordinates).
+ * ------------------------------------------------------------------------------------- */
+int mk_warp_perspective_u8(const uint8_t *src, int src_h, int src_w, int channels, size_t src_pitch,
+                           const double *H_host, uint8_t *dst, int dst_h, int dst_w, size_t dst_pitch,
+                           int interp, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused warp + validity mask + 5x5 erosion + blend + canvas / mask accumulation: one
+ * Mapper.update step (src/mosaicking/mosaic.py:159-172 -> _update_cpu :111-138) in a single
+ * pass over the warped footprint instead of ~8 full-canvas passes.
+ *
+ *   canvas   uint8 [canvas_h][canvas_w][3] BGR, in place       (Mapper._canvas)
+ *   cmask    uint8 [canvas_h][canvas_w], in place              (Mapper._canvas_mask)
+ *   wacc     float [canvas_h][canvas_w] weight plane, MK_BLEND_FEATHER only (else NULL)
+ *   src      uint8 [src_h][src_w][3] BGR frame
+ *   roi      uint8 [src_h][src_w] keypoint-hull mask (mosaic.py:140-157) or NULL
+ *   alpha    Mapper alpha_blend in [0,1]  (MK_BLEND_ALPHA);  feather_ramp in source px
+ *   region   if non-NULL (HOST int32[4]) receives the canvas rectangle x0,y0,x1,y1 visited
+ * Alignment: canvas/cmask/wacc 16-byte aligned with pitches (in bytes) multiples of 16;
+ * src/roi 4-byte aligned with pitches multiples of 4.
+ * ------------------------------------------------------------------------------------- */
+int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *cmask, size_t cmask_pitch,
+                     float *wacc, size_t wacc_pitch, int canvas_h, int canvas_w,
+                     const uint8_t *src, int src_h, int src_w, size_t src_pitch,
+                     const uint8_t *roi, size_t roi_pitch,
+                     const double *H_host, double alpha, int interp, int blend, float feather_ramp,
+                     int32_t *region_host, void *stream);
+
+/* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
+ * A = area of the canvas rectangle visited.  Pure host arithmetic. */
+int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,
+                        int interp, int32_t *region_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSAIC_B200_H */

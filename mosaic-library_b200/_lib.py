@@ -1,0 +1,87 @@
+"""ctypes binding of libmosaic_b200.so (declared in include/mosaic_b200.h).
+
+There is deliberately NO fallback here: if the shared library is missing or no CUDA device
+is present, every compute entry point raises.  PyTorch is used by the callers only to own
+device memory and streams; nothing in this module touches torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libmosaic_b200.so"
+CSRC = PKG_DIR / "csrc"
+
+MK_OK = 0
+NORM_HAMMING, NORM_L2_U8, NORM_L2_F32 = 0, 1, 2
+INTER_LINEAR, INTER_CUBIC = 1, 2
+BLEND_ALPHA, BLEND_FEATHER = 0, 1
+
+EXPORTS = (
+    "mk_abi_version", "mk_version_string", "mk_last_error", "mk_launch_count",
+    "mk_knn2_workspace_bytes", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
+    "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_footprint",
+)
+
+
+class MosaicB200Error(RuntimeError):
+    """Raised when libmosaic_b200 reports an error (the message comes from mk_last_error)."""
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile csrc/*.cu for sm_100a into libmosaic_b200.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", str(CSRC)], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise MosaicB200Error(f"nvcc build failed:\n{out.stdout}\n{out.stderr}")
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MosaicB200Error(
+            f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the CUDA path)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, sz, f64 = C.c_void_p, C.c_int, C.c_size_t, C.c_double
+    L.mk_abi_version.restype = i32
+    L.mk_version_string.restype = C.c_char_p
+    L.mk_last_error.restype = C.c_char_p
+    L.mk_launch_count.restype = C.c_uint64
+    L.mk_knn2_workspace_bytes.restype = sz
+    L.mk_knn2_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.mk_knn2_batched_workspace_bytes.restype = sz
+    L.mk_knn2_batched_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.mk_knn2.restype = i32
+    L.mk_knn2.argtypes = [i32, vp, i32, vp, i32, i32, sz, vp, vp, f64, vp, vp, vp, sz, vp]
+    L.mk_knn2_batched.restype = i32
+    L.mk_knn2_batched.argtypes = [i32, vp, i32, sz, vp, vp, i32, vp, i32, i32, vp, vp, f64, vp, vp, vp, sz, vp]
+    L.mk_warp_perspective_u8.restype = i32
+    L.mk_warp_perspective_u8.argtypes = [vp, i32, i32, i32, sz, vp, vp, i32, i32, sz, i32, vp]
+    L.mk_mapper_update.restype = i32
+    L.mk_mapper_update.argtypes = [vp, sz, vp, sz, vp, sz, i32, i32, vp, i32, i32, sz, vp, sz, vp, f64, i32, i32,
+                                   C.c_float, vp, vp]
+    L.mk_mapper_footprint.restype = i32
+    L.mk_mapper_footprint.argtypes = [i32, i32, i32, i32, vp, i32, vp]
+    if L.mk_abi_version() != 1:
+        raise MosaicB200Error("libmosaic_b200 ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != MK_OK:
+        raise MosaicB200Error(f"libmosaic_b200 error {rc}: {lib().mk_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().mk_launch_count())

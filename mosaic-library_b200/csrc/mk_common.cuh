@@ -1,0 +1,43 @@
+// mk_common.cuh -- shared host/device helpers for libmosaic_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/mosaic_b200.h"
+
+namespace mk {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MK_ERR_CUDA;
+}
+
+#define MK_CUDA_TRY(expr)                                         \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return mk::cuda_fail(_e, #expr);   \
+    } while (0)
+
+#define MK_LAUNCH_CHECK(name)                                     \
+    do {                                                          \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return mk::cuda_fail(_e, name);    \
+        mk::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    } while (0)
+
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// 3x3 inverse exactly as cv::invert does for 3x3 double matrices (closed-form adjugate, no FMA
+// contraction: this translation unit's host code is built with -ffp-contract=off).
+// cv::warpPerspective inverts H unless WARP_INVERSE_MAP is set (mosaic.py:114 does not set it).
+bool invert3x3(const double *S, double *D);
+
+}  // namespace mk

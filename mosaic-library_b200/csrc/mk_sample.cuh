@@ -1,0 +1,200 @@
+// mk_sample.cuh -- OpenCV-exact inverse-map coordinate pipeline and fixed-point samplers.
+//
+// Restates (never copies) what cv::warpPerspective + cv::remap do for uint8 images with
+// BORDER_CONSTANT(0), the call of src/mosaicking/mosaic.py:114:
+//   * destination walked in blocks 64 px wide; X0/Y0/W0 evaluated in double at the block's
+//     first column, advanced by M*x1 inside the block; no FMA contraction anywhere
+//   * W = W ? 32/W : 0; coordinates rounded half-to-even to 1/32 px (cvt.rni saturates like
+//     the INT_MIN/INT_MAX clamp for every finite value)
+//   * INTER_LINEAR: integer weights (32-ax)(32-ay).. , (sum + 512) >> 10
+//   * INTER_CUBIC : 32x32 table of 4x4 int16 weights (sum 32768), (sum + 2^14) >> 15, saturate
+//   * a tap outside the source contributes 0 (per tap)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mk {
+
+constexpr int BLOCK_W = 64;  // OpenCV's warpPerspective block width for dst width >= 64
+
+struct InvMap {
+    double m[9];  // inverse homography (canvas -> frame), cv::invert bits
+    double wr;    // 32 / m[8] when affine
+    int affine;   // m[6] == 0 && m[7] == 0
+};
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+
+// X0/Y0/W0 of a block row: block first column x0, destination row y.
+__device__ __forceinline__ void row_base(const InvMap &M, int x0, int y, double &X0, double &Y0, double &W0)
+{
+    const double dx = (double)x0, dy = (double)y;
+    X0 = dadd(dadd(dmul(M.m[0], dx), dmul(M.m[1], dy)), M.m[2]);
+    Y0 = dadd(dadd(dmul(M.m[3], dx), dmul(M.m[4], dy)), M.m[5]);
+    W0 = dadd(dadd(dmul(M.m[6], dx), dmul(M.m[7], dy)), M.m[8]);
+}
+
+// mx/my/mw = M[0]*x1, M[3]*x1, M[6]*x1 (x1 = column inside the block).
+__device__ __forceinline__ void quantize(const InvMap &M, double X0, double Y0, double W0, double mx, double my,
+                                         double mw, int &X, int &Y)
+{
+    double W;
+    if (M.affine) {
+        W = M.wr;  // W0 + (+-0) == m[8] exactly, so 32/W is a per-frame constant
+    } else {
+        W = dadd(W0, mw);
+        W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+    }
+    X = __double2int_rn(dmul(dadd(X0, mx), W));
+    Y = __double2int_rn(dmul(dadd(Y0, my), W));
+}
+
+__device__ __forceinline__ uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------
+// INTER_LINEAR, 3 channels.  Returns B | G<<8 | R<<16.
+// Fast path: the 2x2 footprint and the three aligned words around it lie inside the row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tap3(const uint8_t *__restrict__ src, size_t pitch, int h, int w, int y, int x)
+{
+    if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return 0u;
+    const uint8_t *p = src + (size_t)y * pitch + (size_t)x * 3;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+}
+
+__device__ __forceinline__ uint32_t lerp3(uint32_t p00, uint32_t p01, uint32_t p10, uint32_t p11, int ax, int ay)
+{
+    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int s = 8 * c;
+        const int v = (int)((p00 >> s) & 255u) * w00 + (int)((p01 >> s) & 255u) * w01 +
+                      (int)((p10 >> s) & 255u) * w10 + (int)((p11 >> s) & 255u) * w11 + 512;
+        out |= (uint32_t)(v >> 10) << s;
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t sample_linear_c3(const uint8_t *__restrict__ src, size_t pitch, int h, int w,
+                                                     int X, int Y)
+{
+    const int sx = X >> 5, sy = Y >> 5, ax = X & 31, ay = Y & 31;
+    if (sx < -1 || sx >= w || sy < -1 || sy >= h) return 0u;
+    uint32_t p00, p01, p10, p11;
+    if (sx >= 0 && sx <= w - 4 && sy >= 0 && sy <= h - 2) {
+        const uint8_t *a = src + (size_t)sy * pitch + (size_t)sx * 3;
+        const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+        const uint32_t *q0 = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
+        const uint32_t *q1 = reinterpret_cast<const uint32_t *>((ai & ~(uintptr_t)3) + pitch);  // pitch % 4 == 0
+        const unsigned sh = (unsigned)(ai & 3) * 8;
+        const uint32_t a0 = ldg32(q0), a1 = ldg32(q0 + 1), a2 = ldg32(q0 + 2);
+        const uint32_t b0 = ldg32(q1), b1 = ldg32(q1 + 1), b2 = ldg32(q1 + 2);
+        const uint32_t alo = __funnelshift_r(a0, a1, sh), ahi = __funnelshift_r(a1, a2, sh);
+        const uint32_t blo = __funnelshift_r(b0, b1, sh), bhi = __funnelshift_r(b1, b2, sh);
+        p00 = alo & 0xFFFFFFu;
+        p01 = (alo >> 24) | ((ahi & 0xFFFFu) << 8);
+        p10 = blo & 0xFFFFFFu;
+        p11 = (blo >> 24) | ((bhi & 0xFFFFu) << 8);
+    } else {
+        p00 = tap3(src, pitch, h, w, sy, sx);
+        p01 = tap3(src, pitch, h, w, sy, sx + 1);
+        p10 = tap3(src, pitch, h, w, sy + 1, sx);
+        p11 = tap3(src, pitch, h, w, sy + 1, sx + 1);
+    }
+    return lerp3(p00, p01, p10, p11, ax, ay);
+}
+
+// INTER_LINEAR, 1 channel (keypoint-hull ROI mask, mosaic.py:118).
+__device__ __forceinline__ uint32_t tap1(const uint8_t *__restrict__ src, size_t pitch, int h, int w, int y, int x)
+{
+    if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return 0u;
+    return (uint32_t)__ldg(src + (size_t)y * pitch + x);
+}
+
+__device__ __forceinline__ uint32_t sample_linear_c1(const uint8_t *__restrict__ src, size_t pitch, int h, int w,
+                                                     int X, int Y)
+{
+    const int sx = X >> 5, sy = Y >> 5, ax = X & 31, ay = Y & 31;
+    if (sx < -1 || sx >= w || sy < -1 || sy >= h) return 0u;
+    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+    const int v = (int)tap1(src, pitch, h, w, sy, sx) * w00 + (int)tap1(src, pitch, h, w, sy, sx + 1) * w01 +
+                  (int)tap1(src, pitch, h, w, sy + 1, sx) * w10 + (int)tap1(src, pitch, h, w, sy + 1, sx + 1) * w11 + 512;
+    return (uint32_t)(v >> 10);
+}
+
+// ------------------------------------------------------------------------------------------
+// INTER_CUBIC.  tab = 1024 x 16 int16 weights ([ay*32+ax][ky*4+kx]) in global memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clamp_u8(int v) { return min(255, max(0, v)); }
+
+__device__ __forceinline__ uint32_t sample_cubic_c3(const uint8_t *__restrict__ src, size_t pitch, int h, int w,
+                                                    int X, int Y, const short *__restrict__ tab)
+{
+    const int sx = X >> 5, sy = Y >> 5, ax = X & 31, ay = Y & 31;
+    if (sx < -2 || sx > w || sy < -2 || sy > h) return 0u;
+    const short *wt = tab + (ay * 32 + ax) * 16;
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+    if (sx >= 1 && sx <= w - 5 && sy >= 1 && sy <= h - 3) {
+        const uint8_t *a = src + (size_t)(sy - 1) * pitch + (size_t)(sx - 1) * 3;
+        const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+        const unsigned sh = (unsigned)(ai & 3) * 8;
+        const uint8_t *base = reinterpret_cast<const uint8_t *>(ai & ~(uintptr_t)3);
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(base + (size_t)ky * pitch);
+            const uint32_t r0 = ldg32(q), r1 = ldg32(q + 1), r2 = ldg32(q + 2), r3 = ldg32(q + 3);
+            const uint32_t d0 = __funnelshift_r(r0, r1, sh), d1 = __funnelshift_r(r1, r2, sh),
+                           d2 = __funnelshift_r(r2, r3, sh);  // 12 bytes: 4 BGR pixels
+            const int w0 = wt[ky * 4 + 0], w1 = wt[ky * 4 + 1], w2 = wt[ky * 4 + 2], w3 = wt[ky * 4 + 3];
+            acc0 += (int)(d0 & 255u) * w0 + (int)(d0 >> 24) * w1 + (int)((d1 >> 16) & 255u) * w2 + (int)((d2 >> 8) & 255u) * w3;
+            acc1 += (int)((d0 >> 8) & 255u) * w0 + (int)(d1 & 255u) * w1 + (int)(d1 >> 24) * w2 + (int)((d2 >> 16) & 255u) * w3;
+            acc2 += (int)((d0 >> 16) & 255u) * w0 + (int)((d1 >> 8) & 255u) * w1 + (int)(d2 & 255u) * w2 + (int)(d2 >> 24) * w3;
+        }
+    } else {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const uint32_t p = tap3(src, pitch, h, w, sy - 1 + ky, sx - 1 + kx);
+                const int wv = wt[ky * 4 + kx];
+                acc0 += (int)(p & 255u) * wv;
+                acc1 += (int)((p >> 8) & 255u) * wv;
+                acc2 += (int)((p >> 16) & 255u) * wv;
+            }
+    }
+    return (uint32_t)clamp_u8((acc0 + (1 << 14)) >> 15) | ((uint32_t)clamp_u8((acc1 + (1 << 14)) >> 15) << 8) |
+           ((uint32_t)clamp_u8((acc2 + (1 << 14)) >> 15) << 16);
+}
+
+__device__ __forceinline__ uint32_t sample_cubic_c1(const uint8_t *__restrict__ src, size_t pitch, int h, int w,
+                                                    int X, int Y, const short *__restrict__ tab)
+{
+    const int sx = X >> 5, sy = Y >> 5, ax = X & 31, ay = Y & 31;
+    if (sx < -2 || sx > w || sy < -2 || sy > h) return 0u;
+    const short *wt = tab + (ay * 32 + ax) * 16;
+    int acc = 0;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+            acc += (int)tap1(src, pitch, h, w, sy - 1 + ky, sx - 1 + kx) * (int)wt[ky * 4 + kx];
+    return (uint32_t)clamp_u8((acc + (1 << 14)) >> 15);
+}
+
+template <int INTERP, int CN>
+__device__ __forceinline__ uint32_t sample(const uint8_t *__restrict__ src, size_t pitch, int h, int w, int X, int Y,
+                                           const short *__restrict__ tab)
+{
+    if constexpr (INTERP == 1) {
+        if constexpr (CN == 3) return sample_linear_c3(src, pitch, h, w, X, Y);
+        else return sample_linear_c1(src, pitch, h, w, X, Y);
+    } else {
+        if constexpr (CN == 3) return sample_cubic_c3(src, pitch, h, w, X, Y, tab);
+        else return sample_cubic_c1(src, pitch, h, w, X, Y, tab);
+    }
+}
+
+}  // namespace mk

@@ -1,0 +1,337 @@
+"""B200 drop-in for mosaicking.mosaic.Mapper and the frame -> tile routing helpers.
+
+Mirrors the reference (paths relative to the mosaic-library checkout):
+  Mapper                       src/mosaicking/mosaic.py:36-183   (update -> _update_cpu :111-138)
+  get_corners                  src/mosaicking/mosaic.py:727-768
+  get_mosaic_dimensions        src/mosaicking/mosaic.py:708-725
+  find_nice_homographies       src/mosaicking/mosaic.py:693-706
+  bbox_overlap                 src/mosaicking/registration.py:375-380 (shapely Polygon.intersects)
+  homogeneous_translation      src/mosaicking/transformations.py:533-536
+  assign_frames_to_tiles       the tile loop of SequentialMosaic._create_tile_graph, mosaic.py:595-619
+  calculate_tiles / assign_image_to_tiles / calculate_translation_homography   splitter.py:11-77
+  combine_tiles                examples/combine_tiles.py:46-62
+
+The per-frame arithmetic (warp, validity mask, 5x5 erosion, blend, mask accumulation) is ONE fused
+CUDA kernel (csrc/mk_mapper.cu) reached through the C ABI of include/mosaic_b200.h; the canvas and
+its mask stay resident in HBM for the Mapper's lifetime.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .registration import _cuda_device
+
+try:
+    import cv2 as _cv2
+except Exception:  # pragma: no cover
+    _cv2 = None
+
+INTERP = {"linear": _lib.INTER_LINEAR, "cubic": _lib.INTER_CUBIC, 1: _lib.INTER_LINEAR, 2: _lib.INTER_CUBIC}
+BLEND = {"alpha": _lib.BLEND_ALPHA, "feather": _lib.BLEND_FEATHER}
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def make_bgr_host(image: np.ndarray) -> np.ndarray:
+    """preprocessing.make_bgr (preprocessing.py:332-346) for host arrays: gray -> BGR, BGRA -> BGR."""
+    if image.ndim == 2:
+        return np.repeat(image[:, :, None], 3, axis=2)
+    if image.shape[-1] == 4:
+        return np.ascontiguousarray(image[:, :, :3])
+    if image.shape[-1] == 1:
+        return np.repeat(image, 3, axis=2)
+    return image
+
+
+class Mapper:
+    """Accumulates warped frames into a canvas resident on the GPU (reference: mosaic.py:36-183).
+
+    Mapper(output_width, output_height, alpha_blend=0.5) and update(image, H, stream, keypoints)
+    keep the reference's signature.  Extra keyword-only knobs:
+      interp   "cubic" (what the reference hard-codes, mosaic.py:114) or "linear" (north-star kernel)
+      blend    "alpha" (reference semantics) or "feather" (SURVEY.md A.4b extension)
+    """
+
+    def __init__(self, output_width: int, output_height: int, alpha_blend: float = 0.5, *, interp="cubic",
+                 blend: str = "alpha", feather_ramp: float | None = None, device=None):
+        assert 0.0 <= alpha_blend <= 1.0, "Alpha blend must in interval [0, 1]."
+        self._alpha = float(alpha_blend)
+        self._interp = INTERP[interp]
+        self._blend = BLEND[blend]
+        self._ramp = feather_ramp
+        self._device = _cuda_device(device)
+        self._lib = _lib.lib()
+        self._width, self._height = int(output_width), int(output_height)
+        self._canvas, self._canvas_mask, self._wacc = self._create_canvas(self._width, self._height)
+        self._stage = None      # device staging buffer for host frames
+        self._stage_roi = None
+        self._flag = True
+        self.last_region = (0, 0, 0, 0)
+
+    # canvas rows are padded so that every 64-px tile row is made of whole 16-byte vectors
+    def _create_canvas(self, output_width: int, output_height: int):
+        cp = _round_up(_round_up(output_width, 64) * 3, 256)
+        mp = _round_up(_round_up(output_width, 64), 256)
+        canvas = torch.zeros((output_height, cp), dtype=torch.uint8, device=self._device)
+        mask = torch.zeros((output_height, mp), dtype=torch.uint8, device=self._device)
+        wacc = None
+        if self._blend == _lib.BLEND_FEATHER:
+            wacc = torch.zeros((output_height, _round_up(output_width, 64)), dtype=torch.float32, device=self._device)
+        return canvas, mask, wacc
+
+    def _create_keypoint_mask(self, keypoints, image_dims: tuple[int, int]) -> np.ndarray:
+        """mosaic.py:140-157: filled convex hull of the keypoints (host side, as in the reference)."""
+        if _cv2 is None:
+            raise _lib.MosaicB200Error("keypoint ROI masks need cv2 for convexHull / fillConvexPoly")
+        mask = np.zeros(image_dims[1::-1], dtype=np.uint8)
+        hull = _cv2.convexHull(np.array(keypoints).astype(np.int32))
+        return _cv2.fillConvexPoly(mask, hull, 255)
+
+    def _to_device(self, image, slot: str, channels: int) -> tuple[torch.Tensor, int, int]:
+        """Host ndarray / tensor [h, w(, c)] -> pitched device buffer; returns (buffer, h, w)."""
+        if isinstance(image, torch.Tensor):
+            t = image
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(image))
+        if t.dtype != torch.uint8:
+            raise TypeError("Mapper.update needs uint8 images")
+        h, w = int(t.shape[0]), int(t.shape[1])
+        row = w * channels
+        t2 = t.reshape(h, row)
+        if t2.is_cuda and t2.stride(0) % 4 == 0 and t2.stride(1) == 1 and t2.data_ptr() % 4 == 0:
+            return t2, h, w
+        pitch = _round_up(row, 128)
+        buf = getattr(self, slot)
+        if buf is None or buf.shape[0] < h or buf.shape[1] != pitch:
+            buf = torch.empty((h, pitch), dtype=torch.uint8, device=self._device)
+            setattr(self, slot, buf)
+        buf[:h, :row].copy_(t2, non_blocking=True)
+        return buf, h, w
+
+    def update_device(self, frame: torch.Tensor, H: np.ndarray, roi: torch.Tensor | None = None) -> None:
+        """One fused update with a frame that already lives in HBM: uint8 [h, w, 3] (row stride a
+        multiple of 4 bytes).  `roi` is an optional uint8 [h, w] keypoint-hull mask on the device."""
+        buf, h, w = self._to_device(frame, "_stage", 3)
+        rbuf = None
+        if roi is not None:
+            rbuf, rh, rw = self._to_device(roi, "_stage_roi", 1)
+            assert (rh, rw) == (h, w)
+        self._launch(buf, h, w, rbuf, H)
+
+    def _launch(self, buf, h, w, rbuf, H) -> None:
+        Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
+        region = (ctypes.c_int32 * 4)()
+        ramp = self._ramp if self._ramp is not None else 0.1 * min(h, w)
+        rc = self._lib.mk_mapper_update(
+            self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
+            self._wacc.data_ptr() if self._wacc is not None else None,
+            self._wacc.stride(0) * 4 if self._wacc is not None else 0,
+            self._height, self._width, buf.data_ptr(), h, w, buf.stride(0),
+            rbuf.data_ptr() if rbuf is not None else None, rbuf.stride(0) if rbuf is not None else 0,
+            Hm.ctypes.data, self._alpha, self._interp, self._blend, float(ramp), region,
+            torch.cuda.current_stream(self._device).cuda_stream)
+        _lib.check(rc)
+        self.last_region = tuple(region)
+
+    def update(self, image, H: np.ndarray, stream=None, keypoints=None):
+        """mosaic.py:159-172.  `stream` is accepted and ignored, as in the reference."""
+        mask = None
+        if keypoints is not None and len(keypoints) and _cv2 is not None and isinstance(keypoints[0], _cv2.KeyPoint):
+            keypoints = _cv2.KeyPoint.convert(keypoints)
+            height, width = image.shape[:2]
+            mask = self._create_keypoint_mask(keypoints, (width, height))
+        if isinstance(image, np.ndarray):
+            image = make_bgr_host(image)
+        buf, h, w = self._to_device(image, "_stage", 3)
+        rbuf = self._to_device(mask, "_stage_roi", 1)[0] if mask is not None else None
+        self._launch(buf, h, w, rbuf, H)
+
+    def release(self):
+        self._canvas = self._canvas_mask = self._wacc = self._stage = self._stage_roi = None
+
+    @property
+    def output(self) -> np.ndarray:
+        """Host copy of the canvas, uint8 [H, W, 3] (mosaic.py:179-183)."""
+        return self.output_device.cpu().numpy()
+
+    @property
+    def output_device(self) -> torch.Tensor:
+        return self._canvas[:, : self._width * 3].reshape(self._height, self._width, 3)
+
+    @property
+    def mask(self) -> np.ndarray:
+        """Host copy of Mapper._canvas_mask, uint8 [H, W]."""
+        return self._canvas_mask[:, : self._width].cpu().numpy()
+
+    @property
+    def weights(self) -> np.ndarray | None:
+        return None if self._wacc is None else self._wacc[:, : self._width].cpu().numpy()
+
+    def footprint_bytes(self, h: int, w: int, H: np.ndarray) -> int:
+        """Algorithmic bytes of one update: src + 2*3*A + 2*A (+ 8*A in feather mode)."""
+        Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
+        region = (ctypes.c_int32 * 4)()
+        _lib.check(self._lib.mk_mapper_footprint(self._height, self._width, h, w, Hm.ctypes.data, self._interp, region))
+        area = max(0, region[2] - region[0]) * max(0, region[3] - region[1])
+        return h * w * 3 + area * (8 + (8 if self._blend == _lib.BLEND_FEATHER else 0))
+
+
+def warp_perspective(image, H: np.ndarray, dsize: tuple[int, int], interp="linear", device=None) -> torch.Tensor:
+    """cv2.warpPerspective(image, H, dsize, None, interp, BORDER_CONSTANT, 0) on the GPU
+    (mosaic.py:114 / transformations.py:116).  uint8, 1 or 3 channels; returns a device tensor."""
+    device = _cuda_device(device)
+    t = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(image))
+    cn = 1 if t.ndim == 2 else int(t.shape[2])
+    h, w = int(t.shape[0]), int(t.shape[1])
+    pitch = _round_up(w * cn, 128)
+    src = torch.empty((h, pitch), dtype=torch.uint8, device=device)
+    src[:, : w * cn].copy_(t.reshape(h, w * cn), non_blocking=True)
+    Wd, Hd = int(dsize[0]), int(dsize[1])
+    dpitch = _round_up(Wd * cn, 128)
+    dst = torch.empty((Hd, dpitch), dtype=torch.uint8, device=device)
+    Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
+    _lib.check(_lib.lib().mk_warp_perspective_u8(src.data_ptr(), h, w, cn, pitch, Hm.ctypes.data, dst.data_ptr(), Hd, Wd,
+                                                 dpitch, INTERP[interp], torch.cuda.current_stream(device).cuda_stream))
+    out = dst[:, : Wd * cn]
+    return out.reshape(Hd, Wd) if cn == 1 else out.reshape(Hd, Wd, cn)
+
+
+# ------------------------------------------------------------------------------------------------
+# Host-side geometry (3x3 float64 math; defines the multi-GPU partition)
+# ------------------------------------------------------------------------------------------------
+def homogeneous_translation(x: float, y: float) -> np.ndarray:
+    out = np.eye(3)
+    out[[0, 1], 2] = [x, y]
+    return out
+
+
+def find_nice_homographies(H: np.ndarray, eps: float = 1e-3) -> np.ndarray:
+    det = np.linalg.det(H[:, :2, :2]) if H.ndim > 2 else np.linalg.det(H)
+    return det > eps
+
+
+def get_corners(H: np.ndarray, width, height) -> np.ndarray:
+    """Warped positions of the image corners (taken at pixel centres, +0.5), shape M x N x 1 x 2."""
+    if isinstance(width, (int, np.integer)):
+        src_crn = np.array([[[0, 0]], [[width - 1, 0]], [[width - 1, height - 1]], [[0, height - 1]]], np.float32) + 0.5
+    elif len(width):
+        crns = [[[0, 0]]]
+        for w, h in zip(width, height):
+            crns.extend([[[w - 1, 0]], [[w - 1, h - 1]], [[0, h - 1]]])
+        src_crn = np.array(crns, np.float32) + 0.5
+    else:
+        raise ValueError("width and height must either be ints or sequences of ints with same length.")
+    H = np.asarray(H)
+    if H.ndim > 2:
+        src_crn = np.stack([src_crn] * len(H), 0)
+    else:
+        src_crn = src_crn[None, ...]
+        H = H[None, ...]
+    M, N = src_crn.shape[:2]
+    src_h = np.concatenate((src_crn, np.ones((M, N, 1, 1))), axis=-1)
+    dst_h = np.swapaxes(H @ np.swapaxes(src_h.squeeze(axis=2), 1, 2), 1, 2)
+    dst = dst_h[:, :, :2] / dst_h[:, :, -1:]
+    return dst[:, :, None, :]
+
+
+def get_mosaic_dimensions(H: np.ndarray, width, height):
+    dst = get_corners(H, width, height).reshape(-1, 2)
+    min_x, min_y = dst.min(axis=0)
+    max_x, max_y = dst.max(axis=0)
+    return min_x, min_y, max_x - min_x, max_y - min_y
+
+
+def _convex_intersects(a: np.ndarray, b: np.ndarray) -> bool:
+    """Closed convex polygons share a point <=> no separating axis with a strict gap."""
+    for poly in (a, b):
+        n = len(poly)
+        for i in range(n):
+            ex, ey = poly[(i + 1) % n] - poly[i]
+            if ex == 0 and ey == 0:
+                continue
+            nx, ny = -ey, ex
+            pa = a[:, 0] * nx + a[:, 1] * ny
+            pb = b[:, 0] * nx + b[:, 1] * ny
+            if pa.max() < pb.min() or pb.max() < pa.min():
+                return False
+    return True
+
+
+def bbox_overlap(shape_1: np.ndarray, shape_2: np.ndarray) -> bool:
+    """registration.py:375-380: Polygon(shape_1).intersects(Polygon(shape_2)) for convex quads."""
+    a = np.asarray(shape_1, np.float64).reshape(-1, 2)
+    b = np.asarray(shape_2, np.float64).reshape(-1, 2)
+    return _convex_intersects(a, b)
+
+
+def assign_frames_to_tiles(H_all: np.ndarray, dims: Sequence[tuple[int, int]], tile_size: tuple[int, int]):
+    """The tile loop of SequentialMosaic._create_tile_graph (mosaic.py:589-619).
+
+    H_all: N x 3 x 3 absolute homographies (top-left referenced); dims: N x (width, height).
+    Returns {(tile_x_idx, tile_y_idx): {frame_index: H_tile}} with H_tile = T(-tx,-ty) @ H (:617)."""
+    H_all = np.asarray(H_all, np.float64)
+    widths = [int(d[0]) for d in dims]
+    heights = [int(d[1]) for d in dims]
+    mosaic_dims = get_mosaic_dimensions(H_all, widths, heights)
+    tile_x = range(0, math.ceil(mosaic_dims[2]), tile_size[0])
+    tile_y = range(0, math.ceil(mosaic_dims[3]), tile_size[1])
+    corners = [get_corners(H_all[k], widths[k], heights[k]).squeeze().astype(int) for k in range(len(H_all))]
+    tiles = {}
+    for xi, tx in enumerate(tile_x):
+        for yi, ty in enumerate(tile_y):
+            tile_crns = np.array([[tx, ty], [tx + tile_size[0], ty], [tx + tile_size[0], ty + tile_size[1]],
+                                  [tx, ty + tile_size[1]]], dtype=int)
+            frames = {}
+            for k in range(len(H_all)):
+                if bbox_overlap(tile_crns, corners[k]):
+                    frames[k] = homogeneous_translation(-tx, -ty) @ H_all[k]
+            if frames:
+                tiles[(xi, yi)] = frames
+    return tiles
+
+
+def calculate_tiles(bounding_box, tile_size):
+    """splitter.py:11-39."""
+    min_x, min_y, width, height = bounding_box
+    max_x, max_y = min_x + width, min_y + height
+    tw, th = tile_size
+    tiles = []
+    for i in range(int(np.ceil(width / tw))):
+        for j in range(int(np.ceil(height / th))):
+            x0, y0 = min_x + i * tw, min_y + j * th
+            tiles.append((x0, y0, min(x0 + tw, max_x), min(y0 + th, max_y)))
+    return tiles
+
+
+def assign_image_to_tiles(warped_corners, tiles):
+    """splitter.py:42-58: a tile is selected when one of the warped corners falls inside it."""
+    out = []
+    for idx, (min_x, min_y, max_x, max_y) in enumerate(tiles):
+        if np.any((warped_corners[:, 0] >= min_x) & (warped_corners[:, 0] < max_x) &
+                  (warped_corners[:, 1] >= min_y) & (warped_corners[:, 1] < max_y)):
+            out.append(idx)
+    return tuple(out)
+
+
+def calculate_translation_homography(homography, tile_origin):
+    """splitter.py:61-77."""
+    return np.array([[1, 0, -tile_origin[0]], [0, 1, -tile_origin[1]], [0, 0, 1]]) @ homography
+
+
+def combine_tiles(tiles: dict, tile_size: tuple[int, int]) -> np.ndarray:
+    """examples/combine_tiles.py:46-62: paste tile (x, y) at (x*tile_w, y*tile_h) of one canvas."""
+    tw, th = tile_size
+    max_x = max(x for x, _ in tiles) * tw + tw
+    max_y = max(y for _, y in tiles) * th + th
+    canvas = np.zeros((max_y, max_x, 3), dtype=np.uint8)
+    for (x, y), img in tiles.items():
+        canvas[y * th:y * th + th, x * tw:x * tw + tw] = img
+    return canvas

@@ -1,0 +1,233 @@
+"""B200 drop-in for mosaicking.registration.Matcher / CompositeMatcher.
+
+Mirrors src/mosaicking/registration.py:226-298 of the reference (same class names, method
+names, argument meaning, return shapes and pickling contract); the arithmetic runs in
+libmosaic_b200 (csrc/mk_knn.cu) instead of cv2.BFMatcher.  PyTorch only owns device memory.
+
+Two things the reference does not have, both optional:
+  * `norm`: the reference Matcher is always NORM_L2, even for ORB bytes (registration.py:231);
+    "l2" (default) reproduces that bit for bit, "hamming" is the north-star ORB metric
+    (cv2.BFMatcher(NORM_HAMMING) semantics).
+  * `knn_match_arrays`: idx / dist / keep arrays with the Lowe ratio test (mosaic.py:430) fused
+    on the device, so callers need not materialise 2*Nq cv2.DMatch objects.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+try:  # cv2 is only used for the DMatch value type the reference API returns
+    import cv2 as _cv2
+    DMatch = _cv2.DMatch
+except Exception:  # pragma: no cover - cv2 is part of the image
+    _cv2 = None
+
+    class DMatch:  # minimal stand-in with cv2.DMatch's attributes
+        __slots__ = ("queryIdx", "trainIdx", "imgIdx", "distance")
+
+        def __init__(self, queryIdx=-1, trainIdx=-1, imgIdx=-1, distance=float("inf")):
+            self.queryIdx, self.trainIdx, self.imgIdx, self.distance = queryIdx, trainIdx, imgIdx, distance
+
+
+def _cuda_device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.MosaicB200Error("no CUDA device: the B200 path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _bad_input(msg: str):
+    if _cv2 is not None:
+        return _cv2.error(msg)
+    return ValueError(msg)
+
+
+def _norm_code(norm: str, dtype) -> int:
+    if dtype == np.uint8:
+        if norm == "hamming":
+            return _lib.NORM_HAMMING
+        if norm == "l2":
+            return _lib.NORM_L2_U8
+    elif dtype == np.float32:
+        if norm == "l2":
+            return _lib.NORM_L2_F32
+        if norm == "hamming":
+            raise _bad_input("hamming norm needs uint8 descriptors")
+    raise _bad_input(f"unsupported descriptor dtype {dtype} / norm {norm} (cv2 accepts CV_8U and CV_32F)")
+
+
+def upload_descriptors(desc, device=None) -> tuple[torch.Tensor, int]:
+    """Host ndarray / tensor [n, dim] -> device tensor whose rows are zero-padded to a multiple of
+    16 bytes (zero padding changes neither Hamming nor L2 distances).  Returns (tensor, dim)."""
+    device = _cuda_device(device)
+    if isinstance(desc, torch.Tensor):
+        t = desc
+    else:
+        a = np.asarray(desc)
+        if a.ndim != 2:
+            raise _bad_input("descriptors must be 2-D")
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in (torch.uint8, torch.float32):
+        raise _bad_input(f"unsupported descriptor dtype {t.dtype}")
+    n, dim = t.shape
+    row_bytes = dim * t.element_size()
+    pad_bytes = (-row_bytes) % 16
+    if pad_bytes == 0 and t.is_cuda and t.is_contiguous():
+        return t, dim
+    pad = pad_bytes // t.element_size()
+    out = torch.zeros((n, dim + pad), dtype=t.dtype, device=device)
+    if n:
+        out[:, :dim].copy_(t, non_blocking=True)
+    return out, dim
+
+
+class Matcher:
+    """Brute-force k=2 matcher (reference: registration.py:226-264)."""
+
+    def __init__(self, norm: str = "l2", device=None):
+        if norm not in ("l2", "hamming"):
+            raise ValueError("norm must be 'l2' (reference behaviour) or 'hamming'")
+        self._norm = norm
+        self._device = device
+        self._matcher = self._create_matcher()
+
+    # -- reference-shaped plumbing ------------------------------------------------------------
+    def _create_matcher(self):
+        # the reference builds a cv2.BFMatcher here (registration.py:230-231); ours is a handle on
+        # the C-ABI library plus a growable device workspace
+        return {"lib": _lib.lib(), "workspace": None}
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        del state["_matcher"]  # no CUDA handles in the pickle (registration.py:255-259)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._matcher = self._create_matcher()
+
+    def _workspace(self, nbytes: int, device) -> torch.Tensor:
+        ws = self._matcher["workspace"]
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+            self._matcher["workspace"] = ws
+        return ws
+
+    # -- device-side entry points --------------------------------------------------------------
+    def knn_match_device(self, query, train, ratio: float = 0.7):
+        """-> (idx int32 [nq,2], dist float32 [nq,2], keep uint8 [nq], n_keep int32 [1]) on the device."""
+        device = _cuda_device(self._device)
+        q, dim = upload_descriptors(query, device)
+        t, dim_t = upload_descriptors(train, device)
+        if q.dtype != t.dtype:
+            raise _bad_input("query and train descriptors must have the same type")
+        if dim != dim_t:
+            raise _bad_input("query and train descriptors must have the same width")
+        code = _norm_code(self._norm, np.uint8 if q.dtype == torch.uint8 else np.float32)
+        nq, nt = q.shape[0], t.shape[0]
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
+        dist = torch.empty((nq, 2), dtype=torch.float32, device=device)
+        keep = torch.empty((nq,), dtype=torch.uint8, device=device)
+        n_keep = torch.zeros((1,), dtype=torch.int32, device=device)
+        if nq == 0:
+            return idx, dist, keep, n_keep
+        L = self._matcher["lib"]
+        ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device)
+        stride = q.stride(0) * q.element_size()
+        assert stride == t.stride(0) * t.element_size()
+        _lib.check(L.mk_knn2(code, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, dim, stride,
+                             idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), n_keep.data_ptr(),
+                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+        return idx, dist, keep, n_keep
+
+    def knn_match_arrays(self, query, train, ratio: float = 0.7):
+        """-> (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) as numpy arrays.
+        idx = -1 / dist = FLT_MAX where the train set has fewer than 2 rows."""
+        idx, dist, keep, _ = self.knn_match_device(query, train, ratio)
+        return idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool)
+
+    # -- reference API ---------------------------------------------------------------------------
+    def knn_match(self, query: np.ndarray, train: np.ndarray, mask: np.ndarray = None) -> Sequence[Sequence[DMatch]]:
+        """registration.py:233-242: cv2.BFMatcher.knnMatch(query, train, k=2, mask=mask)."""
+        if mask is not None:
+            raise NotImplementedError("match masks are not on the accelerated path (the reference passes mask=None)")
+        if len(query) == 0:
+            return ()
+        idx, dist, _ = self.knn_match_arrays(query, train, ratio=0.0)
+        out = []
+        for i in range(idx.shape[0]):
+            row = []
+            for k in range(2):
+                if idx[i, k] >= 0:
+                    row.append(DMatch(i, int(idx[i, k]), 0, float(dist[i, k])))
+            out.append(tuple(row))
+        return tuple(out)
+
+    def match(self, query: np.ndarray, train: np.ndarray, mask: np.ndarray = None) -> Sequence[DMatch]:
+        """registration.py:244-253: best match per query row (rows without any match are dropped)."""
+        if mask is not None:
+            raise NotImplementedError("match masks are not on the accelerated path")
+        if len(query) == 0:
+            return ()
+        idx, dist, _ = self.knn_match_arrays(query, train, ratio=0.0)
+        return tuple(DMatch(i, int(idx[i, 0]), 0, float(dist[i, 0])) for i in range(idx.shape[0]) if idx[i, 0] >= 0)
+
+    def good_matches(self, query, train, ratio: float = 0.7) -> Sequence[DMatch]:
+        """knn_match + the Lowe ratio test of mosaic.py:430, materialising only the survivors."""
+        if len(query) == 0:
+            return ()
+        idx, dist, keep = self.knn_match_arrays(query, train, ratio)
+        return tuple(DMatch(int(i), int(idx[i, 0]), 0, float(dist[i, 0])) for i in np.flatnonzero(keep))
+
+
+class CompositeMatcher(Matcher):
+    """Per-feature-type matching (reference: registration.py:266-298)."""
+
+    def knn_match(self, query: dict, train: dict, mask: np.ndarray = None) -> dict:
+        if mask is not None:
+            warnings.warn("mask variable unused.")
+        matches = dict()
+        for feature_type in query.keys():
+            if query[feature_type] is None or train[feature_type] is None:
+                matches.update({feature_type: tuple()})
+                continue
+            matches.update({feature_type: super().knn_match(query[feature_type], train[feature_type])})
+        return matches
+
+    def match(self, query: dict, train: dict, mask: np.ndarray = None) -> dict:
+        if mask is not None:
+            warnings.warn("mask variable unused.")
+        matches = dict()
+        for feature_type in query:
+            matches.update({feature_type: super().match(query[feature_type], train[feature_type])})
+        return matches
+
+    def good_matches(self, query: dict, train: dict, ratio: float = 0.7) -> dict:
+        out = dict()
+        for feature_type in query.keys():
+            if query[feature_type] is None or train[feature_type] is None:
+                out[feature_type] = tuple()
+            else:
+                out[feature_type] = super().good_matches(query[feature_type], train[feature_type], ratio)
+        return out
+
+
+def get_matches(descriptors1, descriptors2, matcher: Matcher, minmatches: int):
+    """registration.py:300-319 with its evident intent (k=2 + ratio 0.7); the reference helper calls
+    `matcher.match` but unpacks pairs, so it only ever worked with a knn matcher."""
+    if not isinstance(descriptors1, (tuple, list)):
+        descriptors1 = [descriptors1]
+    if not isinstance(descriptors2, (tuple, list)):
+        descriptors2 = [descriptors2]
+    mlength = nlength = 0
+    good = []
+    for d1, d2 in zip(descriptors1, descriptors2):
+        for m in Matcher.good_matches(matcher, d1, d2, 0.7):
+            good.append(DMatch(m.queryIdx + mlength, m.trainIdx + nlength, 0, m.distance))
+        mlength += d1.shape[0]
+        nlength += d2.shape[0]
+    return minmatches <= len(good), good

@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped Python classes)
+against the CPU oracle and the committed golden fixtures.  Bit-exact for indices, integer and
+byte results; fp32 distances are compared bit-exactly as well (the kernels keep cv2's rounding
+order), with the north-star tolerance (1e-4 relative) stated where a looser bound would apply."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import mosaicking_b200 as mb  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+FLT_MAX = np.finfo(np.float32).max
+KNN_TAGS_HAM = ["orb", "ties", "nt1", "nt2", "b64", "realorb"]
+KNN_TAGS_L2 = KNN_TAGS_HAM + ["siftint", "f32", "f32d61", "realsift"]
+
+
+# ------------------------------------------------------------------------------------------------
+# matching
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", KNN_TAGS_HAM)
+def test_knn_hamming_golden(golden, tag):
+    g = golden.knn
+    idx, dist, keep = mb.Matcher(norm="hamming").knn_match_arrays(g[f"{tag}_q"], g[f"{tag}_t"], 0.7)
+    assert np.array_equal(idx, g[f"{tag}_ham_idx"])
+    assert np.array_equal(dist, g[f"{tag}_ham_dist"])
+    assert np.array_equal(keep, g[f"{tag}_ham_keep"])
+
+
+@pytest.mark.parametrize("tag", KNN_TAGS_L2)
+def test_knn_l2_golden(golden, tag):
+    g = golden.knn
+    idx, dist, keep = mb.Matcher().knn_match_arrays(g[f"{tag}_q"], g[f"{tag}_t"], 0.7)
+    assert np.array_equal(idx, g[f"{tag}_l2_idx"])
+    assert np.array_equal(dist, g[f"{tag}_l2_dist"])   # bit-exact; tolerance allowed by the spec: 1e-4 rel
+    assert np.array_equal(keep, g[f"{tag}_l2_keep"])
+
+
+def test_knn_match_api_shapes(golden):
+    """Matcher.knn_match returns what cv2.BFMatcher.knnMatch returns (registration.py:233-242)."""
+    g = golden.knn
+    m = mb.CompositeMatcher()
+    out = m.knn_match({"orb": g["orb_q"], "none": None}, {"orb": g["orb_t"], "none": None})
+    assert out["none"] == tuple()
+    rows = out["orb"]
+    assert len(rows) == len(g["orb_q"])
+    assert [[mm.trainIdx for mm in r] for r in rows] == g["orb_l2_idx"].tolist()
+    assert all(mm.queryIdx == i and mm.imgIdx == 0 for i, r in enumerate(rows) for mm in r)
+    # the reference's ratio comprehension (mosaic.py:430) over our DMatch lists gives the golden flags
+    good = [len(r) == 2 and r[0].distance < 0.7 * r[1].distance for r in rows]
+    assert good == g["orb_l2_keep"].tolist()
+    short = mb.Matcher().knn_match(g["nt1_q"], g["nt1_t"])
+    assert all(len(r) == 1 for r in short)
+    assert mb.Matcher().knn_match(np.zeros((0, 32), np.uint8), g["orb_t"]) == ()
+    assert all(r == () for r in mb.Matcher().knn_match(g["nt1_q"], np.zeros((0, 32), np.uint8)))
+    best = mb.Matcher().match(g["orb_q"], g["orb_t"])
+    assert [b.trainIdx for b in best] == g["orb_l2_idx"][:, 0].tolist()
+
+
+@pytest.mark.parametrize("nq,nt,nbytes", [(2000, 2000, 32), (5000, 5000, 32), (1, 1, 32), (33, 17, 32), (1000, 3, 32),
+                                           (257, 4099, 64), (300, 700, 61), (129, 200, 16)])
+@pytest.mark.parametrize("norm", ["hamming", "l2"])
+def test_knn_u8_vs_oracle(nq, nt, nbytes, norm):
+    rng = np.random.default_rng(nq * 7 + nt)
+    q = rng.integers(0, 256, (nq, nbytes), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, nbytes), dtype=np.uint8)
+    for i in range(0, min(nq, nt) // 100):       # planted duplicates -> exact ties
+        t[(i * 37) % nt] = q[i]; t[(i * 37 + 5) % nt] = q[i]
+    idx, dist, keep = mb.Matcher(norm=norm).knn_match_arrays(q, t, 0.7)
+    oi, od = orc.knn2(q, t, norm)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+    assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+
+
+@pytest.mark.parametrize("nq,nt,dim,integer", [(1000, 1200, 128, True), (500, 777, 128, False), (70, 65, 64, False),
+                                               (64, 64, 61, False), (3, 1, 128, True), (8000, 8000, 128, True)])
+def test_knn_f32_vs_oracle(nq, nt, dim, integer):
+    rng = np.random.default_rng(nq + nt + dim)
+    if integer:   # OpenCV SIFT descriptors are integer-valued floats in [0, 255]
+        q = rng.integers(0, 160, (nq, dim)).astype(np.float32)
+        t = rng.integers(0, 160, (nt, dim)).astype(np.float32)
+    else:
+        q = rng.standard_normal((nq, dim)).astype(np.float32)
+        t = rng.standard_normal((nt, dim)).astype(np.float32)
+    for i in range(min(nq, nt) // 50):
+        t[(i * 13) % nt] = q[i]
+    idx, dist, keep = mb.Matcher().knn_match_arrays(q, t, 0.7)
+    oi, od = orc.knn2(q, t, "l2")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)   # spec tolerance 1e-4 relative; the kernel is bit-exact
+    assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+
+
+def test_knn_batched_vs_single():
+    """mk_knn2_batched over consecutive-frame pairs == per-pair calls."""
+    rng = np.random.default_rng(3)
+    sizes = [700, 33, 1200, 1, 512]
+    sets = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in sizes]
+    desc = torch.from_numpy(np.concatenate(sets)).cuda()
+    set_off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32).cuda()
+    pairs_h = np.array([[1, 0], [2, 1], [3, 2], [4, 3], [0, 4]], np.int32)    # query = current, train = previous
+    out_off_h = np.concatenate([[0], np.cumsum([sizes[a] for a, _ in pairs_h])]).astype(np.int32)
+    pairs, out_off = torch.from_numpy(pairs_h).cuda(), torch.from_numpy(out_off_h).cuda()
+    total = int(out_off_h[-1])
+    L = mb._lib.lib()
+    for code, norm in ((0, "hamming"), (1, "l2")):
+        idx = torch.empty((total, 2), dtype=torch.int32, device="cuda")
+        dist = torch.empty((total, 2), dtype=torch.float32, device="cuda")
+        keep = torch.empty((total,), dtype=torch.uint8, device="cuda")
+        nk = torch.zeros((len(pairs_h),), dtype=torch.int32, device="cuda")
+        wsb = L.mk_knn2_batched_workspace_bytes(code, len(pairs_h), max(sizes), max(sizes), 32)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
+        mb._lib.check(L.mk_knn2_batched(code, desc.data_ptr(), 32, 32, set_off.data_ptr(), pairs.data_ptr(), len(pairs_h),
+                                        out_off.data_ptr(), max(sizes), max(sizes), idx.data_ptr(), dist.data_ptr(), 0.7,
+                                        keep.data_ptr(), nk.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream))
+        idx, dist, keep, nk = idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool), nk.cpu().numpy()
+        for p, (a, b) in enumerate(pairs_h):
+            oi, od = orc.knn2(sets[a], sets[b], norm)
+            sl = slice(out_off_h[p], out_off_h[p + 1])
+            assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od)
+            ok = orc.ratio_test(oi, od, 0.7)
+            assert np.array_equal(keep[sl], ok) and nk[p] == ok.sum()
+
+
+# ------------------------------------------------------------------------------------------------
+# warp
+# ------------------------------------------------------------------------------------------------
+def test_warp_golden(golden):
+    g = golden.warp
+    for n in range(int(g["n"])):
+        img = g[f"img{n}"]
+        if img.ndim == 3 and img.shape[2] == 4:
+            continue  # 4-channel warps are outside the path (Mapper converts BGRA -> BGR first)
+        for tag, interp in (("lin", "linear"), ("cub", "cubic")):
+            got = mb.warp_perspective(img, g[f"H{n}"], tuple(g[f"dsize{n}"]), interp).cpu().numpy()
+            assert np.array_equal(got, g[f"{tag}{n}"]), (n, tag)   # spec: +-1 LSB; achieved: bit-exact
+
+
+def _rand_H(rng, persp, tx, ty, smin=0.6, smax=1.6):
+    th, s = rng.uniform(-3.1, 3.1), rng.uniform(smin, smax)
+    return np.array([[s * np.cos(th), -s * np.sin(th), rng.uniform(0, tx)], [s * np.sin(th), s * np.cos(th), rng.uniform(0, ty)],
+                     [rng.uniform(-persp, persp), rng.uniform(-persp, persp), 1.0]])
+
+
+@pytest.mark.parametrize("interp,code", [("linear", 1), ("cubic", 2)])
+def test_warp_random_vs_oracle(interp, code):
+    rng = np.random.default_rng(21 + code)
+    for trial in range(12):
+        h, w = int(rng.integers(3, 300)), int(rng.integers(3, 400))
+        cn = 3 if trial % 3 else 1
+        img = rng.integers(0, 256, (h, w, cn), dtype=np.uint8)
+        if cn == 1:
+            img = img[:, :, 0]
+        H = _rand_H(rng, [0, 1e-4, 3e-3][trial % 3], 300, 200)
+        dsize = (int(rng.integers(1, 700)), int(rng.integers(1, 500)))
+        got = mb.warp_perspective(img, H, dsize, interp).cpu().numpy()
+        assert np.array_equal(got, orc.warp_perspective(img, H, dsize, code)), trial
+
+
+def test_warp_full_hd_vs_oracle():
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    H = np.array([[0.98, -0.17, 300.25], [0.17, 0.98, 120.5], [1e-6, -2e-6, 1.0]])
+    got = mb.warp_perspective(img, H, (2600, 1800), "linear").cpu().numpy()
+    assert np.array_equal(got, orc.warp_perspective(img, H, (2600, 1800), 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused warp + blend (Mapper)
+# ------------------------------------------------------------------------------------------------
+def test_mapper_golden(golden):
+    """Sequences produced by the reference Mapper (CUBIC as shipped and LINEAR-patched, +-ROI)."""
+    import cv2
+    g = golden.mapper
+    for ci, (interp, alpha, use_kp, nupd, Hc, Wc) in enumerate(g["cases"]):
+        mp = mb.Mapper(int(Wc), int(Hc), alpha_blend=float(alpha), interp=int(interp))
+        for k in range(int(nupd)):
+            kps = None
+            if use_kp:
+                kps = [cv2.KeyPoint(float(x), float(y), 1) for x, y in g[f"c{ci}_kp{k}"]]
+            mp.update(g[f"c{ci}_img{k}"], g[f"c{ci}_H{k}"], None, kps)
+            assert np.array_equal(mp.output, g[f"c{ci}_canvas{k}"]), (ci, k)
+            assert np.array_equal(mp.mask, g[f"c{ci}_mask{k}"]), (ci, k)
+        mp.release()
+
+
+def _img(rng, h, w, black=0.02):
+    base = rng.integers(1, 256, (h // 7 + 2, w // 7 + 2, 3), dtype=np.uint8)
+    img = np.kron(base, np.ones((7, 7, 1), np.uint8))[:h, :w].copy()
+    img[rng.random((h, w)) < black] = 0
+    return img
+
+
+@pytest.mark.parametrize("interp,code", [("linear", 1), ("cubic", 2)])
+@pytest.mark.parametrize("alpha", [0.0, 0.3, 0.5, 1.0])
+def test_mapper_random_vs_oracle(interp, code, alpha):
+    rng = np.random.default_rng(int(alpha * 10) + code)
+    Hc, Wc = 333, 517            # deliberately not multiples of the 64x32 tile
+    mp = mb.Mapper(Wc, Hc, alpha_blend=alpha, interp=interp)
+    canvas = np.zeros((Hc, Wc, 3), np.uint8)
+    cmask = np.zeros((Hc, Wc), np.uint8)
+    for k in range(5):
+        h, w = int(rng.integers(40, 200)), int(rng.integers(40, 260))
+        img = _img(rng, h, w)
+        H = _rand_H(rng, [0, 2e-4][k % 2], 400, 250, 0.7, 1.5)
+        mp.update(img, H)
+        orc.mapper_update(canvas, cmask, img, H, alpha, code)
+        assert np.array_equal(mp.output, canvas), k    # spec: +-1 LSB; achieved: bit-exact
+        assert np.array_equal(mp.mask, cmask), k
+
+
+def test_mapper_gray_and_bgra_inputs():
+    rng = np.random.default_rng(9)
+    gray = rng.integers(1, 256, (60, 80), dtype=np.uint8)
+    bgra = rng.integers(1, 256, (60, 80, 4), dtype=np.uint8)
+    H = np.array([[1.0, 0, 10.5], [0, 1.0, 7.25], [0, 0, 1.0]])
+    for img, ref in ((gray, np.repeat(gray[:, :, None], 3, 2)), (bgra, np.ascontiguousarray(bgra[:, :, :3]))):
+        mp = mb.Mapper(128, 96, alpha_blend=0.5, interp="linear")
+        mp.update(img, H)
+        canvas = np.zeros((96, 128, 3), np.uint8); cmask = np.zeros((96, 128), np.uint8)
+        orc.mapper_update(canvas, cmask, ref, H, 0.5, 1)
+        assert np.array_equal(mp.output, canvas)
+
+
+def test_mapper_feather_vs_oracle():
+    rng = np.random.default_rng(31)
+    Hc, Wc = 300, 400
+    mp = mb.Mapper(Wc, Hc, interp="linear", blend="feather", feather_ramp=12.0)
+    canvas = np.zeros((Hc, Wc, 3), np.uint8); cmask = np.zeros((Hc, Wc), np.uint8); wacc = np.zeros((Hc, Wc), np.float32)
+    for k in range(4):
+        img = _img(rng, 120, 160)
+        H = _rand_H(rng, 1e-4, 250, 180, 0.8, 1.3)
+        mp.update(img, H)
+        orc.mapper_update_feather(canvas, cmask, wacc, img, H, 12.0)
+        assert np.abs(mp.weights - wacc).max() <= 1e-5                               # blend weights within 1e-5
+        assert np.abs(mp.output.astype(int) - canvas.astype(int)).max() <= 1, k      # pixels within +-1 LSB
+        assert np.array_equal(mp.mask, cmask)
+
+
+def test_mapper_footprint_outside_and_partial():
+    mp = mb.Mapper(256, 256, alpha_blend=0.5, interp="linear")
+    img = np.full((50, 50, 3), 200, np.uint8)
+    mp.update(img, np.array([[1.0, 0, 5000.0], [0, 1.0, 5000.0], [0, 0, 1.0]]))     # entirely off-canvas
+    assert mp.output.sum() == 0 and mp.mask.sum() == 0
+    H = np.array([[1.0, 0, -20.0], [0, 1.0, 230.0], [0, 0, 1.0]])                    # straddles two canvas edges
+    mp.update(img, H)
+    canvas = np.zeros((256, 256, 3), np.uint8); cmask = np.zeros((256, 256), np.uint8)
+    orc.mapper_update(canvas, cmask, img, H, 0.5, 1)
+    assert np.array_equal(mp.output, canvas) and np.array_equal(mp.mask, cmask)
+
+
+def test_mapper_full_size_properties():
+    """BASELINE config sizes (1080p frame, 16k x 16k canvas): size-independent properties.
+       (a) alpha = 1 keeps the canvas in overlaps -> re-applying a frame is idempotent;
+       (b) an integer translation reproduces the frame exactly inside the eroded footprint;
+       (c) the region outside the reported footprint rectangle is untouched;
+       (d) a window around the footprint equals the oracle run on the same window (tile-local H, mosaic.py:617)."""
+    rng = np.random.default_rng(77)
+    Hc = Wc = 16384
+    img = rng.integers(1, 256, (1080, 1920, 3), dtype=np.uint8)
+    mp = mb.Mapper(Wc, Hc, alpha_blend=1.0, interp="linear")
+    T = np.array([[1.0, 0, 7000.0], [0, 1.0, 9000.0], [0, 0, 1.0]])
+    mp.update(img, T)
+    x0, y0, x1, y1 = mp.last_region
+    out = mp.output_device
+    assert torch.equal(out[9002:9000 + 1078, 7002:7000 + 1918].cpu(), torch.from_numpy(img[2:1078, 2:1918]))   # (b)
+    total = int(mp._canvas_mask.count_nonzero())
+    assert total == 1076 * 1916
+    before = out.clone()
+    mp.update(img, T)
+    assert torch.equal(before, mp.output_device)                                                               # (a)
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th), 3000.3], [np.sin(th), np.cos(th), 2000.7], [2e-6, 1e-6, 1.0]])
+    mp.update(img, R)
+    x0, y0, x1, y1 = mp.last_region
+    after = mp.output_device
+    keepmask = torch.ones((Hc, Wc), dtype=torch.bool, device="cuda")
+    keepmask[y0:y1, x0:x1] = False
+    assert torch.equal(after[keepmask], before[keepmask])                                                      # (c)
+    wx0, wy0 = (x0 // 64) * 64, (y0 // 32) * 32        # window origin on the 64-px block grid keeps cv2's block bases
+    win = np.zeros((y1 - wy0 + 8, x1 - wx0 + 8, 3), np.uint8); wm = np.zeros(win.shape[:2], np.uint8)
+    Rw = mb.homogeneous_translation(-wx0, -wy0) @ R
+    orc.mapper_update(win, wm, img, Rw, 1.0, 1)
+    got = after[wy0:wy0 + win.shape[0], wx0:wx0 + win.shape[1]].cpu().numpy()
+    assert np.abs(got.astype(int) - win.astype(int)).max() <= 1                                                # (d) +-1 LSB
+    assert (got != win).mean() < 1e-3
