@@ -38,12 +38,21 @@ struct MapperParams {
     float *wacc;
     const uint8_t *src, *roi;
     const short *cubic;
+    const uint2 *lut;
     unsigned long long cpitch, mpitch, wpitch, spitch, rpitch;
     int Hc, Wc, h, w;
     int tx0, ty0;
     InvMap M;
     float alpha, beta, ramp;
+    int src_smem_bytes;  // dynamic shared memory available for the staged source rectangle
+    int src_aligned;     // src 16-byte aligned with pitch % 16 == 0 (needed for 16-byte cp.async)
 };
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int nbytes)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(nbytes) : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -75,40 +84,179 @@ __device__ __forceinline__ uint32_t feather_u8(uint32_t c, uint32_t w, float acc
     return (uint32_t)min(255, max(0, __float2int_rn(t)));
 }
 
+// ---- async-proxy helpers (mbarrier + row-wise bulk copies; SASS: UBLKCP / SYNCS) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, bytes % 16 == 0, both addresses 16-byte aligned; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// byte k of x as float, and round-to-nearest-even back to an integer, both on the FP32 pipe
+// (2^23 / 1.5 * 2^23 magic constants) instead of the 16-lane I2F / F2I unit.  Exact for 0..255.
+template <int K>
+__device__ __forceinline__ float byte_to_float(uint32_t x)
+{
+    return __fadd_rn(__int_as_float((int)__byte_perm(x, 0x4B000000u, 0x7650u | K)), -8388608.0f);
+}
+__device__ __forceinline__ uint32_t rint_u8(float t)   // t in [0, 255.4]
+{
+    return (uint32_t)__float_as_int(__fadd_rn(t, 12582912.0f)) & 0x1FFu;
+}
+
+// cv2.addWeighted on uint8 (mosaic.py:133): rint(fmaf(c, a32, w * b32)), saturate.
+__device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float a, float b)
+{
+    const uint32_t o0 = min(255u, rint_u8(__fmaf_rn(byte_to_float<0>(c), a, __fmul_rn(byte_to_float<0>(w), b))));
+    const uint32_t o1 = min(255u, rint_u8(__fmaf_rn(byte_to_float<1>(c), a, __fmul_rn(byte_to_float<1>(w), b))));
+    const uint32_t o2 = min(255u, rint_u8(__fmaf_rn(byte_to_float<2>(c), a, __fmul_rn(byte_to_float<2>(w), b))));
+    return o0 | (o1 << 8) | (o2 << 16);
+}
+
 template <int INTERP, int BLEND, bool ROI>
 __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
-    __shared__ uint32_t s_warp[TH][TW];
+    __shared__ __align__(16) uint32_t s_warp[TH][TW];
     __shared__ double s_row[3][EH][3];
     __shared__ unsigned long long s_m0[EH];
     __shared__ unsigned long long s_h[EH];
     __shared__ unsigned long long s_v[TH];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint8_t s_side[EH][4];
+    __shared__ int s_corner[4][3];
     // ROI mode keeps the (non-binary) warped ROI values: erosion = 5x5 minimum
     __shared__ uint8_t s_mval[ROI ? EH : 1][ROI ? TW + 2 * HALO + 4 : 1];
     __shared__ uint8_t s_mh[ROI ? EH : 1][ROI ? TW : 1];
     __shared__ float s_wgt[BLEND == MK_BLEND_FEATHER ? TH : 1][BLEND == MK_BLEND_FEATHER ? TW : 1];
+    extern __shared__ __align__(16) uint8_t s_src[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tileX = (p.tx0 + (int)blockIdx.x) * TW, tileY = (p.ty0 + (int)blockIdx.y) * TH;
-    const int nvec = min(ROWV, ((p.Wc - tileX) * 3 + 15) >> 4);  // vectors holding canvas pixels
+    const int nvec = min(ROWV, ((p.Wc - tileX) * 3 + 15) >> 4);  // 16-byte vectors holding canvas pixels
 
-    // ---- stage the canvas tile (async, overlaps phase 1) ---------------------------------
-    for (int v = tid; v < TH * ROWV; v += NTHREADS) {
-        const int r = v / ROWV, c = v - r * ROWV, y = tileY + r;
-        if (y < p.Hc && c < nvec)
-            cp_async16(&s_canvas[r][c * 16], p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3 + c * 16);
-    }
-
-    // ---- per-row coordinate bases for the left / centre / right 64-px blocks --------------
+    // ---- per-row coordinate bases for the left / centre / right 64-px blocks, and the source
+    //      positions of the four corners of the haloed tile ---------------------------------------
     if (tid < 3 * EH) {
         const int b = tid / EH, r = tid - b * EH;
         double X0, Y0, W0;
         row_base(p.M, tileX + (b - 1) * BLOCK_W, tileY - HALO + r, X0, Y0, W0);
         s_row[b][r][0] = X0; s_row[b][r][1] = Y0; s_row[b][r][2] = W0;
+    } else if (tid >= 128 && tid < 132) {
+        const int c = tid - 128;
+        const int x0 = (c & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (c & 1) ? HALO - 1 : BLOCK_W - HALO;
+        const int y = (c & 2) ? tileY + TH + HALO - 1 : tileY - HALO;
+        double X0, Y0, W0;
+        row_base(p.M, x0, y, X0, Y0, W0);
+        const double dx1 = (double)x1;
+        int X, Y;
+        quantize(p.M, X0, Y0, W0, dmul(p.M.m[0], dx1), dmul(p.M.m[3], dx1), dmul(p.M.m[6], dx1), X, Y);
+        const double W = p.M.affine ? p.M.m[8] : dadd(W0, dmul(p.M.m[6], dx1));
+        const bool sane = abs(X) < (1 << 30) && abs(Y) < (1 << 30);   // far from cvt saturation
+        s_corner[c][0] = X; s_corner[c][1] = Y; s_corner[c][2] = !sane ? 0 : ((W > 0.0) ? 1 : ((W < 0.0) ? -1 : 0));
+    } else if (tid == 160) {
+        mbar_init(&s_bar, 1);
     }
     __syncthreads();
+
+    // ---- source rectangle of this tile: the quantised corner images bound every pixel of the tile
+    //      (a homography maps the rectangle to a convex quad as long as W keeps its sign) ----------
+    SrcTile T;
+    bool use_smem = false;
+    {
+        const int sg = s_corner[0][2];
+        const bool convex = sg != 0 && s_corner[1][2] == sg && s_corner[2][2] == sg && s_corner[3][2] == sg;
+        int sx_lo = min(min(s_corner[0][0], s_corner[1][0]), min(s_corner[2][0], s_corner[3][0])) >> 5;
+        int sx_hi = max(max(s_corner[0][0], s_corner[1][0]), max(s_corner[2][0], s_corner[3][0])) >> 5;
+        int sy_lo = min(min(s_corner[0][1], s_corner[1][1]), min(s_corner[2][1], s_corner[3][1])) >> 5;
+        int sy_hi = max(max(s_corner[0][1], s_corner[1][1]), max(s_corner[2][1], s_corner[3][1])) >> 5;
+        constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;  // tap reach + 1 px safety ring
+        sx_lo -= LO; sy_lo -= LO; sx_hi += HI; sy_hi += HI;
+        if (convex && (sx_hi < 0 || sy_hi < 0 || sx_lo > p.w - 1 || sy_lo > p.h - 1)) return;  // tile misses the frame
+        sx_lo = max(sx_lo, -2); sy_lo = max(sy_lo, -2); sx_hi = min(sx_hi, p.w + 1); sy_hi = min(sy_hi, p.h + 1);
+        T.s = s_src; T.sy0 = sy_lo;
+        T.bx0 = ((sx_lo * 3) >> 4) << 4;
+        T.rowbytes = ((sx_hi * 3 + 3 - T.bx0) + 15) & ~15;
+        T.R = sy_hi - sy_lo + 1;
+        use_smem = convex && p.src_aligned && T.R > 1 && T.rowbytes > 0 && T.R * T.rowbytes <= p.src_smem_bytes;
+    }
+
+    // ---- stage the canvas tile and the source rectangle: one bulk copy per row (async proxy),
+    //      completion on one mbarrier; the parts of the rectangle outside the frame are zeroed by
+    //      ordinary stores (BORDER_CONSTANT 0), which only happens for tiles on the frame's edge ----
+    {
+        // bytes [c_lo, c_hi) of every staged row come from the frame by bulk copy
+        const int row_end16 = (p.w * 3) & ~15;
+        const int c_lo = use_smem ? max(0, -T.bx0) : 0;
+        const int c_hi = use_smem ? max(c_lo, min(T.rowbytes, row_end16 - T.bx0)) : 0;
+        const int r_lo = use_smem ? max(0, -T.sy0) : 0, r_hi = use_smem ? min(T.R, p.h - T.sy0) : 0;   // rows inside the frame
+        if (warp == 0) {
+            if (c_hi > c_lo)
+                for (int r = r_lo + lane; r < r_hi; r += 32)
+                    bulk_g2s(s_src + r * T.rowbytes + c_lo, p.src + (size_t)(T.sy0 + r) * p.spitch + (T.bx0 + c_lo),
+                             (uint32_t)(c_hi - c_lo), &s_bar);
+        } else if (warp == 1) {
+            const int y = tileY + lane;
+            if (y < p.Hc)
+                bulk_g2s(&s_canvas[lane][0], p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, (uint32_t)nvec * 16u, &s_bar);
+        } else if (tid == 64) {
+            const int nrows_c = min(TH, p.Hc - tileY);
+            const uint32_t tx = (uint32_t)nrows_c * (uint32_t)nvec * 16u +
+                                ((c_hi > c_lo && r_hi > r_lo) ? (uint32_t)(r_hi - r_lo) * (uint32_t)(c_hi - c_lo) : 0u);
+            mbar_arrive_expect_tx(&s_bar, tx);
+        }
+        if (use_smem && (c_lo > 0 || c_hi < T.rowbytes || r_lo > 0 || r_hi < T.R)) {
+            const int row_end = p.w * 3, nch = T.rowbytes >> 4;
+            for (int i = tid; i < T.R * nch; i += NTHREADS) {
+                const int r = i / nch, c = (i - r * nch) << 4;
+                if (r >= r_lo && r < r_hi && c >= c_lo && c < c_hi) continue;   // covered by the bulk copy
+                const int gy = T.sy0 + r, gb = T.bx0 + c;
+                uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                if (gy >= 0 && gy < p.h && gb + 15 >= 0 && gb < row_end) {       // chunk straddles the frame edge
+                    uint8_t *zb = reinterpret_cast<uint8_t *>(&z);
+                    const uint8_t *g = p.src + (size_t)gy * p.spitch;
+#pragma unroll
+                    for (int b = 0; b < 16; ++b)
+                        if (gb + b >= 0 && gb + b < row_end) zb[b] = __ldg(g + gb + b);
+                }
+                *reinterpret_cast<uint4 *>(s_src + r * T.rowbytes + c) = z;
+            }
+        }
+        mbar_wait(&s_bar, 0);
+        __syncthreads();
+    }
 
     // ---- phase 1: warp tile + vertical halo; lanes = consecutive columns -------------------
     {
@@ -122,8 +270,9 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
             float wg = 0.f;
             if (y >= 0 && y < p.Hc && x < p.Wc) {
                 int X, Y;
-                quantize(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
-                px = sample<INTERP, 3>(p.src, p.spitch, p.h, p.w, X, Y, p.cubic);
+                if (use_smem) quantize_fast(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                else quantize(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                px = sample_c3_tile<INTERP>(use_smem, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
                 if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
                 else mv = px ? 255u : 0u;
                 if constexpr (BLEND == MK_BLEND_FEATHER) {
@@ -154,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
             quantize(p.M, s_row[b][r][0], s_row[b][r][1], s_row[b][r][2], dmul(p.M.m[0], dx1), dmul(p.M.m[3], dx1),
                      dmul(p.M.m[6], dx1), X, Y);
             if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
-            else mv = sample<INTERP, 3>(p.src, p.spitch, p.h, p.w, X, Y, p.cubic) ? 255u : 0u;
+            else mv = sample_c3_tile<INTERP>(use_smem, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
         }
         s_side[r][c] = (uint8_t)mv;
         if constexpr (ROI) s_mval[r][(c < 2) ? c : TW + HALO + (c - 2)] = (uint8_t)mv;
@@ -184,7 +333,7 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
             const int r = i / TW, c = i - r * TW;
             const int m = min(min(min((int)s_mh[r][c], (int)s_mh[r + 1][c]), min((int)s_mh[r + 2][c], (int)s_mh[r + 3][c])),
                               (int)s_mh[r + 4][c]);
-            s_mval[r][c] = (uint8_t)m;   // rows r < TH of s_mval are no longer needed as input: s_mh holds them
+            s_mval[r][c] = (uint8_t)m;   // the horizontal pass already consumed s_mval: reuse it for the result
         }
         __syncthreads();
         if (tid < TH) {
@@ -193,10 +342,11 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
             s_v[tid] = bits;
         }
     }
-    cp_async_commit_wait_all();
     __syncthreads();
 
     // ---- phase 2: blend; thread = 4 consecutive pixels = 3 aligned canvas words --------------
+    const bool keep_old = (BLEND == MK_BLEND_ALPHA) && p.alpha == 1.0f && p.beta == 0.0f;   // fmaf(c,1,w*0) == c
+    const bool take_new = (BLEND == MK_BLEND_ALPHA) && p.alpha == 0.0f && p.beta == 1.0f;   // fmaf(c,0,w*1) == w
 #pragma unroll 1
     for (int item = tid; item < TH * (TW / 4); item += NTHREADS) {
         const int r = item >> 4, g = item & 15, y = tileY + r, x = tileX + 4 * g;
@@ -210,6 +360,8 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
         uint32_t px[4] = { c0 & 0xFFFFFFu, (c0 >> 24) | ((c1 & 0xFFFFu) << 8), (c1 >> 16) | ((c2 & 0xFFu) << 16), c2 >> 8 };
         uint32_t *mp = reinterpret_cast<uint32_t *>(p.cmask + (size_t)y * p.mpitch + x);
         uint32_t mk4 = *mp;
+        const uint4 wv4 = *reinterpret_cast<const uint4 *>(&s_warp[r][4 * g]);
+        const uint32_t wv[4] = { wv4.x, wv4.y, wv4.z, wv4.w };
         float4 wa;
         float *wp = nullptr;
         if constexpr (BLEND == MK_BLEND_FEATHER) {
@@ -220,10 +372,10 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (!((mb >> j) & 1u)) continue;
-            const uint32_t wv = s_warp[r][4 * g + j];
             if constexpr (BLEND == MK_BLEND_ALPHA) {
                 const bool old = ((mk4 >> (8 * j)) & 255u) > 1u;
-                px[j] = old ? blend_px(px[j], wv, p.alpha, p.beta) : wv;
+                if (!old || take_new) px[j] = wv[j];
+                else if (!keep_old) px[j] = blend_px_fast(px[j], wv[j], p.alpha, p.beta);
                 if constexpr (ROI) mk4 |= (uint32_t)s_mval[r][4 * g + j] << (8 * j);
                 else mk4 |= 255u << (8 * j);
                 touched = true;
@@ -232,9 +384,9 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
                 if (gw > 0.f) {
                     float *accp = (j == 0) ? &wa.x : (j == 1) ? &wa.y : (j == 2) ? &wa.z : &wa.w;
                     const float acc = *accp, s = __fadd_rn(acc, gw);
-                    px[j] = feather_u8(px[j] & 255u, wv & 255u, acc, gw, s) |
-                            (feather_u8((px[j] >> 8) & 255u, (wv >> 8) & 255u, acc, gw, s) << 8) |
-                            (feather_u8((px[j] >> 16) & 255u, (wv >> 16) & 255u, acc, gw, s) << 16);
+                    px[j] = feather_u8(px[j] & 255u, wv[j] & 255u, acc, gw, s) |
+                            (feather_u8((px[j] >> 8) & 255u, (wv[j] >> 8) & 255u, acc, gw, s) << 8) |
+                            (feather_u8((px[j] >> 16) & 255u, (wv[j] >> 16) & 255u, acc, gw, s) << 16);
                     *accp = s;
                     mk4 |= 255u << (8 * j);
                     touched = true;
@@ -249,14 +401,15 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
             if constexpr (BLEND == MK_BLEND_FEATHER) *reinterpret_cast<float4 *>(wp) = wa;
         }
     }
+    fence_proxy_async();   // make the generic-proxy writes to s_canvas visible to the bulk store engine
     __syncthreads();
 
-    // ---- write back the rows that changed, as whole 16-byte vectors ---------------------------
-    for (int v = tid; v < TH * ROWV; v += NTHREADS) {
-        const int r = v / ROWV, c = v - r * ROWV, y = tileY + r;
-        if (y < p.Hc && c < nvec && s_v[r] != 0ull)
-            *reinterpret_cast<uint4 *>(p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3 + c * 16) =
-                *reinterpret_cast<const uint4 *>(&s_canvas[r][c * 16]);
+    // ---- write back the rows that changed: one bulk store per row ------------------------------
+    if (warp == 0) {
+        const int y = tileY + lane;
+        if (y < p.Hc && s_v[lane] != 0ull)
+            bulk_s2g(p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, &s_canvas[lane][0], (uint32_t)nvec * 16u);
+        bulk_commit_wait_read();
     }
 }
 
@@ -390,26 +543,48 @@ static void build_cubic_table(short *tab)
         }
 }
 
-static const short *cubic_table_device(int *status)
+// Bilinear weight LUT for lerp3_dp4a: entry [ay*32+ax] = (hi bytes, lo bytes) of the four integer
+// weights (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax*ay split as w = hi*32 + lo.
+static void build_lerp_lut(uint2 *lut)
 {
-    // one table per device, created on first use (read-only afterwards)
-    static std::mutex mu;
-    static short *tabs[64] = { nullptr };
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *status = MK_ERR_CUDA; return nullptr; }
-    std::lock_guard<std::mutex> lk(mu);
-    if (!tabs[dev]) {
-        short host[1024 * 16];
-        build_cubic_table(host);
-        short *d = nullptr;
-        if (cudaMalloc(&d, sizeof host) != cudaSuccess || cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice) != cudaSuccess) {
-            *status = cuda_fail(cudaGetLastError(), "cubic table upload");
-            return nullptr;
+    for (int ay = 0; ay < 32; ++ay)
+        for (int ax = 0; ax < 32; ++ax) {
+            const int w[4] = { (32 - ax) * (32 - ay), ax * (32 - ay), (32 - ax) * ay, ax * ay };
+            uint32_t hi = 0, lo = 0;
+            for (int k = 0; k < 4; ++k) { hi |= (uint32_t)(w[k] >> 5) << (8 * k); lo |= (uint32_t)(w[k] & 31) << (8 * k); }
+            lut[ay * 32 + ax] = make_uint2(hi, lo);
         }
-        tabs[dev] = d;
+}
+
+struct DeviceTables {
+    const short *cubic;
+    const uint2 *lut;
+};
+
+// read-only tables, one copy per device, created on first use
+static int device_tables(DeviceTables &out)
+{
+    static std::mutex mu;
+    static DeviceTables tabs[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tabs[dev].cubic) {
+        static short host_cubic[1024 * 16];
+        static uint2 host_lut[1024];
+        build_cubic_table(host_cubic);
+        build_lerp_lut(host_lut);
+        short *dc = nullptr;
+        uint2 *dl = nullptr;
+        cudaError_t e = cudaMalloc(&dc, sizeof host_cubic);
+        if (e == cudaSuccess) e = cudaMalloc(&dl, sizeof host_lut);
+        if (e == cudaSuccess) e = cudaMemcpy(dc, host_cubic, sizeof host_cubic, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dl, host_lut, sizeof host_lut, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "interpolation table upload");
+        tabs[dev].cubic = dc; tabs[dev].lut = dl;
     }
-    *status = MK_OK;
-    return tabs[dev];
+    out = tabs[dev];
+    return MK_OK;
 }
 
 // Canvas rectangle that can receive a non-zero warped pixel: forward-map the source rectangle grown
@@ -444,11 +619,67 @@ static void footprint(int Hc, int Wc, int h, int w, const double *H, int interp,
     if (rect[2] <= rect[0] || rect[3] <= rect[1]) { rect[0] = rect[1] = rect[2] = rect[3] = 0; }
 }
 
-template <int INTERP, int BLEND>
-static void launch_mapper(bool roi, dim3 grid, cudaStream_t st, const MapperParams &P)
+constexpr int MAX_SRC_SMEM = 96 * 1024;
+
+template <int INTERP, int BLEND, bool ROI>
+static cudaError_t launch_mapper_inst(dim3 grid, cudaStream_t st, const MapperParams &P)
 {
-    if (roi) mapper_update_kernel<INTERP, BLEND, true><<<grid, NTHREADS, 0, st>>>(P);
-    else mapper_update_kernel<INTERP, BLEND, false><<<grid, NTHREADS, 0, st>>>(P);
+    static std::atomic<int> configured{-1};  // device the attribute was last set on
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured.load(std::memory_order_acquire) != dev) {
+        cudaError_t e = cudaFuncSetAttribute(mapper_update_kernel<INTERP, BLEND, ROI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SRC_SMEM);
+        if (e != cudaSuccess) return e;
+        configured.store(dev, std::memory_order_release);
+    }
+    mapper_update_kernel<INTERP, BLEND, ROI><<<grid, NTHREADS, (size_t)P.src_smem_bytes, st>>>(P);
+    return cudaSuccess;
+}
+
+template <int INTERP, int BLEND>
+static cudaError_t launch_mapper(bool roi, dim3 grid, cudaStream_t st, const MapperParams &P)
+{
+    if constexpr (BLEND == MK_BLEND_ALPHA) {
+        if (roi) return launch_mapper_inst<INTERP, BLEND, true>(grid, st, P);
+    }
+    return launch_mapper_inst<INTERP, BLEND, false>(grid, st, P);
+}
+
+// Shared memory needed to stage the source rectangle of one haloed tile: evaluated (in plain double
+// math) for tiles at the corners and the centre of the visited region; each CTA re-derives its own
+// exact rectangle and falls back to global-memory sampling if it does not fit.
+static int estimate_src_smem(const InvMap &M, const int32_t *rect, int interp)
+{
+    const int lohi = (interp == MK_INTER_CUBIC) ? 5 : 3;
+    const double txs[3] = { (double)(rect[0] / TW * TW), (double)((rect[0] + rect[2]) / 2 / TW * TW), (double)((rect[2] - 1) / TW * TW) };
+    const double tys[3] = { (double)(rect[1] / TH * TH), (double)((rect[1] + rect[3]) / 2 / TH * TH), (double)((rect[3] - 1) / TH * TH) };
+    long need = 0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double minu = 1e300, maxu = -1e300, minv = 1e300, maxv = -1e300;
+            bool ok = true;
+            int sign = 0;
+            for (int c = 0; c < 4 && ok; ++c) {
+                const double x = txs[a] + ((c & 1) ? TW + HALO - 1 : -HALO), y = tys[b] + ((c & 2) ? TH + HALO - 1 : -HALO);
+                const double W = M.m[6] * x + M.m[7] * y + M.m[8];
+                const int sg = (W > 0) - (W < 0);
+                if (sg == 0 || (sign && sg != sign)) { ok = false; break; }
+                sign = sg;
+                const double u = (M.m[0] * x + M.m[1] * y + M.m[2]) / W, v = (M.m[3] * x + M.m[4] * y + M.m[5]) / W;
+                if (!isfinite(u) || !isfinite(v)) { ok = false; break; }
+                minu = fmin(minu, u); maxu = fmax(maxu, u); minv = fmin(minv, v); maxv = fmax(maxv, v);
+            }
+            if (!ok) continue;
+            const double rows = ceil(maxv - minv) + 2 + lohi, cols = ceil(maxu - minu) + 2 + lohi;
+            if (rows > 4096 || cols > 4096) continue;
+            const long rowbytes = (((long)cols * 3 + 15 + 15) / 16) * 16;
+            const long bytes = (long)rows * rowbytes;
+            if (bytes > need) need = bytes;
+        }
+    need += need / 16;  // slack for tiles between the probes (perspective)
+    need = (need + 1023) / 1024 * 1024;
+    return need > MAX_SRC_SMEM ? 0 : (int)need;
 }
 
 }  // namespace mk
@@ -503,27 +734,32 @@ extern "C" int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *c
     if (rect[2] <= rect[0]) return MK_OK;  // footprint misses the canvas: nothing to do
 
     MapperParams P;
-    P.canvas = canvas; P.cmask = cmask; P.wacc = wacc; P.src = src; P.roi = roi; P.cubic = nullptr;
+    P.canvas = canvas; P.cmask = cmask; P.wacc = wacc; P.src = src; P.roi = roi; P.cubic = nullptr; P.lut = nullptr;
     P.cpitch = canvas_pitch; P.mpitch = cmask_pitch; P.wpitch = wacc_pitch; P.spitch = src_pitch; P.rpitch = roi_pitch;
     P.Hc = canvas_h; P.Wc = canvas_w; P.h = src_h; P.w = src_w;
     make_invmap(H_host, P.M);
     P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp;
-    if (interp == MK_INTER_CUBIC) {
-        int st = MK_OK;
-        P.cubic = cubic_table_device(&st);
-        if (!P.cubic) return st;
+    {
+        DeviceTables tb;
+        const int st = device_tables(tb);
+        if (st != MK_OK) return st;
+        P.cubic = tb.cubic; P.lut = tb.lut;
     }
     P.tx0 = rect[0] / TW; P.ty0 = rect[1] / TH;
     const int tx1 = (rect[2] + TW - 1) / TW, ty1 = (rect[3] + TH - 1) / TH;
     dim3 grid(tx1 - P.tx0, ty1 - P.ty0);
+    P.src_aligned = (aligned(src, 16) && (src_pitch & 15) == 0) ? 1 : 0;
+    P.src_smem_bytes = P.src_aligned ? estimate_src_smem(P.M, rect, interp) : 0;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t le;
     if (interp == MK_INTER_LINEAR) {
-        if (blend == MK_BLEND_ALPHA) launch_mapper<MK_INTER_LINEAR, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
-        else launch_mapper<MK_INTER_LINEAR, MK_BLEND_FEATHER>(false, grid, st, P);
+        if (blend == MK_BLEND_ALPHA) le = launch_mapper<MK_INTER_LINEAR, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
+        else le = launch_mapper<MK_INTER_LINEAR, MK_BLEND_FEATHER>(false, grid, st, P);
     } else {
-        if (blend == MK_BLEND_ALPHA) launch_mapper<MK_INTER_CUBIC, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
-        else launch_mapper<MK_INTER_CUBIC, MK_BLEND_FEATHER>(false, grid, st, P);
+        if (blend == MK_BLEND_ALPHA) le = launch_mapper<MK_INTER_CUBIC, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
+        else le = launch_mapper<MK_INTER_CUBIC, MK_BLEND_FEATHER>(false, grid, st, P);
     }
+    if (le != cudaSuccess) return cuda_fail(le, "cudaFuncSetAttribute(mapper_update_kernel)");
     MK_LAUNCH_CHECK("mapper_update_kernel");
     return MK_OK;
 }
@@ -547,10 +783,11 @@ extern "C" int mk_warp_perspective_u8(const uint8_t *src, int src_h, int src_w, 
     P.src = src; P.dst = dst; P.cubic = nullptr; P.spitch = src_pitch; P.dpitch = dst_pitch;
     P.h = src_h; P.w = src_w; P.Hd = dst_h; P.Wd = dst_w;
     make_invmap(H_host, P.M);
-    if (interp == MK_INTER_CUBIC) {
-        int st = MK_OK;
-        P.cubic = cubic_table_device(&st);
-        if (!P.cubic) return st;
+    {
+        DeviceTables tb;
+        const int st = device_tables(tb);
+        if (st != MK_OK) return st;
+        P.cubic = tb.cubic;
     }
     dim3 grid((dst_w + TW - 1) / TW, (dst_h + TH - 1) / TH);
     cudaStream_t st = (cudaStream_t)stream;

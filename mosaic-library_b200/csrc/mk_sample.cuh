@@ -51,6 +51,26 @@ __device__ __forceinline__ void quantize(const InvMap &M, double X0, double Y0, 
     Y = __double2int_rn(dmul(dadd(Y0, my), W));
 }
 
+// Same as quantize() for |value| < 2^31 (guaranteed by the caller: the tile corners bound every
+// pixel of the tile and were checked to be far from saturation): adding 1.5 * 2^52 rounds to the
+// nearest-even integer exactly like cvt.rni.s32.f64, but runs on the FP64 pipe instead of the
+// 16-lane conversion unit.
+__device__ __forceinline__ int round_magic(double v) { return __double2loint(__dadd_rn(v, 6755399441055744.0)); }
+
+__device__ __forceinline__ void quantize_fast(const InvMap &M, double X0, double Y0, double W0, double mx, double my,
+                                              double mw, int &X, int &Y)
+{
+    double W;
+    if (M.affine) {
+        W = M.wr;
+    } else {
+        W = dadd(W0, mw);
+        W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+    }
+    X = round_magic(dmul(dadd(X0, mx), W));
+    Y = round_magic(dmul(dadd(Y0, my), W));
+}
+
 __device__ __forceinline__ uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
 
 // ------------------------------------------------------------------------------------------
@@ -182,6 +202,106 @@ __device__ __forceinline__ uint32_t sample_cubic_c1(const uint8_t *__restrict__ 
         for (int kx = 0; kx < 4; ++kx)
             acc += (int)tap1(src, pitch, h, w, sy - 1 + ky, sx - 1 + kx) * (int)wt[ky * 4 + kx];
     return (uint32_t)clamp_u8((acc + (1 << 14)) >> 15);
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory samplers.  The CTA has staged the source rectangle rows [sy0, sy0+R) x bytes
+// [bx0, bx0+rowbytes) (bx0 % 16 == 0) with zero fill outside the image, so border taps need no
+// predicates.  A tap set that does not lie inside the staged rectangle (never expected: the
+// rectangle is the quantised image of the tile corners plus a safety ring) returns false and the
+// caller falls back to the global-memory sampler, so exactness never depends on the estimate.
+// ------------------------------------------------------------------------------------------
+struct SrcTile {
+    const uint8_t *s;   // shared memory
+    int sy0, bx0, R, rowbytes;
+};
+
+// Bilinear weights as two byte-packed words (taps p00, p01, p10, p11): w = hi * 32 + lo, so that
+//   sum(v * w) + 512 = dp4a(V, hi) * 32 + dp4a(V, lo, 512)      (exact integer identity)
+// lut[ay * 32 + ax] = (hi, lo).  Filled on the host (mk_mapper.cu).
+__device__ __forceinline__ uint32_t lerp3_dp4a(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint2 wt)
+{
+    // alo = [B0 G0 R0 B1], ahi = [G1 R1 . .] (row sy), blo / bhi the same for row sy + 1
+    const uint32_t vb = __byte_perm(alo, blo, 0x7430);          // B0 B1 B0' B1'
+    const uint32_t ra = __byte_perm(alo, ahi, 0x5241);          // G0 G1 R0 R1
+    const uint32_t rb = __byte_perm(blo, bhi, 0x5241);          // G0' G1' R0' R1'
+    const uint32_t vg = __byte_perm(ra, rb, 0x5410);            // G0 G1 G0' G1'
+    const uint32_t vr = __byte_perm(ra, rb, 0x7632);            // R0 R1 R0' R1'
+    const uint32_t b = (__dp4a(vb, wt.x, 0u) * 32u + __dp4a(vb, wt.y, 512u)) >> 10;
+    const uint32_t g = (__dp4a(vg, wt.x, 0u) * 32u + __dp4a(vg, wt.y, 512u)) >> 10;
+    const uint32_t r = (__dp4a(vr, wt.x, 0u) * 32u + __dp4a(vr, wt.y, 512u)) >> 10;
+    return b | (g << 8) | (r << 16);
+}
+
+__device__ __forceinline__ bool sample_linear_c3_smem_lut(const SrcTile &T, int X, int Y, const uint2 *__restrict__ lut,
+                                                          uint32_t &out)
+{
+    const int r = (Y >> 5) - T.sy0, cb = (X >> 5) * 3 - T.bx0;
+    if ((unsigned)r >= (unsigned)(T.R - 1) || cb < 0 || cb + 12 > T.rowbytes) return false;
+    const uint2 wt = __ldg(lut + ((Y & 31) * 32 + (X & 31)));
+    const uint32_t *q0 = reinterpret_cast<const uint32_t *>(T.s + r * T.rowbytes + (cb & ~3));
+    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
+    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
+    out = lerp3_dp4a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
+                     __funnelshift_r(b1, b2, sh), wt);
+    return true;
+}
+
+__device__ __forceinline__ bool sample_linear_c3_smem(const SrcTile &T, int X, int Y, uint32_t &out)
+{
+    const int ax = X & 31, ay = Y & 31;
+    const int r = (Y >> 5) - T.sy0, cb = (X >> 5) * 3 - T.bx0;
+    if ((unsigned)r >= (unsigned)(T.R - 1) || cb < 0 || cb + 12 > T.rowbytes) return false;
+    const uint32_t *q0 = reinterpret_cast<const uint32_t *>(T.s + r * T.rowbytes + (cb & ~3));
+    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
+    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
+    const uint32_t alo = __funnelshift_r(a0, a1, sh), ahi = __funnelshift_r(a1, a2, sh);
+    const uint32_t blo = __funnelshift_r(b0, b1, sh), bhi = __funnelshift_r(b1, b2, sh);
+    out = lerp3(alo & 0xFFFFFFu, (alo >> 24) | ((ahi & 0xFFFFu) << 8), blo & 0xFFFFFFu, (blo >> 24) | ((bhi & 0xFFFFu) << 8),
+                ax, ay);
+    return true;
+}
+
+__device__ __forceinline__ bool sample_cubic_c3_smem(const SrcTile &T, int X, int Y, const short *__restrict__ tab,
+                                                     uint32_t &out)
+{
+    const int ax = X & 31, ay = Y & 31;
+    const int r = (Y >> 5) - 1 - T.sy0, cb = ((X >> 5) - 1) * 3 - T.bx0;
+    if (r < 0 || r + 3 >= T.R || cb < 0 || cb + 16 > T.rowbytes) return false;
+    const short *wt = tab + (ay * 32 + ax) * 16;
+    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint8_t *base = T.s + r * T.rowbytes + (cb & ~3);
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(base + ky * T.rowbytes);
+        const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
+        const uint32_t d0 = __funnelshift_r(r0, r1, sh), d1 = __funnelshift_r(r1, r2, sh), d2 = __funnelshift_r(r2, r3, sh);
+        const int w0 = wt[ky * 4 + 0], w1 = wt[ky * 4 + 1], w2 = wt[ky * 4 + 2], w3 = wt[ky * 4 + 3];
+        acc0 += (int)(d0 & 255u) * w0 + (int)(d0 >> 24) * w1 + (int)((d1 >> 16) & 255u) * w2 + (int)((d2 >> 8) & 255u) * w3;
+        acc1 += (int)((d0 >> 8) & 255u) * w0 + (int)(d1 & 255u) * w1 + (int)(d1 >> 24) * w2 + (int)((d2 >> 16) & 255u) * w3;
+        acc2 += (int)((d0 >> 16) & 255u) * w0 + (int)((d1 >> 8) & 255u) * w1 + (int)(d2 & 255u) * w2 + (int)(d2 >> 24) * w3;
+    }
+    out = (uint32_t)clamp_u8((acc0 + (1 << 14)) >> 15) | ((uint32_t)clamp_u8((acc1 + (1 << 14)) >> 15) << 8) |
+          ((uint32_t)clamp_u8((acc2 + (1 << 14)) >> 15) << 16);
+    return true;
+}
+
+template <int INTERP>
+__device__ __forceinline__ uint32_t sample_c3_tile(bool use_smem, const SrcTile &T, const uint8_t *__restrict__ src,
+                                                   size_t pitch, int h, int w, int X, int Y, const short *__restrict__ tab,
+                                                   const uint2 *__restrict__ lut)
+{
+    uint32_t out;
+    if (use_smem) {
+        if constexpr (INTERP == 1) { if (sample_linear_c3_smem_lut(T, X, Y, lut, out)) return out; }
+        else { if (sample_cubic_c3_smem(T, X, Y, tab, out)) return out; }
+        // outside the staged rectangle: if it is also outside the tap reach of the image the value is 0
+    }
+    if constexpr (INTERP == 1) return sample_linear_c3(src, pitch, h, w, X, Y);
+    else return sample_cubic_c3(src, pitch, h, w, X, Y, tab);
 }
 
 template <int INTERP, int CN>

@@ -1,0 +1,155 @@
+"""Tile-sharded mosaic canvas over the GPUs of one box (one process per GPU, torch.distributed).
+
+Mirrors how the reference decomposes a large mosaic: SequentialMosaic._create_tile_graph cuts the
+canvas into a regular grid of tiles (src/mosaicking/mosaic.py:595-604), a frame is assigned to every
+tile its warped corner quad overlaps (get_corners + registration.bbox_overlap on int-truncated
+corners, mosaic.py:612-614), each tile is rendered by its own Mapper with the tile-local homography
+H_tile = T(-tx, -ty) @ H (mosaic.py:617), and examples/combine_tiles.py:46-62 pastes the tiles back
+together.  Tiles never read each other, so the path shards with NO data-path collective between
+tiles; every tile is eroded independently exactly like the reference's per-tile Mapper, hence no
+seam (halo) exchange is needed for reference-tile semantics.
+
+What does cross GPUs:
+  * the per-frame homographies: all_gather of 9 doubles per rank and step, so that every rank can
+    derive the same routing table;
+  * the frames themselves, only towards the ranks that own a tile the footprint overlaps
+    (batched isend / irecv = ncclSend / ncclRecv over NVLink);
+  * the final tile gather (= combine_tiles).
+Each rank ingests its own frame stream ("camera"), so per-GPU work is constant as ranks are added.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .mosaic import bbox_overlap, combine_tiles, get_corners, homogeneous_translation
+
+
+def tiles_of_footprint(H: np.ndarray, width: int, height: int, tile_size: tuple[int, int], grid: tuple[int, int]):
+    """Tiles (xi, yi) of a grid[0] x grid[1] tile grid that the warped frame overlaps -- the test of
+    mosaic.py:612-614 restricted to the tiles the corner bounding box can reach."""
+    crn = get_corners(H, width, height).squeeze().astype(int)
+    tw, th = tile_size
+    # one extra tile on each side: closed polygons that merely touch a tile edge still intersect it
+    x0 = max(0, int(np.floor(crn[:, 0].min() / tw)) - 1); x1 = min(grid[0] - 1, int(np.floor(crn[:, 0].max() / tw)) + 1)
+    y0 = max(0, int(np.floor(crn[:, 1].min() / th)) - 1); y1 = min(grid[1] - 1, int(np.floor(crn[:, 1].max() / th)) + 1)
+    out = []
+    for xi in range(x0, x1 + 1):
+        for yi in range(y0, y1 + 1):
+            tx, ty = xi * tw, yi * th
+            tile_crns = np.array([[tx, ty], [tx + tw, ty], [tx + tw, ty + th], [tx, ty + th]], dtype=int)
+            if bbox_overlap(tile_crns, crn):
+                out.append((xi, yi))
+    return out
+
+
+class ShardedMosaic:
+    """Canvas of grid[0] x grid[1] tiles, tile (xi, yi) owned by rank (yi * grid[0] + xi) % world.
+
+    mapper_factory(tile_w, tile_h) builds the per-tile compositor: mosaicking_b200.Mapper on the GPU
+    path; the CPU tests inject an oracle-backed stand-in and run this class over gloo."""
+
+    def __init__(self, grid: tuple[int, int], tile_size: tuple[int, int], mapper_factory: Callable, frame_shape: tuple[int, int],
+                 device, rank: int | None = None, world: int | None = None):
+        self.grid, self.tile_size = grid, tile_size
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.device = device
+        self.h, self.w = frame_shape
+        self._factory = mapper_factory
+        self.mappers: dict[tuple[int, int], object] = {}
+        self._recv = {}          # source rank -> receive buffer
+        self.frames_applied = 0
+        self.bytes_sent = 0
+
+    def owner(self, tile: tuple[int, int]) -> int:
+        return (tile[1] * self.grid[0] + tile[0]) % self.world
+
+    def owned_tiles(self) -> list[tuple[int, int]]:
+        return [(xi, yi) for yi in range(self.grid[1]) for xi in range(self.grid[0]) if self.owner((xi, yi)) == self.rank]
+
+    def _mapper(self, tile):
+        if tile not in self.mappers:
+            self.mappers[tile] = self._factory(*self.tile_size)
+        return self.mappers[tile]
+
+    def routing(self, H_all: Sequence[np.ndarray]):
+        """-> per source rank: {owner rank: [tiles]} for the frame of that source."""
+        table = []
+        for s, H in enumerate(H_all):
+            dests: dict[int, list] = {}
+            if H is not None:
+                for tile in tiles_of_footprint(H, self.w, self.h, self.tile_size, self.grid):
+                    dests.setdefault(self.owner(tile), []).append(tile)
+            table.append(dests)
+        return table
+
+    def exchange_homographies(self, H: np.ndarray | None) -> list:
+        """all_gather of the 9 doubles of every rank's current frame (NaN = no frame this step)."""
+        mine = torch.full((9,), float("nan"), dtype=torch.float64)
+        if H is not None:
+            mine = torch.from_numpy(np.ascontiguousarray(np.asarray(H, np.float64).reshape(9)))
+        if self.world == 1:
+            return [None if H is None else np.asarray(H, np.float64).reshape(3, 3)]
+        mine = mine.to(self.device)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine)
+        allH = torch.stack(out).cpu().numpy()
+        return [None if np.isnan(a[0]) else a.reshape(3, 3) for a in allH]
+
+    def step(self, frame: torch.Tensor | None, H: np.ndarray | None, H_all: Sequence | None = None) -> int:
+        """One step: this rank contributes `frame` [h, w, 3] uint8 (already on self.device) with absolute
+        homography H (frame -> global canvas).  Frames are applied tile by tile in source-rank order so
+        that every tile sees the same sequence on every run.  Returns the number of tile updates done."""
+        if H_all is None:
+            H_all = self.exchange_homographies(H)
+        table = self.routing(H_all)
+        ops, incoming = [], {}
+        if self.world > 1:
+            for s, dests in enumerate(table):
+                if s == self.rank:
+                    for d in dests:
+                        if d != self.rank:
+                            ops.append(dist.P2POp(dist.isend, frame, d))
+                            self.bytes_sent += frame.numel()
+                elif self.rank in dests:
+                    buf = self._recv.get(s)
+                    if buf is None:
+                        buf = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device)
+                        self._recv[s] = buf
+                    incoming[s] = buf
+                    ops.append(dist.P2POp(dist.irecv, buf, s))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+        done = 0
+        for s, dests in enumerate(table):
+            if self.rank not in dests:
+                continue
+            src = frame if s == self.rank else incoming[s]
+            for (xi, yi) in dests[self.rank]:
+                H_tile = homogeneous_translation(-xi * self.tile_size[0], -yi * self.tile_size[1]) @ H_all[s]   # mosaic.py:617
+                self._mapper((xi, yi)).update_device(src, H_tile)
+                done += 1
+        self.frames_applied += done
+        return done
+
+    def gather(self, dst: int = 0) -> np.ndarray | None:
+        """combine_tiles (examples/combine_tiles.py:46-62): every tile travels to rank `dst`, which
+        pastes tile (x, y) at (x*tile_w, y*tile_h).  Tiles nobody touched stay black, like missing PNGs."""
+        local = {t: m.output for t, m in self.mappers.items()}
+        if self.world == 1:
+            tiles = local
+        else:
+            box = [None] * self.world if self.rank == dst else None
+            dist.gather_object(local, box, dst=dst)
+            if self.rank != dst:
+                return None
+            tiles = {}
+            for part in box:
+                tiles.update(part)
+        tiles.setdefault((self.grid[0] - 1, self.grid[1] - 1), np.zeros((self.tile_size[1], self.tile_size[0], 3), np.uint8))
+        return combine_tiles(tiles, self.tile_size)

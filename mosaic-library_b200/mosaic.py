@@ -71,8 +71,11 @@ class Mapper:
         self._lib = _lib.lib()
         self._width, self._height = int(output_width), int(output_height)
         self._canvas, self._canvas_mask, self._wacc = self._create_canvas(self._width, self._height)
-        self._stage = None      # device staging buffer for host frames
-        self._stage_roi = None
+        # host frames are uploaded on a side stream into a small ring of staging buffers so that the
+        # H2D copy of frame k+1 overlaps the kernel of frame k
+        self._copy_stream = torch.cuda.Stream(device=self._device)
+        self._slots = [{"buf": None, "roi": None, "free": None} for _ in range(3)]
+        self._slot = 0
         self._flag = True
         self.last_region = (0, 0, 0, 0)
 
@@ -95,36 +98,60 @@ class Mapper:
         hull = _cv2.convexHull(np.array(keypoints).astype(np.int32))
         return _cv2.fillConvexPoly(mask, hull, 255)
 
-    def _to_device(self, image, slot: str, channels: int) -> tuple[torch.Tensor, int, int]:
-        """Host ndarray / tensor [h, w(, c)] -> pitched device buffer; returns (buffer, h, w)."""
-        if isinstance(image, torch.Tensor):
-            t = image
-        else:
-            t = torch.from_numpy(np.ascontiguousarray(image))
+    @staticmethod
+    def _as_rows(image, channels: int) -> tuple[torch.Tensor, int, int]:
+        t = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(image))
         if t.dtype != torch.uint8:
             raise TypeError("Mapper.update needs uint8 images")
         h, w = int(t.shape[0]), int(t.shape[1])
-        row = w * channels
-        t2 = t.reshape(h, row)
-        if t2.is_cuda and t2.stride(0) % 4 == 0 and t2.stride(1) == 1 and t2.data_ptr() % 4 == 0:
-            return t2, h, w
+        return t.reshape(h, w * channels), h, w
+
+    @staticmethod
+    def _usable_in_place(t2: torch.Tensor) -> bool:
+        return t2.is_cuda and t2.stride(1) == 1 and t2.stride(0) % 4 == 0 and t2.data_ptr() % 4 == 0
+
+    def _stage_upload(self, slot: dict, key: str, t2: torch.Tensor) -> torch.Tensor:
+        """Copy rows into the slot's pitched device buffer on the copy stream."""
+        h, row = int(t2.shape[0]), int(t2.shape[1])
         pitch = _round_up(row, 128)
-        buf = getattr(self, slot)
+        buf = slot[key]
         if buf is None or buf.shape[0] < h or buf.shape[1] != pitch:
             buf = torch.empty((h, pitch), dtype=torch.uint8, device=self._device)
-            setattr(self, slot, buf)
+            slot[key] = buf
         buf[:h, :row].copy_(t2, non_blocking=True)
-        return buf, h, w
+        return buf
 
     def update_device(self, frame: torch.Tensor, H: np.ndarray, roi: torch.Tensor | None = None) -> None:
-        """One fused update with a frame that already lives in HBM: uint8 [h, w, 3] (row stride a
-        multiple of 4 bytes).  `roi` is an optional uint8 [h, w] keypoint-hull mask on the device."""
-        buf, h, w = self._to_device(frame, "_stage", 3)
-        rbuf = None
+        """One fused update with a frame that already lives in HBM: uint8 [h, w, 3].  Rows are used in
+        place when their stride is a multiple of 4 bytes (16 for the bulk-copy fast path).  `roi` is an
+        optional uint8 [h, w] keypoint-hull mask on the device."""
+        self._update_any(frame, H, roi)
+
+    def _update_any(self, image, H, roi) -> None:
+        t2, h, w = self._as_rows(image, 3)
+        r2 = None
         if roi is not None:
-            rbuf, rh, rw = self._to_device(roi, "_stage_roi", 1)
+            r2, rh, rw = self._as_rows(roi, 1)
             assert (rh, rw) == (h, w)
+        cur = torch.cuda.current_stream(self._device)
+        if self._usable_in_place(t2) and (r2 is None or self._usable_in_place(r2)):
+            self._launch(t2, h, w, r2, H)
+            return
+        slot = self._slots[self._slot]
+        self._slot = (self._slot + 1) % len(self._slots)
+        cs = self._copy_stream
+        if slot["free"] is not None:
+            cs.wait_event(slot["free"])          # the kernel that last read this slot has finished
+        if t2.is_cuda:
+            cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            buf = self._stage_upload(slot, "buf", t2)
+            rbuf = self._stage_upload(slot, "roi", r2) if r2 is not None else None
+        cur.wait_stream(cs)
         self._launch(buf, h, w, rbuf, H)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        slot["free"] = ev
 
     def _launch(self, buf, h, w, rbuf, H) -> None:
         Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
@@ -150,12 +177,11 @@ class Mapper:
             mask = self._create_keypoint_mask(keypoints, (width, height))
         if isinstance(image, np.ndarray):
             image = make_bgr_host(image)
-        buf, h, w = self._to_device(image, "_stage", 3)
-        rbuf = self._to_device(mask, "_stage_roi", 1)[0] if mask is not None else None
-        self._launch(buf, h, w, rbuf, H)
+        self._update_any(image, H, mask)
 
     def release(self):
-        self._canvas = self._canvas_mask = self._wacc = self._stage = self._stage_roi = None
+        self._canvas = self._canvas_mask = self._wacc = None
+        self._slots = [{"buf": None, "roi": None, "free": None} for _ in range(3)]
 
     @property
     def output(self) -> np.ndarray:
