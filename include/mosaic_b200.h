@@ -75,9 +75,13 @@ uint64_t mk_launch_count(void);
  *             sqrtf of the squared L2 sum); FLT_MAX where idx = -1.
  *   keep      uint8 [nq] ratio-test flag (may be NULL); ratio <= 0 disables the test (keep=0).
  *   n_keep    int32 [1] device counter of kept rows (may be NULL); overwritten.
- *   workspace scratch of at least mk_knn2_workspace_bytes(..) bytes, 16-byte aligned.
+ *   workspace scratch of at least mk_knn2_workspace_bytes(..) bytes, 256-byte aligned.
  * ------------------------------------------------------------------------------------- */
 size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim);
+/* 1 if mk_knn2 routes this problem through the tcgen05 / TMA descriptor GEMM (L2 norms, dim <= 128 and
+ * enough pairs to amortise the extra launches; float rows must also turn out to be integer-valued in
+ * [0,255] -- OpenCV SIFT is -- otherwise the bit-exact SIMT kernel runs, decided on the device). */
+int mk_knn2_uses_tensor_cores(int norm, int nq, int nt, int dim);
 
 int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t row_stride,
             int32_t *idx, float *dist, double ratio, uint8_t *keep, int32_t *n_keep,

@@ -21,7 +21,7 @@ BLEND_ALPHA, BLEND_FEATHER = 0, 1
 
 EXPORTS = (
     "mk_abi_version", "mk_version_string", "mk_last_error", "mk_launch_count",
-    "mk_knn2_workspace_bytes", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
+    "mk_knn2_workspace_bytes", "mk_knn2_uses_tensor_cores", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_footprint",
 )
 
@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
     L.mk_launch_count.restype = C.c_uint64
     L.mk_knn2_workspace_bytes.restype = sz
     L.mk_knn2_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.mk_knn2_uses_tensor_cores.restype = i32
+    L.mk_knn2_uses_tensor_cores.argtypes = [i32, i32, i32, i32]
     L.mk_knn2_batched_workspace_bytes.restype = sz
     L.mk_knn2_batched_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.mk_knn2.restype = i32

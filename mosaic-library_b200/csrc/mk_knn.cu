@@ -42,7 +42,14 @@ struct KnnParams {
     uint8_t *keep;
     int32_t *n_keep;
     double ratio;
+    const int *guard;   // if non-null the kernel only runs when *guard != 0 (SIMT fallback of the tensor-core path)
 };
+
+// tensor-core path (mk_knn_tc.cu)
+size_t knn_tc_workspace_bytes(int nq, int nt, int dim);
+bool knn_tc_supported(int norm, int nq, int nt, int dim);
+int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, int32_t *idx, float *dist, double ratio,
+               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out);
 
 struct Problem {
     const uint8_t *q, *t;
@@ -201,6 +208,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_reg_kernel(const __grid_cons
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int z = blockIdx.z, qblk = blockIdx.x;
+    if (p.guard && *p.guard == 0) return;
     const Problem pr = load_problem(p, z);
     if (qblk * QB >= pr.nq) return;
     const int qi = qblk * QB + lane;
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_f32_kernel(const __grid_cons
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int z = blockIdx.z, qblk = blockIdx.x;
+    if (p.guard && *p.guard == 0) return;
     const Problem pr = load_problem(p, z);
     if (qblk * FT >= pr.nq) return;
     const int q0 = qblk * FT;
@@ -422,7 +431,7 @@ static void launch_reg(dim3 grid, cudaStream_t st, const KnnParams &P)
 }
 
 static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, void *workspace, size_t workspace_bytes,
-                   cudaStream_t st)
+                   cudaStream_t st, bool zero_n_keep = true)
 {
     const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
     if (workspace_bytes < pl.ticket_bytes + pl.part_bytes || !workspace) { set_error("mk_knn2: workspace too small (%zu < %zu)", workspace_bytes, pl.ticket_bytes + pl.part_bytes); return MK_ERR_WORKSPACE; }
@@ -431,7 +440,7 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
     P.tickets = reinterpret_cast<int *>(workspace);
     P.part = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(workspace) + pl.ticket_bytes);
     P.splits = pl.splits; P.nqb = pl.nqb;
-    if (P.n_keep) MK_CUDA_TRY(cudaMemsetAsync(P.n_keep, 0, sizeof(int32_t) * npairs, st));
+    if (P.n_keep && zero_n_keep) MK_CUDA_TRY(cudaMemsetAsync(P.n_keep, 0, sizeof(int32_t) * npairs, st));
     if (pl.nqb == 0 || npairs == 0) return MK_OK;
     if (pl.splits > 1) MK_CUDA_TRY(cudaMemsetAsync(P.tickets, 0, pl.ticket_bytes, st));
     dim3 grid(pl.nqb, pl.splits, npairs);
@@ -469,12 +478,21 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
 
 using namespace mk;
 
+// Problems large enough to amortise the extra launches go through the tensor-core GEMM.
+static bool use_tc(int norm, int nq, int nt, int dim)
+{
+    return knn_tc_supported(norm, nq, nt, dim) && (long)nq * nt >= 256L * 1024;
+}
+
 extern "C" size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim)
 {
-    (void)dim;
     const KnnPlan pl = make_plan(norm, 1, nq, nt);
-    return pl.ticket_bytes + pl.part_bytes;
+    size_t bytes = pl.ticket_bytes + pl.part_bytes;
+    if (use_tc(norm, nq, nt, dim)) bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_workspace_bytes(nq, nt, dim);
+    return bytes;
 }
+
+extern "C" int mk_knn2_uses_tensor_cores(int norm, int nq, int nt, int dim) { return use_tc(norm, nq, nt, dim) ? 1 : 0; }
 
 extern "C" size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim)
 {
@@ -495,6 +513,19 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
     P.q = static_cast<const uint8_t *>(q); P.t = static_cast<const uint8_t *>(t);
     P.nq = nq; P.nt = nt; P.dim = dim; P.stride = row_stride;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
+    if (use_tc(norm, nq, nt, dim)) {
+        // [SIMT scratch][tensor-core scratch]; the SIMT kernel only runs if the prep pass found values that
+        // bf16 cannot hold exactly (never the case for uint8 rows, so it is not even launched for them)
+        const KnnPlan pl = make_plan(norm, 1, nq, nt);
+        const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
+        if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2: workspace too small"); return MK_ERR_WORKSPACE; }
+        const int *flags = nullptr;
+        rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, idx, dist, ratio, keep, n_keep,
+                        static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags);
+        if (rc != MK_OK || norm == MK_NORM_L2_U8) return rc;
+        P.guard = flags;
+        return run_knn(norm, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+    }
     return run_knn(norm, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,475 @@
+// mk_knn_tc.cu -- L2 kNN-2 as a tcgen05 / TMA descriptor GEMM (K2-TC) for sm_100a.
+//
+// L2 matching is a dense contraction: d^2(q,t) = |q|^2 + |t|^2 - 2 q.t .  OpenCV's SIFT descriptors
+// are integer-valued floats in [0,255] and the reference matches ORB bytes under NORM_L2 as well
+// (src/mosaicking/registration.py:230-242), so bf16 operands are exact, every partial sum is an
+// integer < 2^24 and the fp32 accumulator in tensor memory holds q.t EXACTLY: the distances equal
+// cv2's sqrtf((float)sum) bit for bit.
+//
+//   prep kernel   rows -> bf16 [n][KP] (KP = K padded to 64), |row|^2 in fp32, "all integers in
+//                 [0,255]" flag.  Rows that are not integer-valued make the TC kernel return at once
+//                 and the bit-exact SIMT kernel (mk_knn.cu) takes over -- decided on the device.
+//   TC kernel     CTA = 128 queries (UMMA M=128), loops over train tiles of 256 rows (UMMA N=256).
+//                 warp 0   TMA producer  : cp.async.bulk.tensor 2-D boxes of 64 x rows bf16, 128-B swizzle
+//                 warp 1   MMA issuer    : one thread issues tcgen05.mma (kind::f16, K=16 per instr),
+//                                          accumulators 128 x 256 fp32 in TMEM, two accumulator stages
+//                 warps 2-5 epilogue     : tcgen05.ld 32x32b -> one query row per thread, d^2 = (|q|^2 - 2S) + |t|^2,
+//                                          pre-filter on d^2, exact top-2 on (sqrtf bits << 32 | index) keys
+//                 Train splits are merged by the ticket scheme of mk_knn.cu (finish_block).
+#include "mk_common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include <mutex>
+
+namespace mk {
+
+// ---- shared with mk_knn.cu --------------------------------------------------------------------
+struct KnnParams;  // defined in mk_knn.cu (same translation-unit-independent layout declared below)
+
+constexpr int TC_M = 128;          // queries per CTA
+constexpr int TC_N = 256;          // train rows per tile
+constexpr int TC_KA = 64;          // bf16 elements per 128-byte swizzle atom
+constexpr int TC_STAGES = 2;       // B tile ring
+constexpr int TC_THREADS = 192;    // warps: 0 TMA, 1 MMA, 2..5 epilogue
+constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
+
+struct TcParams {
+    const __nv_bfloat16 *qb, *tb;   // bf16 copies [n][KP]
+    const float *qn, *tn;           // squared norms
+    const int *flags;               // flags[0] != 0  =>  inputs are not exact in bf16: do nothing
+    int nq, nt, kp;
+    int splits, nqb;
+    unsigned long long *part;
+    int *tickets;
+    int32_t *idx;
+    float *dist;
+    uint8_t *keep;
+    int32_t *n_keep;
+    double ratio;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     smem_addr(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor
+// version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  Advancing K by 16 bf16 = +32 B on the start address.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address, 16-byte units, bits [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset = 1024 B
+    d |= (uint64_t)1 << 46;                            // descriptor version
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+
+#define TC_LD32(taddr, r)                                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                    \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+                 : "r"(taddr))
+
+struct TcKey {
+    using Key = unsigned long long;
+    static constexpr Key NONE = ~0ull;
+    static __device__ __forceinline__ void decode(Key k, int &idx, float &d)
+    {
+        if (k == NONE) { idx = -1; d = FLT_MAX; }
+        else { idx = (int)(uint32_t)k; d = __uint_as_float((uint32_t)(k >> 32)); }
+    }
+};
+
+// layout of the dynamic shared memory (1024-byte aligned base)
+struct TcSmem {
+    static constexpr int A_BYTES = TC_M * 128;                  // one k-half of A (128 rows x 128 B)
+    static constexpr int B_BYTES = TC_N * 128;                  // one k-half of one B stage
+    static __host__ __device__ constexpr int a_off(int half) { return half * A_BYTES; }
+    static __host__ __device__ constexpr int b_off(int stage, int half) { return 2 * A_BYTES + (stage * 2 + half) * B_BYTES; }
+    static __host__ __device__ constexpr int tn_off(int stage) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + stage * TC_N * 4; }
+    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [128][2] u64
+    static constexpr int bar_off = keys_off + TC_M * 2 * 8;
+    static constexpr int total = bar_off + 128;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    if (p.flags[0] != 0) return;   // not exactly representable in bf16: the SIMT kernel handles this call
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TcSmem::bar_off);
+    unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_STAGES,
+                       *bar_tfull = bars + 1 + 2 * TC_STAGES, *bar_tempty = bars + 3 + 2 * TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + 2 * TC_STAGES);
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qblk = blockIdx.x, split = blockIdx.y;
+    const int q0 = qblk * TC_M;
+    const int nhalf = p.kp / TC_KA;                      // 1 (K <= 64) or 2 (K = 128)
+    // train tiles of this split
+    const int ntiles = (p.nt + TC_N - 1) / TC_N;
+    const int per = (ntiles + p.splits - 1) / p.splits;
+    const int tile_lo = min(ntiles, split * per), tile_hi = min(ntiles, tile_lo + per);
+    const int my_tiles = tile_hi - tile_lo;
+
+    if (tid == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {   // allocate all 512 TMEM columns (2 accumulator stages x 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_addr(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
+            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * TC_KA, q0, bar_a);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % TC_STAGES, use = i / TC_STAGES;
+                if (use > 0) mbar_wait(bar_bempty + s, (use - 1) & 1);
+                mbar_expect_tx(bar_bfull + s, (uint32_t)(nhalf * TcSmem::B_BYTES));
+                for (int h = 0; h < nhalf; ++h)
+                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * TC_KA, (tile_lo + i) * TC_N, bar_bfull + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % TC_STAGES, use = i / TC_STAGES;
+                const int acc = i & 1, acc_use = i >> 1;
+                if (acc_use > 0) mbar_wait(bar_tempty + acc, (acc_use - 1) & 1);   // epilogue drained this accumulator
+                mbar_wait(bar_bfull + s, use & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+                uint32_t accumulate = 0;
+                for (int h = 0; h < nhalf; ++h) {
+                    const uint64_t ad = make_sw128_desc(smem_addr(smem + TcSmem::a_off(h)));
+                    const uint64_t bd = make_sw128_desc(smem_addr(smem + TcSmem::b_off(s, h)));
+#pragma unroll
+                    for (int k = 0; k < TC_KA / 16; ++k) {
+                        umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), TC_IDESC, accumulate);   // +32 B per K step
+                        accumulate = 1;
+                    }
+                }
+                umma_commit(bar_bempty + s);      // smem stage free once these MMAs retire
+                umma_commit(bar_tfull + acc);     // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue: one query row per thread =====================
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const int et = tid - 64;                           // 0..127 among epilogue threads
+        const int qi = q0 + row;
+        const float qn = (qi < p.nq) ? p.qn[qi] : 0.f;
+        unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;
+        float d2sq = __int_as_float(0x7f800000);           // squared distance of the current 2nd best (+inf)
+        float d1sq = d2sq;
+        float *s_tn0 = reinterpret_cast<float *>(smem + TcSmem::tn_off(0));
+        for (int i = 0; i < my_tiles; ++i) {
+            const int acc = i & 1, acc_use = i >> 1;
+            const int col0 = (tile_lo + i) * TC_N;
+            float *s_tn = s_tn0 + acc * TC_N;
+            // |t|^2 of this tile (+inf beyond nt so that padded columns never win)
+            for (int c = et; c < TC_N; c += 128) s_tn[c] = (col0 + c < p.nt) ? p.tn[col0 + c] : __int_as_float(0x7f800000);
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            mbar_wait(bar_tfull + acc, acc_use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N);
+#pragma unroll 1
+            for (int c = 0; c < TC_N; c += 32) {
+                uint32_t r[32];
+                TC_LD32(taddr + (uint32_t)c, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float d2 = __fadd_rn(__fmaf_rn(-2.f, __uint_as_float(r[j]), qn), s_tn[c + j]);
+                    if (d2 <= d2sq) {                      // rare: exact insertion on cv2's rooted distances
+                        const int col = col0 + c + j;
+                        if (col < p.nt) {
+                            const float sd = __fsqrt_rn(fmaxf(d2, 0.f));
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(sd) << 32) | (uint32_t)col;
+                            if (key < k1) { k2 = k1; d2sq = d1sq; k1 = key; d1sq = d2; }
+                            else if (key < k2) { k2 = key; d2sq = d2; }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + acc);                 // 128 arrivals release the accumulator stage
+        }
+        unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
+        s_keys[row * 2] = k1; s_keys[row * 2 + 1] = k2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+    }
+
+    // ---- merge the train splits and write the outputs (same ticket scheme as mk_knn.cu) ----------
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
+    unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;
+    const bool is_row_thread = tid < TC_M;
+    if (is_row_thread) { k1 = s_keys[tid * 2]; k2 = s_keys[tid * 2 + 1]; }
+    if (p.splits > 1) {
+        unsigned long long *base = p.part + ((size_t)qblk * p.splits) * TC_M * 2;
+        if (is_row_thread) {
+            unsigned long long *mine = base + ((size_t)split * TC_M + tid) * 2;
+            mine[0] = k1; mine[1] = k2;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_flag = (atomicAdd(&p.tickets[qblk], 1) == p.splits - 1);
+        __syncthreads();
+        if (!s_flag) return;
+        __threadfence();
+        if (is_row_thread) {
+            k1 = TcKey::NONE; k2 = TcKey::NONE;
+            for (int s = 0; s < p.splits; ++s) {
+                const unsigned long long *o = base + ((size_t)s * TC_M + tid) * 2;
+                const unsigned long long a = __ldcg(o), b = __ldcg(o + 1);
+                if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
+                if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
+            }
+        }
+        if (tid == 0) p.tickets[qblk] = 0;
+    }
+    bool kept = false;
+    const int qi = q0 + tid;
+    if (is_row_thread && qi < p.nq) {
+        int i1, i2; float d1, d2;
+        TcKey::decode(k1, i1, d1);
+        TcKey::decode(k2, i2, d2);
+        p.idx[2 * (size_t)qi] = i1; p.idx[2 * (size_t)qi + 1] = i2;
+        p.dist[2 * (size_t)qi] = d1; p.dist[2 * (size_t)qi + 1] = d2;
+        kept = (i2 >= 0) && (p.ratio > 0.0) && ((double)d1 < p.ratio * (double)d2);   // mosaic.py:430
+        if (p.keep) p.keep[qi] = kept ? 1 : 0;
+    }
+    if (p.n_keep && tid < TC_M) {
+        const unsigned b = __ballot_sync(0xffffffffu, kept);
+        if (lane == 0 && b) atomicAdd(p.n_keep, __popc(b));
+    }
+}
+
+// ---- prep: rows -> bf16 [n][kp] (zero padded), squared norms, exactness flag --------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ src, size_t stride_bytes, int n, int dim, int kp,
+                                                          __nv_bfloat16 *__restrict__ dst, float *__restrict__ norms, int *flags)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const T *row = reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(src) + (size_t)warp * stride_bytes);
+    float acc = 0.f;
+    bool bad = false;
+    for (int k = lane; k < kp; k += 32) {
+        float v = 0.f;
+        if (k < dim) v = (float)row[k];
+        if (!(v >= 0.f && v <= 255.f && v == truncf(v))) bad = true;     // also catches NaN
+        dst[(size_t)warp * kp + k] = __float2bfloat16_rn(v);
+        acc = __fadd_rn(acc, __fmul_rn(v, v));                            // integers: exact in any order
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) norms[warp] = acc;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
+}
+
+// ---- host -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MK_ERR_CUDA; }
+    const cuuint64_t dims[2] = { (cuuint64_t)kp, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)kp * 2 };
+    const cuuint32_t box[2] = { (cuuint32_t)TC_KA, (cuuint32_t)box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MK_ERR_CUDA; }
+    return MK_OK;
+}
+
+struct TcPlan {
+    int kp, nqb, splits;
+    size_t off_qb, off_tb, off_qn, off_tn, off_flags, off_tickets, off_part, total;
+};
+
+static TcPlan tc_plan(int nq, int nt, int dim)
+{
+    TcPlan pl;
+    pl.kp = dim <= 64 ? 64 : 128;
+    pl.nqb = (nq + TC_M - 1) / TC_M;
+    const int ntiles = (nt + TC_N - 1) / TC_N;
+    // one CTA per SM (160 KB of shared memory): pick the split count whose CTA total wastes the least of the last wave
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= ntiles && s <= 64; ++s) {
+        const int per = (ntiles + s - 1) / s;
+        const int s_eff = (ntiles + per - 1) / per;
+        const long ctas = (long)pl.nqb * s_eff;
+        const long waves = (ctas + 147) / 148;
+        const double eff = (double)(pl.nqb) * ntiles / (double)(waves * 148 * per);   // useful tiles / tile slots
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s_eff; }
+    }
+    pl.splits = pl.nqb > 0 ? best : 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    pl.off_qb = take((size_t)nq * pl.kp * 2);
+    pl.off_tb = take((size_t)nt * pl.kp * 2);
+    pl.off_qn = take((size_t)nq * 4);
+    pl.off_tn = take((size_t)nt * 4);
+    pl.off_flags = take(256);
+    pl.off_tickets = take((size_t)(pl.nqb > 0 ? pl.nqb : 1) * 4);
+    pl.off_part = take(pl.splits > 1 ? (size_t)pl.nqb * pl.splits * TC_M * 2 * 8 : 0);
+    pl.total = o;
+    return pl;
+}
+
+size_t knn_tc_workspace_bytes(int nq, int nt, int dim) { return tc_plan(nq, nt, dim).total; }
+
+bool knn_tc_supported(int norm, int nq, int nt, int dim)
+{
+    if (norm != MK_NORM_L2_F32 && norm != MK_NORM_L2_U8) return false;
+    if (dim > TC_MAX_KP || nq < 1 || nt < 2) return false;
+    return true;
+}
+
+// Launches prep + the TC kernel.  `flags` (device int) ends up non-zero when the inputs are not integer-valued
+// in [0,255]; the caller then runs the SIMT kernel guarded by the same flag (see mk_knn.cu).
+int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, int32_t *idx, float *dist, double ratio,
+               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out)
+{
+    const TcPlan pl = tc_plan(nq, nt, dim);
+    if (workspace_bytes < pl.total) { set_error("mk_knn2: workspace too small for the tensor-core path (%zu < %zu)", workspace_bytes, pl.total); return MK_ERR_WORKSPACE; }
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    if (!aligned(ws, 256)) { set_error("mk_knn2: workspace must be 256-byte aligned for the tensor-core path"); return MK_ERR_ALIGN; }
+    __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_qb), *tb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_tb);
+    float *qn = reinterpret_cast<float *>(ws + pl.off_qn), *tn = reinterpret_cast<float *>(ws + pl.off_tn);
+    int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
+    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, 256, st));
+    MK_CUDA_TRY(cudaMemsetAsync(tickets, 0, (size_t)pl.nqb * 4, st));
+    if (n_keep) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), st));
+    const int wpb = 8;
+    if (norm == MK_NORM_L2_F32) {
+        knn_tc_prep_kernel<float><<<(nq + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), stride, nq, dim, pl.kp, qb, qn, flags);
+        knn_tc_prep_kernel<float><<<(nt + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(t), stride, nt, dim, pl.kp, tb, tn, flags);
+    } else {
+        knn_tc_prep_kernel<uint8_t><<<(nq + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), stride, nq, dim, pl.kp, qb, qn, flags);
+        knn_tc_prep_kernel<uint8_t><<<(nt + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(t), stride, nt, dim, pl.kp, tb, tn, flags);
+    }
+    MK_LAUNCH_CHECK("knn_tc_prep_kernel");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    alignas(64) CUtensorMap map_q, map_t;
+    int rc = make_map(&map_q, qb, nq, pl.kp, TC_M);
+    if (rc != MK_OK) return rc;
+    rc = make_map(&map_t, tb, nt, pl.kp, TC_N);
+    if (rc != MK_OK) return rc;
+    TcParams P;
+    P.qb = qb; P.tb = tb; P.qn = qn; P.tn = tn; P.flags = flags;
+    P.nq = nq; P.nt = nt; P.kp = pl.kp; P.splits = pl.splits; P.nqb = pl.nqb;
+    P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
+    P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
+    static std::atomic<int> configured{-1};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int smem = TcSmem::total + 1024;
+    if (configured.load() != dev) {
+        MK_CUDA_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured.store(dev);
+    }
+    dim3 grid(pl.nqb, pl.splits);
+    knn2_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
+    MK_LAUNCH_CHECK("knn2_tc_kernel");
+    *flags_out = flags;
+    return MK_OK;
+}
+
+}  // namespace mk

@@ -93,6 +93,29 @@ def test_knn_f32_vs_oracle(nq, nt, dim, integer):
     assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
 
 
+def test_tensor_core_path_is_the_one_that_runs():
+    """SIFT-sized L2 problems go through the tcgen05 GEMM: the call launches prep x2 + the TC kernel (+ the guarded
+    SIMT kernel for float rows) and the result is still bit-exact; small problems stay on the SIMT kernels."""
+    L = mb._lib.lib()
+    assert L.mk_knn2_uses_tensor_cores(2, 8000, 8000, 128) == 1 and L.mk_knn2_uses_tensor_cores(1, 5000, 5000, 32) == 1
+    assert L.mk_knn2_uses_tensor_cores(0, 5000, 5000, 32) == 0 and L.mk_knn2_uses_tensor_cores(2, 100, 100, 128) == 0
+    rng = np.random.default_rng(1)
+    q = rng.integers(0, 256, (4000, 128)).astype(np.float32)
+    t = rng.integers(0, 256, (4100, 128)).astype(np.float32)
+    t[7] = q[5]; t[4000] = q[5]            # exact tie at distance 0 -> lowest train index first
+    n0 = mb.launch_count()
+    idx, dist, keep = mb.Matcher().knn_match_arrays(q, t, 0.7)
+    assert mb.launch_count() - n0 == 4
+    oi, od = orc.knn2(q, t, "l2")
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    assert idx[5].tolist() == [7, 4000] and dist[5].tolist() == [0.0, 0.0]
+    # worst-case magnitudes: all 255 vs all 0 (sum = 128 * 255^2 = 8.3e6 < 2^24 stays exact)
+    q2 = np.full((600, 128), 255, np.float32); t2 = np.zeros((700, 128), np.float32); t2[3, :5] = 1
+    idx, dist, _ = mb.Matcher().knn_match_arrays(q2, t2, 0.7)
+    oi, od = orc.knn2(q2, t2, "l2")
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
 def test_knn_batched_vs_single():
     """mk_knn2_batched over consecutive-frame pairs == per-pair calls."""
     rng = np.random.default_rng(3)
