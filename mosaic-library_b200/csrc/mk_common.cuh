@@ -40,4 +40,14 @@ inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_
 // cv::warpPerspective inverts H unless WARP_INVERSE_MAP is set (mosaic.py:114 does not set it).
 bool invert3x3(const double *S, double *D);
 
+// Tensor-core kNN flags, written on the DEVICE (prep pass + TC kernel) and read by the guarded SIMT fallback:
+//   flags[0] != 0  some value is not an integer in [0,255]: bf16 operands would round it, the TC kernel does nothing;
+//   flags[3] != 0  some row's best-two squared distance reached 2^22: the TC path ranks by the integer d^2, which equals
+//                  cv2's ranking by sqrtf((float)d^2) only while sqrtf is injective (d^2 < 2^22), so the whole call is
+//                  recomputed by the bit-exact SIMT kernel.  (Never happens for uint8 rows <= 64 bytes or SIFT.)
+#ifdef __CUDACC__
+__device__ __forceinline__ bool knn_tc_inputs_ok(const int *flags) { return flags[0] == 0; }
+__device__ __forceinline__ bool knn_tc_result_ok(const int *flags) { return flags[0] == 0 && flags[3] == 0; }
+#endif
+
 }  // namespace mk

@@ -42,7 +42,7 @@ struct KnnParams {
     uint8_t *keep;
     int32_t *n_keep;
     double ratio;
-    const int *guard;   // if non-null the kernel only runs when *guard != 0 (SIMT fallback of the tensor-core path)
+    const int *guard;   // if non-null the kernel only runs when the tensor-core path did not produce the result
 };
 
 // tensor-core path (mk_knn_tc.cu)
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_reg_kernel(const __grid_cons
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int z = blockIdx.z, qblk = blockIdx.x;
-    if (p.guard && *p.guard == 0) return;
+    if (p.guard && knn_tc_result_ok(p.guard)) return;
     const Problem pr = load_problem(p, z);
     if (qblk * QB >= pr.nq) return;
     const int qi = qblk * QB + lane;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_f32_kernel(const __grid_cons
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int z = blockIdx.z, qblk = blockIdx.x;
-    if (p.guard && *p.guard == 0) return;
+    if (p.guard && knn_tc_result_ok(p.guard)) return;
     const Problem pr = load_problem(p, z);
     if (qblk * FT >= pr.nq) return;
     const int q0 = qblk * FT;
@@ -522,7 +522,7 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
         const int *flags = nullptr;
         rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, idx, dist, ratio, keep, n_keep,
                         static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags);
-        if (rc != MK_OK || norm == MK_NORM_L2_U8) return rc;
+        if (rc != MK_OK || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;   // dim*255^2 < 2^22: the TC result always stands
         P.guard = flags;
         return run_knn(norm, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
     }

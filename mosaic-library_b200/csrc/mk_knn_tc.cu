@@ -33,14 +33,16 @@ constexpr int TC_M = 128;          // queries per CTA
 constexpr int TC_N = 256;          // train rows per tile
 constexpr int TC_KA = 64;          // bf16 elements per 128-byte swizzle atom
 constexpr int TC_STAGES = 2;       // B tile ring
-constexpr int TC_THREADS = 192;    // warps: 0 TMA, 1 MMA, 2..5 epilogue
+constexpr int TC_EPI_WARPS = 8;    // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2..9 epilogue
 constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
 
 struct TcParams {
     const __nv_bfloat16 *qb, *tb;   // bf16 copies [n][KP]
     const float *qn, *tn;           // squared norms
-    const int *flags;               // flags[0] != 0  =>  inputs are not exact in bf16: do nothing
-    int nq, nt, kp;
+    int *flags;                     // see mk_common.cuh: flags[0] inputs not exact in bf16, flags[3] result needs the SIMT recompute
+    int nq, nt, kp, dim;
     int splits, nqb;
     unsigned long long *part;
     int *tickets;
@@ -133,7 +135,7 @@ struct TcKey {
     static __device__ __forceinline__ void decode(Key k, int &idx, float &d)
     {
         if (k == NONE) { idx = -1; d = FLT_MAX; }
-        else { idx = (int)(uint32_t)k; d = __uint_as_float((uint32_t)(k >> 32)); }
+        else { idx = (int)(uint32_t)k; d = __fsqrt_rn((float)(uint32_t)(k >> 32)); }   // cv2: sqrtf((float)sum)
     }
 };
 
@@ -144,8 +146,8 @@ struct TcSmem {
     static __host__ __device__ constexpr int a_off(int half) { return half * A_BYTES; }
     static __host__ __device__ constexpr int b_off(int stage, int half) { return 2 * A_BYTES + (stage * 2 + half) * B_BYTES; }
     static __host__ __device__ constexpr int tn_off(int stage) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + stage * TC_N * 4; }
-    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [128][2] u64
-    static constexpr int bar_off = keys_off + TC_M * 2 * 8;
+    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [2][128][2] u64
+    static constexpr int bar_off = keys_off + 2 * TC_M * 2 * 8;
     static constexpr int total = bar_off + 128;
 };
 
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
-    if (p.flags[0] != 0) return;   // not exactly representable in bf16: the SIMT kernel handles this call
+    if (!knn_tc_inputs_ok(p.flags)) return;   // not exact on this path: the guarded SIMT kernel handles this call
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TcSmem::bar_off);
     unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_STAGES,
@@ -174,7 +176,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (tid == 0) {
         mbar_init(bar_a, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, TC_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {   // allocate all 512 TMEM columns (2 accumulator stages x 256)
@@ -225,50 +227,65 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue: one query row per thread =====================
-        const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+        // ===================== epilogue: one query row x one 128-column half per thread =====================
+        // S = q.t is an exact integer < 2^23, so bits(S + 2^23) = 0x4B000000 + S and
+        //     key = -256 * bits + (|t|^2 * 128 + col)  ==  (|t|^2 - 2 S) * 128 + col      (mod 2^32; 256 * 0x4B000000 == 0)
+        // is ONE IMAD per element; it orders candidates by (d^2, column) because |q|^2 is a per-row constant, it fits
+        // int32 (|.| <= 2^30 + 127) and min / second-min over keys needs no branch, hence no warp divergence.
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
+        const int chalf = (warp - 2) >> 2;                 // which 128-column half of every tile this warp scans
         const int row = quarter * 32 + lane;
-        const int et = tid - 64;                           // 0..127 among epilogue threads
+        const int et = tid - 64;                           // 0..255 among epilogue threads
         const int qi = q0 + row;
-        const float qn = (qi < p.nq) ? p.qn[qi] : 0.f;
-        unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;
-        float d2sq = __int_as_float(0x7f800000);           // squared distance of the current 2nd best (+inf)
-        float d1sq = d2sq;
-        float *s_tn0 = reinterpret_cast<float *>(smem + TcSmem::tn_off(0));
+        const int qn = (qi < p.nq) ? (int)p.qn[qi] : 0;    // exact integer
+        unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;   // running (d^2 << 32 | train index)
+        int *s_T0 = reinterpret_cast<int *>(smem + TcSmem::tn_off(0));
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1, acc_use = i >> 1;
             const int col0 = (tile_lo + i) * TC_N;
-            float *s_tn = s_tn0 + acc * TC_N;
-            // |t|^2 of this tile (+inf beyond nt so that padded columns never win)
-            for (int c = et; c < TC_N; c += 128) s_tn[c] = (col0 + c < p.nt) ? p.tn[col0 + c] : __int_as_float(0x7f800000);
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            int *s_T = s_T0 + acc * TC_N;
+            // per-column constant |t|^2 * 128 + (col & 127); INT_MAX beyond nt (S = 0 there, so the key stays INT_MAX)
+            s_T[et] = (col0 + et < p.nt) ? ((int)p.tn[col0 + et] * 128 + (et & 127)) : 0x7fffffff;
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
             mbar_wait(bar_tfull + acc, acc_use & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * (TC_N / 2));
+            int b1 = 0x7fffffff, b2 = 0x7fffffff;
 #pragma unroll 1
-            for (int c = 0; c < TC_N; c += 32) {
+            for (int c = 0; c < TC_N / 2; c += 32) {
                 uint32_t r[32];
                 TC_LD32(taddr + (uint32_t)c, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                const int *T = s_T + chalf * (TC_N / 2) + c;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d2 = __fadd_rn(__fmaf_rn(-2.f, __uint_as_float(r[j]), qn), s_tn[c + j]);
-                    if (d2 <= d2sq) {                      // rare: exact insertion on cv2's rooted distances
-                        const int col = col0 + c + j;
-                        if (col < p.nt) {
-                            const float sd = __fsqrt_rn(fmaxf(d2, 0.f));
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(sd) << 32) | (uint32_t)col;
-                            if (key < k1) { k2 = k1; d2sq = d1sq; k1 = key; d1sq = d2; }
-                            else if (key < k2) { k2 = key; d2sq = d2; }
-                        }
+                for (int j = 0; j < 32; j += 4) {
+                    const int4 t4 = *reinterpret_cast<const int4 *>(T + j);
+                    const int tv[4] = { t4.x, t4.y, t4.z, t4.w };
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int bits = __float_as_int(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
+                        const int key = bits * -256 + tv[u];
+                        b2 = min(b2, max(b1, key));
+                        b1 = min(b1, key);
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_tempty + acc);                 // 128 arrivals release the accumulator stage
+            mbar_arrive(bar_tempty + acc);                 // all epilogue threads release the accumulator stage
+            // fold the tile's two best into the running keys (key >> 7 = d^2 - |q|^2, key & 127 = column in this half)
+            if (b1 != 0x7fffffff) {
+                const unsigned long long key = ((unsigned long long)(uint32_t)((b1 >> 7) + qn) << 32) |
+                                               (uint32_t)(col0 + chalf * (TC_N / 2) + (b1 & 127));
+                const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
+            }
+            if (b2 != 0x7fffffff) {
+                const unsigned long long key = ((unsigned long long)(uint32_t)((b2 >> 7) + qn) << 32) |
+                                               (uint32_t)(col0 + chalf * (TC_N / 2) + (b2 & 127));
+                const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
+            }
         }
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
-        s_keys[row * 2] = k1; s_keys[row * 2 + 1] = k2;
+        s_keys[(chalf * TC_M + row) * 2] = k1; s_keys[(chalf * TC_M + row) * 2 + 1] = k2;
     }
     tc_fence_before();
     __syncthreads();
@@ -281,7 +298,12 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
     unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;
     const bool is_row_thread = tid < TC_M;
-    if (is_row_thread) { k1 = s_keys[tid * 2]; k2 = s_keys[tid * 2 + 1]; }
+    if (is_row_thread) {                                   // merge the two column halves of this row
+        k1 = s_keys[tid * 2]; k2 = s_keys[tid * 2 + 1];
+        const unsigned long long a = s_keys[(TC_M + tid) * 2], b = s_keys[(TC_M + tid) * 2 + 1];
+        if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
+        if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
+    }
     if (p.splits > 1) {
         unsigned long long *base = p.part + ((size_t)qblk * p.splits) * TC_M * 2;
         if (is_row_thread) {
@@ -311,6 +333,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         int i1, i2; float d1, d2;
         TcKey::decode(k1, i1, d1);
         TcKey::decode(k2, i2, d2);
+        if ((k1 != TcKey::NONE && (uint32_t)(k1 >> 32) >= 4194304u) || (k2 != TcKey::NONE && (uint32_t)(k2 >> 32) >= 4194304u))
+            atomicOr(p.flags + 3, 1);                      // sqrtf no longer injective: let the SIMT kernel redo the call
         p.idx[2 * (size_t)qi] = i1; p.idx[2 * (size_t)qi + 1] = i2;
         p.dist[2 * (size_t)qi] = d1; p.dist[2 * (size_t)qi + 1] = d2;
         kept = (i2 >= 0) && (p.ratio > 0.0) && ((double)d1 < p.ratio * (double)d2);   // mosaic.py:430
@@ -388,16 +412,17 @@ static TcPlan tc_plan(int nq, int nt, int dim)
     pl.kp = dim <= 64 ? 64 : 128;
     pl.nqb = (nq + TC_M - 1) / TC_M;
     const int ntiles = (nt + TC_N - 1) / TC_N;
-    // one CTA per SM (160 KB of shared memory): pick the split count whose CTA total wastes the least of the last wave
+    // one CTA per SM (165 KB of shared memory).  Cost model: waves x (tiles per CTA + 4); the constant stands for the A tile,
+    // the prologue and the cold-threshold phase every (CTA, row) scan starts with, so long scans are preferred.
     int best = 1;
-    double best_eff = 0.0;
+    double best_cost = 1e300;
     for (int s = 1; s <= ntiles && s <= 64; ++s) {
         const int per = (ntiles + s - 1) / s;
         const int s_eff = (ntiles + per - 1) / per;
         const long ctas = (long)pl.nqb * s_eff;
         const long waves = (ctas + 147) / 148;
-        const double eff = (double)(pl.nqb) * ntiles / (double)(waves * 148 * per);   // useful tiles / tile slots
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = s_eff; }
+        const double cost = (double)waves * (per + 4.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s_eff; }
     }
     pl.splits = pl.nqb > 0 ? best : 1;
     size_t o = 0;
@@ -454,7 +479,7 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     if (rc != MK_OK) return rc;
     TcParams P;
     P.qb = qb; P.tb = tb; P.qn = qn; P.tn = tn; P.flags = flags;
-    P.nq = nq; P.nt = nt; P.kp = pl.kp; P.splits = pl.splits; P.nqb = pl.nqb;
+    P.nq = nq; P.nt = nt; P.kp = pl.kp; P.dim = dim; P.splits = pl.splits; P.nqb = pl.nqb;
     P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
     static std::atomic<int> configured{-1};

@@ -32,7 +32,7 @@ for n in (4000, 8000):
     t = torch.from_numpy(rng.integers(0, 200, (n, 128)).astype(np.float32)).to(dev)
     m = mb.Matcher()
     med, best = timeit(lambda: m.knn_match_device(q, t, 0.7), n=5, warm=1)
-    print(f"knn l2 f32 simt {n}x{n}x128: median {med:.1f} us -> {n*n/med*1e6:.3e} pairs/s")
+    print(f"knn l2 f32 (tcgen05 when integer-valued) {n}x{n}x128: median {med:.1f} us -> {n*n/med*1e6:.3e} pairs/s")
 
 for (h, w, C) in ((1080, 1920, 16384), (2160, 3840, 16384)):
     for interp in ("linear", "cubic"):
