@@ -137,6 +137,16 @@ int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *cmask, size_
                      const double *H_host, double alpha, int interp, int blend, float feather_ramp,
                      int32_t *region_host, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Host <-> device helpers for callers that hold HOST buffers (the reference passes numpy arrays):
+ * thin wrappers over cudaMemcpy2DAsync so that a binding needs nothing but this library.
+ * Asynchronous when the host buffer is page-locked, staged by the driver otherwise.
+ * ------------------------------------------------------------------------------------- */
+int mk_upload_2d(void *dst_dev, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t row_bytes,
+                 size_t rows, void *stream);
+int mk_download_2d(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch, size_t row_bytes,
+                   size_t rows, void *stream);
+
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */
 int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,

@@ -22,3 +22,21 @@ extern "C" int mk_abi_version(void) { return MK_ABI_VERSION; }
 extern "C" const char *mk_version_string(void) { return "mosaic_b200 0.1 (sm_100a)"; }
 extern "C" const char *mk_last_error(void) { return mk::t_err; }
 extern "C" uint64_t mk_launch_count(void) { return mk::g_launches.load(); }
+
+extern "C" int mk_upload_2d(void *dst_dev, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t row_bytes, size_t rows,
+                            void *stream)
+{
+    if (!dst_dev || !src_host) { mk::set_error("mk_upload_2d: null pointer"); return MK_ERR_ARG; }
+    if (rows == 0 || row_bytes == 0) return MK_OK;
+    MK_CUDA_TRY(cudaMemcpy2DAsync(dst_dev, dst_pitch, src_host, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MK_OK;
+}
+
+extern "C" int mk_download_2d(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch, size_t row_bytes, size_t rows,
+                              void *stream)
+{
+    if (!dst_host || !src_dev) { mk::set_error("mk_download_2d: null pointer"); return MK_ERR_ARG; }
+    if (rows == 0 || row_bytes == 0) return MK_OK;
+    MK_CUDA_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MK_OK;
+}

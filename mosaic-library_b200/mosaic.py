@@ -74,7 +74,7 @@ class Mapper:
         # host frames are uploaded on a side stream into a small ring of staging buffers so that the
         # H2D copy of frame k+1 overlaps the kernel of frame k
         self._copy_stream = torch.cuda.Stream(device=self._device)
-        self._slots = [{"buf": None, "roi": None, "free": None} for _ in range(3)]
+        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
         self._slot = 0
         self._flag = True
         self.last_region = (0, 0, 0, 0)
@@ -127,31 +127,57 @@ class Mapper:
         optional uint8 [h, w] keypoint-hull mask on the device."""
         self._update_any(frame, H, roi)
 
+    def _slot_buffer(self, slot: dict, key: str, h: int, row: int) -> torch.Tensor:
+        pitch = _round_up(row, 128)
+        buf = slot[key]
+        if buf is None or buf.shape[0] < h or buf.shape[1] != pitch:
+            buf = torch.empty((h, pitch), dtype=torch.uint8, device=self._device)
+            slot[key] = buf
+        return buf
+
     def _update_any(self, image, H, roi) -> None:
-        t2, h, w = self._as_rows(image, 3)
-        r2 = None
-        if roi is not None:
-            r2, rh, rw = self._as_rows(roi, 1)
-            assert (rh, rw) == (h, w)
         cur = torch.cuda.current_stream(self._device)
-        if self._usable_in_place(t2) and (r2 is None or self._usable_in_place(r2)):
-            self._launch(t2, h, w, r2, H)
-            return
+        host_np = isinstance(image, np.ndarray) and (roi is None or isinstance(roi, np.ndarray))
+        if not host_np:
+            t2, h, w = self._as_rows(image, 3)
+            r2 = None
+            if roi is not None:
+                r2, rh, rw = self._as_rows(roi, 1)
+                assert (rh, rw) == (h, w)
+            if self._usable_in_place(t2) and (r2 is None or self._usable_in_place(r2)):
+                self._launch(t2, h, w, r2, H)
+                return
+        else:
+            if image.dtype != np.uint8:
+                raise TypeError("Mapper.update needs uint8 images")
+            image = np.ascontiguousarray(image)
+            h, w = image.shape[:2]
         slot = self._slots[self._slot]
         self._slot = (self._slot + 1) % len(self._slots)
         cs = self._copy_stream
-        if slot["free"] is not None:
+        if slot["free"] is None:
+            slot["free"], slot["ready"] = torch.cuda.Event(), torch.cuda.Event()
+        else:
             cs.wait_event(slot["free"])          # the kernel that last read this slot has finished
-        if t2.is_cuda:
-            cs.wait_stream(cur)
-        with torch.cuda.stream(cs):
-            buf = self._stage_upload(slot, "buf", t2)
-            rbuf = self._stage_upload(slot, "roi", r2) if r2 is not None else None
-        cur.wait_stream(cs)
+        rbuf = None
+        if host_np:
+            # straight cudaMemcpy2DAsync on the copy stream: asynchronous when the array is page-locked
+            buf = self._slot_buffer(slot, "buf", h, w * 3)
+            _lib.check(self._lib.mk_upload_2d(buf.data_ptr(), buf.stride(0), image.ctypes.data, w * 3, w * 3, h, cs.cuda_stream))
+            if roi is not None:
+                roi = np.ascontiguousarray(roi)
+                rbuf = self._slot_buffer(slot, "roi", h, w)
+                _lib.check(self._lib.mk_upload_2d(rbuf.data_ptr(), rbuf.stride(0), roi.ctypes.data, w, w, h, cs.cuda_stream))
+        else:
+            if t2.is_cuda:
+                cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                buf = self._stage_upload(slot, "buf", t2)
+                rbuf = self._stage_upload(slot, "roi", r2) if r2 is not None else None
+        slot["ready"].record(cs)
+        cur.wait_event(slot["ready"])
         self._launch(buf, h, w, rbuf, H)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        slot["free"] = ev
+        slot["free"].record(cur)
 
     def _launch(self, buf, h, w, rbuf, H) -> None:
         Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
@@ -181,7 +207,7 @@ class Mapper:
 
     def release(self):
         self._canvas = self._canvas_mask = self._wacc = None
-        self._slots = [{"buf": None, "roi": None, "free": None} for _ in range(3)]
+        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
 
     @property
     def output(self) -> np.ndarray:

@@ -110,11 +110,11 @@ class Matcher:
         self.__dict__.update(state)
         self._matcher = self._create_matcher()
 
-    def _workspace(self, nbytes: int, device) -> torch.Tensor:
-        ws = self._matcher["workspace"]
+    def _workspace(self, nbytes: int, device, key: str = "workspace") -> torch.Tensor:
+        ws = self._matcher.get(key)
         if ws is None or ws.numel() < nbytes or ws.device != device:
             ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-            self._matcher["workspace"] = ws
+            self._matcher[key] = ws
         return ws
 
     # -- device-side entry points --------------------------------------------------------------
@@ -146,9 +146,80 @@ class Matcher:
 
     def knn_match_arrays(self, query, train, ratio: float = 0.7):
         """-> (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) as numpy arrays.
-        idx = -1 / dist = FLT_MAX where the train set has fewer than 2 rows."""
+        idx = -1 / dist = FLT_MAX where the train set has fewer than 2 rows.
+        Host arrays take the lean path: persistent device buffers, plain cudaMemcpyAsync uploads, ONE packed
+        device->host copy of idx | dist | keep into page-locked memory and a single stream synchronisation."""
+        if isinstance(query, np.ndarray) and isinstance(train, np.ndarray):
+            return self._knn_host(query, train, ratio)
         idx, dist, keep, _ = self.knn_match_device(query, train, ratio)
         return idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool)
+
+    def _dev_rows(self, slot: str, a: np.ndarray, device, stream) -> tuple[torch.Tensor, int, int]:
+        """Upload a host descriptor array into a persistent device buffer whose rows are padded to 16 bytes."""
+        if a.ndim != 2:
+            raise _bad_input("descriptors must be 2-D")
+        if a.dtype not in (np.uint8, np.float32):
+            raise _bad_input(f"unsupported descriptor dtype {a.dtype} (cv2 accepts CV_8U and CV_32F)")
+        a = np.ascontiguousarray(a)
+        n, dim = a.shape
+        row = dim * a.itemsize
+        stride = (row + 15) & ~15
+        st = self._matcher.setdefault("dev", {})
+        buf = st.get(slot)
+        if buf is None or buf.numel() < max(n, 1) * stride or buf.device != device:
+            buf = torch.zeros(max(n, 1) * stride * 2, dtype=torch.uint8, device=device)
+            st[slot] = buf
+            st[slot + "_stride"] = None
+        if st.get(slot + "_stride") != (stride, row):
+            if stride != row:
+                buf.zero_()                       # the padding columns must read as zero (runs on the matcher's stream)
+            st[slot + "_stride"] = (stride, row)
+        if n:
+            _lib.check(self._matcher["lib"].mk_upload_2d(buf.data_ptr(), stride, a.ctypes.data, row, row, n, stream))
+        return buf, dim, stride
+
+    def _knn_host(self, q: np.ndarray, t: np.ndarray, ratio: float):
+        device = _cuda_device(self._device)
+        if q.dtype != t.dtype:
+            raise _bad_input("query and train descriptors must have the same type")
+        if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1]:
+            raise _bad_input("query and train descriptors must have the same width")
+        code = _norm_code(self._norm, q.dtype)
+        nq, nt = q.shape[0], t.shape[0]
+        if nq == 0:
+            return np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool)
+        L = self._matcher["lib"]
+        # host in, host out: nothing depends on the caller's stream, so the call runs on a private stream and
+        # overlaps whatever the caller has in flight (e.g. Mapper's frame upload + fused kernel)
+        cur = self._matcher.get("stream")
+        if cur is None or cur.device != device:
+            cur = torch.cuda.Stream(device=device)
+            self._matcher["stream"] = cur
+        with torch.cuda.stream(cur):             # every torch-side fill / allocation below runs on the private stream too
+            stream = cur.cuda_stream
+            qd, dim, stride = self._dev_rows("q", q, device, stream)
+            td, _, _ = self._dev_rows("t", t, device, stream)
+            # packed outputs: idx (nq*8) | dist (nq*8) | keep (nq) | pad | n_keep (4)
+            off_keep, off_n = nq * 16, (nq * 17 + 3) & ~3
+            total = off_n + 4
+            st = self._matcher["dev"]
+            out = st.get("out")
+            if out is None or out.numel() < total or out.device != device:
+                out = torch.empty(total * 2, dtype=torch.uint8, device=device)
+                st["out"] = out
+                st["out_host"] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
+            host = st["out_host"]
+            ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace_host_path")
+            base = out.data_ptr()
+            _lib.check(L.mk_knn2(code, qd.data_ptr(), nq, td.data_ptr() if nt else None, nt, dim, stride, base, base + nq * 8,
+                                 float(ratio), base + off_keep, base + off_n, ws.data_ptr(), ws.numel(), stream))
+            _lib.check(L.mk_download_2d(host.data_ptr(), total, base, total, total, 1, stream))
+            cur.synchronize()
+        hb = host.numpy()
+        idx = hb[: nq * 8].view(np.int32).reshape(nq, 2).copy()
+        dist = hb[nq * 8: nq * 16].view(np.float32).reshape(nq, 2).copy()
+        keep = hb[off_keep: off_keep + nq].astype(bool)
+        return idx, dist, keep
 
     # -- reference API ---------------------------------------------------------------------------
     def knn_match(self, query: np.ndarray, train: np.ndarray, mask: np.ndarray = None) -> Sequence[Sequence[DMatch]]:
