@@ -22,6 +22,7 @@
 
 #include <math.h>
 #include <mutex>
+#include <type_traits>
 
 namespace mk {
 
@@ -29,7 +30,8 @@ constexpr int TW = 64;   // tile width  (== BLOCK_W)
 constexpr int TH = 32;   // tile height
 constexpr int HALO = 2;  // 5x5 erosion radius
 constexpr int EH = TH + 2 * HALO;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;       // K3 warp kernel
+constexpr int MTHREADS = 256;       // K4 (512 threads per tile measured 30-50 % slower: serial per-tile sections, lower occupancy)
 constexpr int ROWB = TW * 3;       // canvas bytes per tile row
 constexpr int ROWV = ROWB / 16;    // 16-byte vectors per tile row
 
@@ -146,7 +148,7 @@ __device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float 
 }
 
 template <int INTERP, int BLEND, bool ROI>
-__global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_constant__ MapperParams p)
+__global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
     __shared__ __align__(16) uint32_t s_warp[TH][TW];
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
         double X0, Y0, W0;
         row_base(p.M, tileX + (b - 1) * BLOCK_W, tileY - HALO + r, X0, Y0, W0);
         s_row[b][r][0] = X0; s_row[b][r][1] = Y0; s_row[b][r][2] = W0;
+        if (b == 0) s_m0[r] = ~0ull;   // rows / columns outside the canvas count as set (cv2.erode's default border)
     } else if (tid >= 128 && tid < 132) {
         const int c = tid - 128;
         const int x0 = (c & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (c & 1) ? HALO - 1 : BLOCK_W - HALO;
@@ -205,12 +208,14 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
         constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;  // tap reach + 1 px safety ring
         sx_lo -= LO; sy_lo -= LO; sx_hi += HI; sy_hi += HI;
         if (convex && (sx_hi < 0 || sy_hi < 0 || sx_lo > p.w - 1 || sy_lo > p.h - 1)) return;  // tile misses the frame
-        sx_lo = max(sx_lo, -2); sy_lo = max(sy_lo, -2); sx_hi = min(sx_hi, p.w + 1); sy_hi = min(sy_hi, p.h + 1);
+        // the rectangle is NOT clamped to the frame: the part outside is zero-filled below, so that the fast sampler can
+        // skip all containment tests (it is tile-sized by construction; the budget test below still guards the size)
         T.s = s_src; T.sy0 = sy_lo;
         T.bx0 = ((sx_lo * 3) >> 4) << 4;
         T.rowbytes = ((sx_hi * 3 + 3 - T.bx0) + 15) & ~15;
         T.R = sy_hi - sy_lo + 1;
-        use_smem = convex && p.src_aligned && T.R > 1 && T.rowbytes > 0 && T.R * T.rowbytes <= p.src_smem_bytes;
+        use_smem = convex && p.src_aligned && T.R > 1 && T.R < 4096 && T.rowbytes > 0 && T.rowbytes < 16384 &&
+                   T.R * T.rowbytes <= p.src_smem_bytes;
     }
 
     // ---- stage the canvas tile and the source rectangle: one bulk copy per row (async proxy),
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
         }
         if (use_smem && (c_lo > 0 || c_hi < T.rowbytes || r_lo > 0 || r_hi < T.R)) {
             const int row_end = p.w * 3, nch = T.rowbytes >> 4;
-            for (int i = tid; i < T.R * nch; i += NTHREADS) {
+            for (int i = tid; i < T.R * nch; i += MTHREADS) {
                 const int r = i / nch, c = (i - r * nch) << 4;
                 if (r >= r_lo && r < r_hi && c >= c_lo && c < c_hi) continue;   // covered by the bulk copy
                 const int gy = T.sy0 + r, gb = T.bx0 + c;
@@ -261,34 +266,54 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
     // ---- phase 1: warp tile + vertical halo; lanes = consecutive columns -------------------
     {
         const int cx = (warp & 1) * 32 + lane, x = tileX + cx;
+        const bool xvalid = x < p.Wc;
         const double dx1 = (double)cx;
         const double mx = dmul(p.M.m[0], dx1), my = dmul(p.M.m[3], dx1), mw = dmul(p.M.m[6], dx1);
+        // rows of the haloed tile that lie inside the canvas (the others keep their all-ones bit rows)
+        const int r_lo = max(0, HALO - tileY), r_hi = min(EH, p.Hc - tileY + HALO);
+        constexpr int RSTEP = MTHREADS / 64;   // rows advanced per pass: two warps cover one 64-px row
+        int r0 = warp >> 1;
+        if (r0 < r_lo) r0 += (r_lo - r0 + RSTEP - 1) / RSTEP * RSTEP;
+        auto body = [&](auto fast_tag, auto affine_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
+            const double wr = p.M.wr;
 #pragma unroll 1
-        for (int k = 0; k < EH / 4; ++k) {
-            const int r = (warp >> 1) + 4 * k, y = tileY - HALO + r;
-            uint32_t px = 0, mv = 255;
-            float wg = 0.f;
-            if (y >= 0 && y < p.Hc && x < p.Wc) {
-                int X, Y;
-                if (use_smem) quantize_fast(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
-                else quantize(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
-                px = sample_c3_tile<INTERP>(use_smem, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
-                if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
-                else mv = px ? 255u : 0u;
-                if constexpr (BLEND == MK_BLEND_FEATHER) {
-                    const float u = (float)X * 0.03125f, v = (float)Y * 0.03125f;
-                    const float e = fminf(fminf(__fadd_rn(u, 0.5f), __fsub_rn(__fsub_rn((float)p.w, 0.5f), u)),
-                                          fminf(__fadd_rn(v, 0.5f), __fsub_rn(__fsub_rn((float)p.h, 0.5f), v)));
-                    wg = fminf(1.f, fmaxf(0.f, __fdiv_rn(e, p.ramp)));
+            for (int r = r0; r < r_hi; r += RSTEP) {
+                uint32_t px = 0, mv = 255;
+                float wg = 0.f;
+                if (xvalid) {
+                    int X, Y;
+                    if constexpr (FAST) quantize_fast_t<AFF>(p.M, wr, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                    else quantize(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                    if constexpr (FAST && INTERP == 1) px = sample_linear_c3_smem_fast(T, X, Y, p.lut);
+                    else px = sample_c3_tile<INTERP>(FAST, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
+                    if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
+                    else mv = px ? 255u : 0u;
+                    if constexpr (BLEND == MK_BLEND_FEATHER) {
+                        const float u = (float)X * 0.03125f, v = (float)Y * 0.03125f;
+                        const float e = fminf(fminf(__fadd_rn(u, 0.5f), __fsub_rn(__fsub_rn((float)p.w, 0.5f), u)),
+                                              fminf(__fadd_rn(v, 0.5f), __fsub_rn(__fsub_rn((float)p.h, 0.5f), v)));
+                        wg = fminf(1.f, fmaxf(0.f, __fdiv_rn(e, p.ramp)));
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, mv != 0);
+                if (lane == 0) reinterpret_cast<uint32_t *>(&s_m0[r])[warp & 1] = bal;
+                if constexpr (ROI) s_mval[r][cx + HALO] = (uint8_t)mv;
+                if (r >= HALO && r < HALO + TH) {
+                    s_warp[r - HALO][cx] = px;
+                    if constexpr (BLEND == MK_BLEND_FEATHER) s_wgt[r - HALO][cx] = wg;
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, mv != 0);
-            if (lane == 0) reinterpret_cast<uint32_t *>(&s_m0[r])[warp & 1] = bal;
-            if constexpr (ROI) s_mval[r][cx + HALO] = (uint8_t)mv;
-            if (r >= HALO && r < HALO + TH) {
-                s_warp[r - HALO][cx] = px;
-                if constexpr (BLEND == MK_BLEND_FEATHER) s_wgt[r - HALO][cx] = wg;
-            }
+        };
+        if (use_smem) {
+            if (p.M.affine) body(std::true_type{}, std::true_type{});
+            else body(std::true_type{}, std::false_type{});
+        } else {
+            body(std::false_type{}, std::false_type{});
+        }
+        if constexpr (ROI) {   // rows outside the canvas: the erosion minimum must see "set" there
+            for (int r = warp >> 1; r < EH; r += RSTEP)
+                if (r < r_lo || r >= r_hi) s_mval[r][cx + HALO] = 255;
         }
     }
     // ---- phase 1b: the 2 + 2 side-halo columns (they live in the neighbouring blocks) -------
@@ -323,13 +348,13 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
         __syncthreads();
         if (tid < TH) s_v[tid] = s_h[tid] & s_h[tid + 1] & s_h[tid + 2] & s_h[tid + 3] & s_h[tid + 4];
     } else {
-        for (int i = tid; i < EH * TW; i += NTHREADS) {
+        for (int i = tid; i < EH * TW; i += MTHREADS) {
             const int r = i / TW, c = i - r * TW;
             const uint8_t *q = &s_mval[r][c];
             s_mh[r][c] = (uint8_t)min(min(min((int)q[0], (int)q[1]), min((int)q[2], (int)q[3])), (int)q[4]);
         }
         __syncthreads();
-        for (int i = tid; i < TH * TW; i += NTHREADS) {
+        for (int i = tid; i < TH * TW; i += MTHREADS) {
             const int r = i / TW, c = i - r * TW;
             const int m = min(min(min((int)s_mh[r][c], (int)s_mh[r + 1][c]), min((int)s_mh[r + 2][c], (int)s_mh[r + 3][c])),
                               (int)s_mh[r + 4][c]);
@@ -348,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS) mapper_update_kernel(const __grid_co
     const bool keep_old = (BLEND == MK_BLEND_ALPHA) && p.alpha == 1.0f && p.beta == 0.0f;   // fmaf(c,1,w*0) == c
     const bool take_new = (BLEND == MK_BLEND_ALPHA) && p.alpha == 0.0f && p.beta == 1.0f;   // fmaf(c,0,w*1) == w
 #pragma unroll 1
-    for (int item = tid; item < TH * (TW / 4); item += NTHREADS) {
+    for (int item = tid; item < TH * (TW / 4); item += MTHREADS) {
         const int r = item >> 4, g = item & 15, y = tileY + r, x = tileX + 4 * g;
         if (y >= p.Hc || x >= p.Wc) continue;
         unsigned mb = (unsigned)(s_v[r] >> (4 * g)) & 15u;
@@ -633,7 +658,7 @@ static cudaError_t launch_mapper_inst(dim3 grid, cudaStream_t st, const MapperPa
         if (e != cudaSuccess) return e;
         configured.store(dev, std::memory_order_release);
     }
-    mapper_update_kernel<INTERP, BLEND, ROI><<<grid, NTHREADS, (size_t)P.src_smem_bytes, st>>>(P);
+    mapper_update_kernel<INTERP, BLEND, ROI><<<grid, MTHREADS, (size_t)P.src_smem_bytes, st>>>(P);
     return cudaSuccess;
 }
 

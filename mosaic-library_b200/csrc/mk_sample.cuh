@@ -71,6 +71,19 @@ __device__ __forceinline__ void quantize_fast(const InvMap &M, double X0, double
     Y = round_magic(dmul(dadd(Y0, my), W));
 }
 
+template <bool AFFINE>
+__device__ __forceinline__ void quantize_fast_t(const InvMap &M, double wr, double X0, double Y0, double W0, double mx, double my,
+                                                double mw, int &X, int &Y)
+{
+    double W = wr;
+    if constexpr (!AFFINE) {
+        W = dadd(W0, mw);
+        W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+    }
+    X = round_magic(dmul(dadd(X0, mx), W));
+    Y = round_magic(dmul(dadd(Y0, my), W));
+}
+
 __device__ __forceinline__ uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
 
 // ------------------------------------------------------------------------------------------
@@ -246,6 +259,21 @@ __device__ __forceinline__ bool sample_linear_c3_smem_lut(const SrcTile &T, int 
     out = lerp3_dp4a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
                      __funnelshift_r(b1, b2, sh), wt);
     return true;
+}
+
+// Same without the containment test: valid when the staged rectangle is the UNCLAMPED corner hull + safety ring, which
+// provably contains the taps of every pixel of the haloed tile (W keeps its sign => the image of the tile is the convex
+// hull of the corner images; rounding to 1/32 px is monotone; the ring absorbs the 1-ulp evaluation-order differences).
+__device__ __forceinline__ uint32_t sample_linear_c3_smem_fast(const SrcTile &T, int X, int Y, const uint2 *__restrict__ lut)
+{
+    const int r = (Y >> 5) - T.sy0, cb = (X >> 5) * 3 - T.bx0;
+    const uint2 wt = __ldg(lut + ((Y & 31) * 32 + (X & 31)));
+    const uint32_t *q0 = reinterpret_cast<const uint32_t *>(T.s + r * T.rowbytes + (cb & ~3));
+    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
+    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
+    return lerp3_dp4a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
+                      __funnelshift_r(b1, b2, sh), wt);
 }
 
 __device__ __forceinline__ bool sample_linear_c3_smem(const SrcTile &T, int X, int Y, uint32_t &out)

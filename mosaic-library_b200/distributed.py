@@ -100,6 +100,23 @@ class ShardedMosaic:
         allH = torch.stack(out).cpu().numpy()
         return [None if np.isnan(a[0]) else a.reshape(3, 3) for a in allH]
 
+    def connect(self) -> None:
+        """Establish every rank-to-rank NCCL send/recv channel up front (they are otherwise created lazily by the
+        first routed frame, which costs hundreds of milliseconds once)."""
+        if self.world == 1:
+            return
+        token = torch.zeros(8, dtype=torch.uint8, device=self.device)
+        sink = [torch.empty_like(token) for _ in range(self.world)]
+        ops = []
+        for peer in range(self.world):
+            if peer != self.rank:
+                ops.append(dist.P2POp(dist.isend, token, peer))
+                ops.append(dist.P2POp(dist.irecv, sink[peer], peer))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def plan(self, H_local: np.ndarray) -> None:
         """Exchange the homographies of ALL upcoming frames once (the reference also knows every pose
         before it renders: global_registration precedes generate, and _create_tile_graph routes every

@@ -66,6 +66,7 @@ def _worker(rank, world, port, q):
     try:
         frames, Hs = _scenario(world)
         sm = ShardedMosaic(GRID, TILE, OracleMapper, FRAME, torch.device("cpu"))
+        sm.connect()
         sm.plan(Hs[:, rank])                 # one all_gather of every pose (the bench path) ...
         for k in range(STEPS):
             if k % 2 == 0:
