@@ -313,6 +313,7 @@ def run_b200(args):
         "match_pairs_per_s": NDESC * NDESC / (float(match_ms.mean()) * 1e-3),
     }
     if not multi:
+        out["other_kernels"] = other_kernels(torch, mb, dev, flush)
         out["roofline"] = roofline(nbytes, blend_ms)
         out["warp_blend_gpix_per_s"] = float(((nbytes - fh * fw * 3) / 8).sum() / (blend_ms.sum() * 1e-3) / 1e9)
         out["roofline_match"] = roofline_popc(match_ms)
@@ -331,6 +332,32 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def other_kernels(torch, mb, dev, flush) -> dict:
+    """Device-side timings of the matching kernels the headline step does not use (BASELINE configs[2] / the reference's
+    own ORB-under-L2 metric): CUDA events, L2 flushed before every launch, median of 10."""
+    rng = np.random.default_rng(3)
+    res = {}
+    cases = (("l2_sift_8000x8000x128_tcgen05", "l2", rng.integers(0, 120, (8000, 128)).astype(np.float32), 2 * 8000 * 8000 * 128),
+             ("l2_u8_orb_5000x5000x32_tcgen05", "l2", rng.integers(0, 256, (5000, 32), dtype=np.uint8), 2 * 5000 * 5000 * 64))
+    for name, norm, a, flops in cases:
+        q = torch.from_numpy(a).to(dev)
+        t = torch.from_numpy(np.roll(a, 7, axis=0).copy()).to(dev)
+        m = mb.Matcher(norm=norm, device=dev)
+        for _ in range(3):
+            m.knn_match_device(q, t, RATIO)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); m.knn_match_device(q, t, RATIO); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        med = float(np.median(ts))
+        n = a.shape[0]
+        res[name] = {"call_us": med * 1e3, "pairs_per_s": n * n / (med * 1e-3), "tflops_incl_prep_and_epilogue": flops / (med * 1e-3) / 1e12}
+    return res
+
+
 def peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -344,8 +371,12 @@ def roofline(nbytes: np.ndarray, ms: np.ndarray) -> dict:
     A = canvas rectangle visited; duration = CUDA events around the launch (L2 cold)."""
     peak, src = peaks()
     achieved = float(nbytes.sum() / (ms.sum() * 1e-3) / 1e9)
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"     # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("mk::mapper_update_kernel")
     return {"kernel": "mk::mapper_update_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": src,
+            "frac": achieved / peak, "traffic": traffic, "peak_source": src,
             "algorithmic_bytes_per_launch": float(nbytes.mean()), "launch_us": float(ms.mean() * 1e3)}
 
 

@@ -33,9 +33,11 @@ constexpr int TC_M = 128;          // queries per CTA
 constexpr int TC_N = 256;          // train rows per tile
 constexpr int TC_KA = 64;          // bf16 elements per 128-byte swizzle atom
 constexpr int TC_STAGES = 2;       // B tile ring
-constexpr int TC_EPI_WARPS = 8;    // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TC_EPI_WARPS = 16;   // four warps per TMEM lane quarter, each takes a quarter of the tile's columns
+constexpr int TC_CSPLIT = TC_EPI_WARPS / 4;      // column groups per tile
+constexpr int TC_CW = TC_N / TC_CSPLIT;         // columns scanned per epilogue thread and tile (<= 128: 7 key bits)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2..9 epilogue
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2.. epilogue
 constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
 
 struct TcParams {
@@ -146,8 +148,8 @@ struct TcSmem {
     static __host__ __device__ constexpr int a_off(int half) { return half * A_BYTES; }
     static __host__ __device__ constexpr int b_off(int stage, int half) { return 2 * A_BYTES + (stage * 2 + half) * B_BYTES; }
     static __host__ __device__ constexpr int tn_off(int stage) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + stage * TC_N * 4; }
-    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [2][128][2] u64
-    static constexpr int bar_off = keys_off + 2 * TC_M * 2 * 8;
+    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [TC_CSPLIT][128][2] u64
+    static constexpr int bar_off = keys_off + TC_CSPLIT * TC_M * 2 * 8;
     static constexpr int total = bar_off + 128;
 };
 
@@ -233,9 +235,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // is ONE IMAD per element; it orders candidates by (d^2, column) because |q|^2 is a per-row constant, it fits
         // int32 (|.| <= 2^30 + 127) and min / second-min over keys needs no branch, hence no warp divergence.
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
-        const int chalf = (warp - 2) >> 2;                 // which 128-column half of every tile this warp scans
+        const int chalf = (warp - 2) >> 2;                 // which column group of every tile this warp scans
         const int row = quarter * 32 + lane;
-        const int et = tid - 64;                           // 0..255 among epilogue threads
+        const int et = tid - 64;                           // index among the epilogue threads
         const int qi = q0 + row;
         const int qn = (qi < p.nq) ? (int)p.qn[qi] : 0;    // exact integer
         unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;   // running (d^2 << 32 | train index)
@@ -245,18 +247,18 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const int col0 = (tile_lo + i) * TC_N;
             int *s_T = s_T0 + acc * TC_N;
             // per-column constant |t|^2 * 128 + (col & 127); INT_MAX beyond nt (S = 0 there, so the key stays INT_MAX)
-            s_T[et] = (col0 + et < p.nt) ? ((int)p.tn[col0 + et] * 128 + (et & 127)) : 0x7fffffff;
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            if (et < TC_N) s_T[et] = (col0 + et < p.nt) ? ((int)p.tn[col0 + et] * 128 + (et % TC_CW)) : 0x7fffffff;
+            asm volatile("bar.sync 1, %0;\n" ::"n"(TC_EPI_THREADS) : "memory");
             mbar_wait(bar_tfull + acc, acc_use & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * (TC_N / 2));
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * TC_CW);
             int b1 = 0x7fffffff, b2 = 0x7fffffff;
 #pragma unroll 1
-            for (int c = 0; c < TC_N / 2; c += 32) {
+            for (int c = 0; c < TC_CW; c += 32) {
                 uint32_t r[32];
                 TC_LD32(taddr + (uint32_t)c, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                const int *T = s_T + chalf * (TC_N / 2) + c;
+                const int *T = s_T + chalf * TC_CW + c;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int4 t4 = *reinterpret_cast<const int4 *>(T + j);
@@ -275,12 +277,12 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             // fold the tile's two best into the running keys (key >> 7 = d^2 - |q|^2, key & 127 = column in this half)
             if (b1 != 0x7fffffff) {
                 const unsigned long long key = ((unsigned long long)(uint32_t)((b1 >> 7) + qn) << 32) |
-                                               (uint32_t)(col0 + chalf * (TC_N / 2) + (b1 & 127));
+                                               (uint32_t)(col0 + chalf * TC_CW + (b1 & 127));
                 const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
             }
             if (b2 != 0x7fffffff) {
                 const unsigned long long key = ((unsigned long long)(uint32_t)((b2 >> 7) + qn) << 32) |
-                                               (uint32_t)(col0 + chalf * (TC_N / 2) + (b2 & 127));
+                                               (uint32_t)(col0 + chalf * TC_CW + (b2 & 127));
                 const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
             }
         }
@@ -298,11 +300,14 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
     unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;
     const bool is_row_thread = tid < TC_M;
-    if (is_row_thread) {                                   // merge the two column halves of this row
+    if (is_row_thread) {                                   // merge the column groups of this row
         k1 = s_keys[tid * 2]; k2 = s_keys[tid * 2 + 1];
-        const unsigned long long a = s_keys[(TC_M + tid) * 2], b = s_keys[(TC_M + tid) * 2 + 1];
-        if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
-        if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
+#pragma unroll
+        for (int g = 1; g < TC_CSPLIT; ++g) {
+            const unsigned long long a = s_keys[(g * TC_M + tid) * 2], b = s_keys[(g * TC_M + tid) * 2 + 1];
+            if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
+            if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
+        }
     }
     if (p.splits > 1) {
         unsigned long long *base = p.part + ((size_t)qblk * p.splits) * TC_M * 2;
@@ -346,25 +351,32 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
-// ---- prep: rows -> bf16 [n][kp] (zero padded), squared norms, exactness flag --------------------------
+// ---- prep: rows -> bf16 [n][kp] (zero padded), squared norms, exactness flag; one launch for both sets ----------
 template <typename T>
-__global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ src, size_t stride_bytes, int n, int dim, int kp,
-                                                          __nv_bfloat16 *__restrict__ dst, float *__restrict__ norms, int *flags)
+__global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ q, int nq, const T *__restrict__ t, int nt,
+                                                          size_t stride_bytes, int dim, int kp, __nv_bfloat16 *__restrict__ qb,
+                                                          __nv_bfloat16 *__restrict__ tb, float *__restrict__ qn,
+                                                          float *__restrict__ tn, int *flags, int32_t *n_keep)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const T *row = reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(src) + (size_t)warp * stride_bytes);
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row == 0 && lane == 0 && n_keep) *n_keep = 0;
+    if (row >= nq + nt) return;
+    const bool is_q = row < nq;
+    if (!is_q) row -= nq;
+    const T *src = reinterpret_cast<const T *>(reinterpret_cast<const uint8_t *>(is_q ? q : t) + (size_t)row * stride_bytes);
+    __nv_bfloat16 *dst = (is_q ? qb : tb) + (size_t)row * kp;
     float acc = 0.f;
     bool bad = false;
     for (int k = lane; k < kp; k += 32) {
         float v = 0.f;
-        if (k < dim) v = (float)row[k];
+        if (k < dim) v = (float)src[k];
         if (!(v >= 0.f && v <= 255.f && v == truncf(v))) bad = true;     // also catches NaN
-        dst[(size_t)warp * kp + k] = __float2bfloat16_rn(v);
+        dst[k] = __float2bfloat16_rn(v);
         acc = __fadd_rn(acc, __fmul_rn(v, v));                            // integers: exact in any order
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) norms[warp] = acc;
+    if (lane == 0) (is_q ? qn : tn)[row] = acc;
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
 }
 
@@ -459,19 +471,16 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_qb), *tb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_tb);
     float *qn = reinterpret_cast<float *>(ws + pl.off_qn), *tn = reinterpret_cast<float *>(ws + pl.off_tn);
     int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
-    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, 256, st));
-    MK_CUDA_TRY(cudaMemsetAsync(tickets, 0, (size_t)pl.nqb * 4, st));
-    if (n_keep) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), st));
-    const int wpb = 8;
-    if (norm == MK_NORM_L2_F32) {
-        knn_tc_prep_kernel<float><<<(nq + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), stride, nq, dim, pl.kp, qb, qn, flags);
-        knn_tc_prep_kernel<float><<<(nt + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(t), stride, nt, dim, pl.kp, tb, tn, flags);
-    } else {
-        knn_tc_prep_kernel<uint8_t><<<(nq + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), stride, nq, dim, pl.kp, qb, qn, flags);
-        knn_tc_prep_kernel<uint8_t><<<(nt + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(t), stride, nt, dim, pl.kp, tb, tn, flags);
-    }
+    // flags and tickets are adjacent in the workspace: one memset
+    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)pl.nqb * 4, st));
+    const int wpb = 8, rows = nq + nt;
+    if (norm == MK_NORM_L2_F32)
+        knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), nq, static_cast<const float *>(t), nt,
+                                                                          stride, dim, pl.kp, qb, tb, qn, tn, flags, n_keep);
+    else
+        knn_tc_prep_kernel<uint8_t><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), nq, static_cast<const uint8_t *>(t), nt,
+                                                                            stride, dim, pl.kp, qb, tb, qn, tn, flags, n_keep);
     MK_LAUNCH_CHECK("knn_tc_prep_kernel");
-    g_launches.fetch_add(1, std::memory_order_relaxed);
     alignas(64) CUtensorMap map_q, map_t;
     int rc = make_map(&map_q, qb, nq, pl.kp, TC_M);
     if (rc != MK_OK) return rc;
