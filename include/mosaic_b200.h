@@ -89,15 +89,15 @@ int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, int dim, siz
 
 /* Batched form: many (query set, train set) pairs in one launch -- consecutive-frame pairs of
  * SequentialMosaic.match_features (mosaic.py:402-438) or all-pairs loop closure.
- *   desc       all descriptor rows of all sets, concatenated (same dim / row_stride)
+ *   desc       all descriptor rows of all sets, concatenated (same dim / row_stride); total_rows of them
  *   set_off    int32 [nsets+1] DEVICE: first row of each set
  *   pairs      int32 [npairs][2] DEVICE: (query set, train set)
  *   out_off    int32 [npairs+1] DEVICE: first output row of each pair (prefix sum of nq)
  *   max_nq / max_nt  upper bounds of the set sizes (host side, sizes the grid)
  *   idx/dist/keep     outputs over sum(nq) rows;  n_keep int32 [npairs] (may be NULL) */
-size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim);
+size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim, int total_rows);
 
-int mk_knn2_batched(int norm, const void *desc, int dim, size_t row_stride, const int32_t *set_off,
+int mk_knn2_batched(int norm, const void *desc, int total_rows, int dim, size_t row_stride, const int32_t *set_off,
                     const int32_t *pairs, int npairs, const int32_t *out_off, int max_nq, int max_nt,
                     int32_t *idx, float *dist, double ratio, uint8_t *keep, int32_t *n_keep,
                     void *workspace, size_t workspace_bytes, void *stream);

@@ -62,11 +62,11 @@ def lib() -> C.CDLL:
     L.mk_knn2_uses_tensor_cores.restype = i32
     L.mk_knn2_uses_tensor_cores.argtypes = [i32, i32, i32, i32]
     L.mk_knn2_batched_workspace_bytes.restype = sz
-    L.mk_knn2_batched_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.mk_knn2_batched_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
     L.mk_knn2.restype = i32
     L.mk_knn2.argtypes = [i32, vp, i32, vp, i32, i32, sz, vp, vp, f64, vp, vp, vp, sz, vp]
     L.mk_knn2_batched.restype = i32
-    L.mk_knn2_batched.argtypes = [i32, vp, i32, sz, vp, vp, i32, vp, i32, i32, vp, vp, f64, vp, vp, vp, sz, vp]
+    L.mk_knn2_batched.argtypes = [i32, vp, i32, i32, sz, vp, vp, i32, vp, i32, i32, vp, vp, f64, vp, vp, vp, sz, vp]
     L.mk_warp_perspective_u8.restype = i32
     L.mk_warp_perspective_u8.argtypes = [vp, i32, i32, i32, sz, vp, vp, i32, i32, sz, i32, vp]
     L.mk_mapper_update.restype = i32

@@ -47,8 +47,10 @@ struct KnnParams {
 
 // tensor-core path (mk_knn_tc.cu)
 size_t knn_tc_workspace_bytes(int nq, int nt, int dim);
+size_t knn_tc_batched_workspace_bytes(int npairs, int max_nq, int max_nt, int dim, int total_rows);
 bool knn_tc_supported(int norm, int nq, int nt, int dim);
-int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, int32_t *idx, float *dist, double ratio,
+int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
+               const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out);
 
 struct Problem {
@@ -514,11 +516,18 @@ extern "C" size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim)
 
 extern "C" int mk_knn2_uses_tensor_cores(int norm, int nq, int nt, int dim) { return use_tc(norm, nq, nt, dim) ? 1 : 0; }
 
-extern "C" size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim)
+static bool use_tc_batched(int norm, int npairs, int max_nq, int max_nt, int dim)
 {
-    (void)dim;
+    return knn_tc_supported(norm, max_nq, max_nt, dim) && (long)npairs * max_nq * max_nt >= 256L * 1024;
+}
+
+extern "C" size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim, int total_rows)
+{
     const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
-    return pl.ticket_bytes + pl.part_bytes;
+    size_t bytes = pl.ticket_bytes + pl.part_bytes;
+    if (use_tc_batched(norm, npairs, max_nq, max_nt, dim))
+        bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_batched_workspace_bytes(npairs, max_nq, max_nt, dim, total_rows);
+    return bytes;
 }
 
 extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t row_stride, int32_t *idx,
@@ -540,7 +549,7 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
         const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
-        rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, idx, dist, ratio, keep, n_keep,
+        rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, nullptr, nullptr, 1, nullptr, 0, idx, dist, ratio, keep, n_keep,
                         static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags);
         if (rc != MK_OK || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;   // dim*255^2 < 2^22: the TC result always stands
         P.guard = flags;
@@ -549,7 +558,7 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
     return run_knn(norm, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int mk_knn2_batched(int norm, const void *desc, int dim, size_t row_stride, const int32_t *set_off,
+extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int dim, size_t row_stride, const int32_t *set_off,
                                const int32_t *pairs, int npairs, const int32_t *out_off, int max_nq, int max_nt, int32_t *idx,
                                float *dist, double ratio, uint8_t *keep, int32_t *n_keep, void *workspace,
                                size_t workspace_bytes, void *stream)
@@ -567,5 +576,17 @@ extern "C" int mk_knn2_batched(int norm, const void *desc, int dim, size_t row_s
     P.set_off = set_off; P.pairs = pairs; P.out_off = out_off;
     P.nq = max_nq; P.nt = max_nt; P.dim = dim; P.stride = row_stride;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
+    if (total_rows > 0 && use_tc_batched(norm, npairs, max_nq, max_nt, dim)) {
+        const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
+        const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
+        if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2_batched: workspace too small"); return MK_ERR_WORKSPACE; }
+        const int *flags = nullptr;
+        rc = knn_tc_run(norm, desc, max_nq, nullptr, max_nt, dim, row_stride, set_off, pairs, npairs, out_off, total_rows, idx, dist,
+                        ratio, keep, n_keep, static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes,
+                        (cudaStream_t)stream, &flags);
+        if (rc != MK_OK || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
+        P.guard = flags;
+        return run_knn(norm, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+    }
     return run_knn(norm, P, npairs, max_nq, max_nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -44,7 +44,8 @@ struct TcParams {
     const __nv_bfloat16 *qb, *tb;   // bf16 copies [n][KP]
     const float *qn, *tn;           // squared norms
     int *flags;                     // see mk_common.cuh: flags[0] inputs not exact in bf16, flags[3] result needs the SIMT recompute
-    int nq, nt, kp, dim;
+    int nq, nt, kp, dim;            // single pair: sizes; batched: upper bounds
+    const int32_t *set_off, *pairs, *out_off;   // batched tables (device) or null: rows of qb == rows of tb == all sets
     int splits, nqb;
     unsigned long long *part;
     int *tickets;
@@ -166,11 +167,20 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     __shared__ int s_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int qblk = blockIdx.x, split = blockIdx.y;
+    const int qblk = blockIdx.x, split = blockIdx.y, z = blockIdx.z;
+    // problem of this CTA: rows [qrow0, qrow0 + nq) of the query matrix against rows [trow0, trow0 + nt) of the train matrix
+    int qrow0 = 0, trow0 = 0, nq = p.nq, nt = p.nt, out0 = 0;
+    if (p.pairs) {
+        const int qs = p.pairs[2 * z], ts = p.pairs[2 * z + 1];
+        qrow0 = p.set_off[qs]; nq = p.set_off[qs + 1] - qrow0;
+        trow0 = p.set_off[ts]; nt = p.set_off[ts + 1] - trow0;
+        out0 = p.out_off[z];
+    }
     const int q0 = qblk * TC_M;
+    if (q0 >= nq) return;
     const int nhalf = p.kp / TC_KA;                      // 1 (K <= 64) or 2 (K = 128)
     // train tiles of this split
-    const int ntiles = (p.nt + TC_N - 1) / TC_N;
+    const int ntiles = (nt + TC_N - 1) / TC_N;
     const int per = (ntiles + p.splits - 1) / p.splits;
     const int tile_lo = min(ntiles, split * per), tile_hi = min(ntiles, tile_lo + per);
     const int my_tiles = tile_hi - tile_lo;
@@ -194,13 +204,13 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
-            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * TC_KA, q0, bar_a);
+            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * TC_KA, qrow0 + q0, bar_a);
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % TC_STAGES, use = i / TC_STAGES;
                 if (use > 0) mbar_wait(bar_bempty + s, (use - 1) & 1);
                 mbar_expect_tx(bar_bfull + s, (uint32_t)(nhalf * TcSmem::B_BYTES));
                 for (int h = 0; h < nhalf; ++h)
-                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * TC_KA, (tile_lo + i) * TC_N, bar_bfull + s);
+                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * TC_KA, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
             }
         }
     } else if (warp == 1) {
@@ -239,7 +249,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int row = quarter * 32 + lane;
         const int et = tid - 64;                           // index among the epilogue threads
         const int qi = q0 + row;
-        const int qn = (qi < p.nq) ? (int)p.qn[qi] : 0;    // exact integer
+        const int qn = (qi < nq) ? (int)p.qn[qrow0 + qi] : 0;    // exact integer
         unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;   // running (d^2 << 32 | train index)
         int *s_T0 = reinterpret_cast<int *>(smem + TcSmem::tn_off(0));
         for (int i = 0; i < my_tiles; ++i) {
@@ -247,7 +257,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const int col0 = (tile_lo + i) * TC_N;
             int *s_T = s_T0 + acc * TC_N;
             // per-column constant |t|^2 * 128 + (col & 127); INT_MAX beyond nt (S = 0 there, so the key stays INT_MAX)
-            if (et < TC_N) s_T[et] = (col0 + et < p.nt) ? ((int)p.tn[col0 + et] * 128 + (et % TC_CW)) : 0x7fffffff;
+            if (et < TC_N) s_T[et] = (col0 + et < nt) ? ((int)p.tn[trow0 + col0 + et] * 128 + (et % TC_CW)) : 0x7fffffff;
+            const bool partial = col0 + TC_N > nt;        // the tile's tail columns belong to another set (batched) or are zero fill
             asm volatile("bar.sync 1, %0;\n" ::"n"(TC_EPI_THREADS) : "memory");
             mbar_wait(bar_tfull + acc, acc_use & 1);
             tc_fence_after();
@@ -266,7 +277,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int bits = __float_as_int(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
-                        const int key = bits * -256 + tv[u];
+                        int key = bits * -256 + tv[u];
+                        if (partial) key = (tv[u] == 0x7fffffff) ? 0x7fffffff : key;   // warp-uniform branch, last tile only
                         b2 = min(b2, max(b1, key));
                         b1 = min(b1, key);
                     }
@@ -310,14 +322,15 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
     }
     if (p.splits > 1) {
-        unsigned long long *base = p.part + ((size_t)qblk * p.splits) * TC_M * 2;
+        const size_t blk = (size_t)z * p.nqb + qblk;
+        unsigned long long *base = p.part + (blk * p.splits) * TC_M * 2;
         if (is_row_thread) {
             unsigned long long *mine = base + ((size_t)split * TC_M + tid) * 2;
             mine[0] = k1; mine[1] = k2;
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_flag = (atomicAdd(&p.tickets[qblk], 1) == p.splits - 1);
+        if (tid == 0) s_flag = (atomicAdd(&p.tickets[blk], 1) == p.splits - 1);
         __syncthreads();
         if (!s_flag) return;
         __threadfence();
@@ -330,24 +343,25 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
             }
         }
-        if (tid == 0) p.tickets[qblk] = 0;
+        if (tid == 0) p.tickets[blk] = 0;
     }
     bool kept = false;
     const int qi = q0 + tid;
-    if (is_row_thread && qi < p.nq) {
+    if (is_row_thread && qi < nq) {
+        const size_t o = (size_t)out0 + qi;
         int i1, i2; float d1, d2;
         TcKey::decode(k1, i1, d1);
         TcKey::decode(k2, i2, d2);
         if ((k1 != TcKey::NONE && (uint32_t)(k1 >> 32) >= 4194304u) || (k2 != TcKey::NONE && (uint32_t)(k2 >> 32) >= 4194304u))
             atomicOr(p.flags + 3, 1);                      // sqrtf no longer injective: let the SIMT kernel redo the call
-        p.idx[2 * (size_t)qi] = i1; p.idx[2 * (size_t)qi + 1] = i2;
-        p.dist[2 * (size_t)qi] = d1; p.dist[2 * (size_t)qi + 1] = d2;
+        p.idx[2 * o] = i1; p.idx[2 * o + 1] = i2;
+        p.dist[2 * o] = d1; p.dist[2 * o + 1] = d2;
         kept = (i2 >= 0) && (p.ratio > 0.0) && ((double)d1 < p.ratio * (double)d2);   // mosaic.py:430
-        if (p.keep) p.keep[qi] = kept ? 1 : 0;
+        if (p.keep) p.keep[o] = kept ? 1 : 0;
     }
     if (p.n_keep && tid < TC_M) {
         const unsigned b = __ballot_sync(0xffffffffu, kept);
-        if (lane == 0 && b) atomicAdd(p.n_keep, __popc(b));
+        if (lane == 0 && b) atomicAdd(p.n_keep + z, __popc(b));
     }
 }
 
@@ -418,20 +432,21 @@ struct TcPlan {
     size_t off_qb, off_tb, off_qn, off_tn, off_flags, off_tickets, off_part, total;
 };
 
-static TcPlan tc_plan(int nq, int nt, int dim)
+// rows_q / rows_t: rows of the bf16 copies (batched: both = all rows of all sets and the copies are shared)
+static TcPlan tc_plan(int npairs, int max_nq, int max_nt, int dim, long rows_q, long rows_t, bool shared)
 {
     TcPlan pl;
     pl.kp = dim <= 64 ? 64 : 128;
-    pl.nqb = (nq + TC_M - 1) / TC_M;
-    const int ntiles = (nt + TC_N - 1) / TC_N;
+    pl.nqb = (max_nq + TC_M - 1) / TC_M;
+    const int ntiles = (max_nt + TC_N - 1) / TC_N;
     // one CTA per SM (165 KB of shared memory).  Cost model: waves x (tiles per CTA + 4); the constant stands for the A tile,
-    // the prologue and the cold-threshold phase every (CTA, row) scan starts with, so long scans are preferred.
+    // the prologue and the merge, so long scans are preferred.
     int best = 1;
     double best_cost = 1e300;
     for (int s = 1; s <= ntiles && s <= 64; ++s) {
         const int per = (ntiles + s - 1) / s;
         const int s_eff = (ntiles + per - 1) / per;
-        const long ctas = (long)pl.nqb * s_eff;
+        const long ctas = (long)npairs * pl.nqb * s_eff;
         const long waves = (ctas + 147) / 148;
         const double cost = (double)waves * (per + 4.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = s_eff; }
@@ -439,18 +454,23 @@ static TcPlan tc_plan(int nq, int nt, int dim)
     pl.splits = pl.nqb > 0 ? best : 1;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-    pl.off_qb = take((size_t)nq * pl.kp * 2);
-    pl.off_tb = take((size_t)nt * pl.kp * 2);
-    pl.off_qn = take((size_t)nq * 4);
-    pl.off_tn = take((size_t)nt * 4);
+    pl.off_qb = take((size_t)rows_q * pl.kp * 2);
+    pl.off_tb = shared ? pl.off_qb : take((size_t)rows_t * pl.kp * 2);
+    pl.off_qn = take((size_t)rows_q * 4);
+    pl.off_tn = shared ? pl.off_qn : take((size_t)rows_t * 4);
     pl.off_flags = take(256);
-    pl.off_tickets = take((size_t)(pl.nqb > 0 ? pl.nqb : 1) * 4);
-    pl.off_part = take(pl.splits > 1 ? (size_t)pl.nqb * pl.splits * TC_M * 2 * 8 : 0);
+    const size_t blocks = (size_t)(npairs > 0 ? npairs : 1) * (pl.nqb > 0 ? pl.nqb : 1);
+    pl.off_tickets = take(blocks * 4);
+    pl.off_part = take(pl.splits > 1 ? blocks * pl.splits * TC_M * 2 * 8 : 0);
     pl.total = o;
     return pl;
 }
 
-size_t knn_tc_workspace_bytes(int nq, int nt, int dim) { return tc_plan(nq, nt, dim).total; }
+size_t knn_tc_workspace_bytes(int nq, int nt, int dim) { return tc_plan(1, nq, nt, dim, nq, nt, false).total; }
+size_t knn_tc_batched_workspace_bytes(int npairs, int max_nq, int max_nt, int dim, int total_rows)
+{
+    return tc_plan(npairs, max_nq, max_nt, dim, total_rows, total_rows, true).total;
+}
 
 bool knn_tc_supported(int norm, int nq, int nt, int dim)
 {
@@ -459,36 +479,42 @@ bool knn_tc_supported(int norm, int nq, int nt, int dim)
     return true;
 }
 
-// Launches prep + the TC kernel.  `flags` (device int) ends up non-zero when the inputs are not integer-valued
-// in [0,255]; the caller then runs the SIMT kernel guarded by the same flag (see mk_knn.cu).
-int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, int32_t *idx, float *dist, double ratio,
+// Launches prep + the TC kernel.  Single pair: q / t are the two row sets.  Batched: q = all rows of all sets (t unused),
+// set_off / pairs / out_off are the device tables of mk_knn2_batched.  *flags_out lets the caller guard the SIMT fallback.
+int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
+               const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out)
 {
-    const TcPlan pl = tc_plan(nq, nt, dim);
+    const bool batched = pairs != nullptr;
+    const TcPlan pl = batched ? tc_plan(npairs, nq, nt, dim, total_rows, total_rows, true) : tc_plan(1, nq, nt, dim, nq, nt, false);
     if (workspace_bytes < pl.total) { set_error("mk_knn2: workspace too small for the tensor-core path (%zu < %zu)", workspace_bytes, pl.total); return MK_ERR_WORKSPACE; }
     uint8_t *ws = static_cast<uint8_t *>(workspace);
     if (!aligned(ws, 256)) { set_error("mk_knn2: workspace must be 256-byte aligned for the tensor-core path"); return MK_ERR_ALIGN; }
     __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_qb), *tb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_tb);
     float *qn = reinterpret_cast<float *>(ws + pl.off_qn), *tn = reinterpret_cast<float *>(ws + pl.off_tn);
     int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
+    const int np = batched ? npairs : 1;
     // flags and tickets are adjacent in the workspace: one memset
-    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)pl.nqb * 4, st));
-    const int wpb = 8, rows = nq + nt;
+    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4, st));
+    if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
+    const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
+    const int wpb = 8, rows = rows_q + rows_t;
     if (norm == MK_NORM_L2_F32)
-        knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), nq, static_cast<const float *>(t), nt,
-                                                                          stride, dim, pl.kp, qb, tb, qn, tn, flags, n_keep);
+        knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), rows_q, static_cast<const float *>(t), rows_t,
+                                                                          stride, dim, pl.kp, qb, tb, qn, tn, flags, batched ? nullptr : n_keep);
     else
-        knn_tc_prep_kernel<uint8_t><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), nq, static_cast<const uint8_t *>(t), nt,
-                                                                            stride, dim, pl.kp, qb, tb, qn, tn, flags, n_keep);
+        knn_tc_prep_kernel<uint8_t><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t,
+                                                                            stride, dim, pl.kp, qb, tb, qn, tn, flags, batched ? nullptr : n_keep);
     MK_LAUNCH_CHECK("knn_tc_prep_kernel");
     alignas(64) CUtensorMap map_q, map_t;
-    int rc = make_map(&map_q, qb, nq, pl.kp, TC_M);
+    int rc = make_map(&map_q, qb, rows_q, pl.kp, TC_M);
     if (rc != MK_OK) return rc;
-    rc = make_map(&map_t, tb, nt, pl.kp, TC_N);
+    rc = make_map(&map_t, tb, batched ? total_rows : nt, pl.kp, TC_N);
     if (rc != MK_OK) return rc;
     TcParams P;
     P.qb = qb; P.tb = tb; P.qn = qn; P.tn = tn; P.flags = flags;
     P.nq = nq; P.nt = nt; P.kp = pl.kp; P.dim = dim; P.splits = pl.splits; P.nqb = pl.nqb;
+    P.set_off = set_off; P.pairs = pairs; P.out_off = out_off;
     P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
     static std::atomic<int> configured{-1};
@@ -499,7 +525,7 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
         MK_CUDA_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured.store(dev);
     }
-    dim3 grid(pl.nqb, pl.splits);
+    dim3 grid(pl.nqb, pl.splits, np);
     knn2_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
     MK_LAUNCH_CHECK("knn2_tc_kernel");
     *flags_out = flags;

@@ -221,6 +221,50 @@ class Matcher:
         keep = hb[off_keep: off_keep + nq].astype(bool)
         return idx, dist, keep
 
+    def knn_match_sets(self, sets: Sequence[np.ndarray], pairs: Sequence[tuple[int, int]], ratio: float = 0.7):
+        """Many (query set, train set) pairs in ONE launch: the consecutive-frame loop of
+        SequentialMosaic.match_features (mosaic.py:402-438: query = frame k+1, train = frame k) or all-pairs loop closure.
+        sets: descriptor arrays of equal width / dtype; pairs: (query index, train index) into `sets`.
+        -> list of (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) per pair (same values as knn_match_arrays)."""
+        device = _cuda_device(self._device)
+        if not len(pairs):
+            return []
+        arrs = [np.ascontiguousarray(a) for a in sets]
+        dtype, dim = arrs[0].dtype, arrs[0].shape[1]
+        if any(a.dtype != dtype or a.ndim != 2 or a.shape[1] != dim for a in arrs):
+            raise _bad_input("all descriptor sets must share dtype and width")
+        code = _norm_code(self._norm, dtype)
+        sizes = np.array([a.shape[0] for a in arrs], np.int64)
+        total = int(sizes.sum())
+        desc, _ = upload_descriptors(np.concatenate(arrs) if total else np.zeros((0, dim), dtype), device)
+        set_off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)).to(device)
+        pr = np.asarray(pairs, np.int32).reshape(-1, 2)
+        nq_per = sizes[pr[:, 0]]
+        out_off_h = np.concatenate([[0], np.cumsum(nq_per)]).astype(np.int32)
+        rows = int(out_off_h[-1])
+        max_nq, max_nt = int(nq_per.max()), int(sizes[pr[:, 1]].max())
+        pairs_d, out_off = torch.from_numpy(pr).to(device), torch.from_numpy(out_off_h).to(device)
+        idx = torch.empty((rows, 2), dtype=torch.int32, device=device)
+        dist = torch.empty((rows, 2), dtype=torch.float32, device=device)
+        keep = torch.empty((rows,), dtype=torch.uint8, device=device)
+        L = self._matcher["lib"]
+        out = []
+        CH = 65535                                   # grid.z limit per launch
+        for lo in range(0, len(pr), CH):
+            hi = min(len(pr), lo + CH)
+            ws = self._workspace(L.mk_knn2_batched_workspace_bytes(code, hi - lo, max_nq, max_nt, dim, total), device)
+            stride = desc.stride(0) * desc.element_size()
+            base = int(out_off_h[lo])
+            _lib.check(L.mk_knn2_batched(code, desc.data_ptr(), total, dim, stride, set_off.data_ptr(),
+                                         pairs_d.data_ptr() + lo * 8, hi - lo, out_off.data_ptr() + lo * 4, max_nq, max_nt,
+                                         idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), None,
+                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+        idx_h, dist_h, keep_h = idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool)
+        for p in range(len(pr)):
+            sl = slice(out_off_h[p], out_off_h[p + 1])
+            out.append((idx_h[sl], dist_h[sl], keep_h[sl]))
+        return out
+
     # -- reference API ---------------------------------------------------------------------------
     def knn_match(self, query: np.ndarray, train: np.ndarray, mask: np.ndarray = None) -> Sequence[Sequence[DMatch]]:
         """registration.py:233-242: cv2.BFMatcher.knnMatch(query, train, k=2, mask=mask)."""

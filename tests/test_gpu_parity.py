@@ -133,9 +133,9 @@ def test_knn_batched_vs_single():
         dist = torch.empty((total, 2), dtype=torch.float32, device="cuda")
         keep = torch.empty((total,), dtype=torch.uint8, device="cuda")
         nk = torch.zeros((len(pairs_h),), dtype=torch.int32, device="cuda")
-        wsb = L.mk_knn2_batched_workspace_bytes(code, len(pairs_h), max(sizes), max(sizes), 32)
+        wsb = L.mk_knn2_batched_workspace_bytes(code, len(pairs_h), max(sizes), max(sizes), 32, int(sum(sizes)))
         ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device="cuda")
-        mb._lib.check(L.mk_knn2_batched(code, desc.data_ptr(), 32, 32, set_off.data_ptr(), pairs.data_ptr(), len(pairs_h),
+        mb._lib.check(L.mk_knn2_batched(code, desc.data_ptr(), int(sum(sizes)), 32, 32, set_off.data_ptr(), pairs.data_ptr(), len(pairs_h),
                                         out_off.data_ptr(), max(sizes), max(sizes), idx.data_ptr(), dist.data_ptr(), 0.7,
                                         keep.data_ptr(), nk.data_ptr(), ws.data_ptr(), ws.numel(),
                                         torch.cuda.current_stream().cuda_stream))
@@ -146,6 +146,29 @@ def test_knn_batched_vs_single():
             assert np.array_equal(idx[sl], oi) and np.array_equal(dist[sl], od)
             ok = orc.ratio_test(oi, od, 0.7)
             assert np.array_equal(keep[sl], ok) and nk[p] == ok.sum()
+
+
+@pytest.mark.parametrize("kind", ["sift_int", "orb_l2", "orb_hamming", "f32_generic"])
+def test_knn_match_sets_vs_oracle(kind):
+    """Batched matching (consecutive pairs + a few loop-closure pairs, ragged set sizes) through the Python API; the
+    L2 cases run on the batched tcgen05 path (shared bf16 copy, masked partial tiles), generic floats on the SIMT one."""
+    rng = np.random.default_rng(17)
+    sizes = [700, 300, 1030, 2, 513, 900]
+    if kind == "sift_int":
+        sets = [rng.integers(0, 140, (n, 128)).astype(np.float32) for n in sizes]; norm = "l2"
+    elif kind == "f32_generic":
+        sets = [rng.standard_normal((n, 128)).astype(np.float32) for n in sizes]; norm = "l2"
+    else:
+        sets = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in sizes]; norm = "l2" if kind == "orb_l2" else "hamming"
+    sets[2][5] = sets[0][9]; sets[2][77] = sets[0][9]          # planted exact ties across sets
+    pairs = [(k + 1, k) for k in range(len(sizes) - 1)] + [(0, 2), (5, 0), (2, 2)]
+    res = mb.Matcher(norm=norm).knn_match_sets(sets, pairs, 0.7)
+    assert len(res) == len(pairs)
+    for (a, b), (idx, dist, keep) in zip(pairs, res):
+        oi, od = orc.knn2(sets[a], sets[b], norm)
+        assert np.array_equal(idx, oi), (kind, a, b)
+        assert np.array_equal(dist, od), (kind, a, b)
+        assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
 
 
 # ------------------------------------------------------------------------------------------------
