@@ -333,3 +333,49 @@ def test_mapper_full_size_properties():
     got = after[wy0:wy0 + win.shape[0], wx0:wx0 + win.shape[1]].cpu().numpy()
     assert np.abs(got.astype(int) - win.astype(int)).max() <= 1                                                # (d) +-1 LSB
     assert (got != win).mean() < 1e-3
+
+
+def test_mapper_unaligned_source_takes_the_global_path():
+    """C ABI with a source that is only 4-byte aligned (pitch % 16 != 0): no bulk-copy staging, exact global sampling."""
+    rng = np.random.default_rng(41)
+    h, w = 97, 131
+    img = _img(rng, h, w)
+    pitch = w * 3 + 7                               # 400: multiple of 4, not of 16
+    pitch += (-pitch) % 4
+    if pitch % 16 == 0:
+        pitch += 4
+    buf = torch.zeros(h * pitch + 64, dtype=torch.uint8, device="cuda")
+    off = 4 if buf.data_ptr() % 16 == 0 else 0      # make the base address 4-byte but not 16-byte aligned
+    view = buf[off: off + h * pitch].view(h, pitch)
+    view[:, : w * 3] = torch.from_numpy(img.reshape(h, w * 3)).cuda()
+    Hc, Wc = 300, 400
+    canvas = torch.zeros((Hc, 1280), dtype=torch.uint8, device="cuda"); cmask = torch.zeros((Hc, 512), dtype=torch.uint8, device="cuda")
+    ocanvas = np.zeros((Hc, Wc, 3), np.uint8); omask = np.zeros((Hc, Wc), np.uint8)
+    L = mb._lib.lib()
+    for k in range(3):
+        H = _rand_H(rng, 2e-4, 250, 180, 0.8, 1.4)
+        Hm = np.ascontiguousarray(H)
+        mb._lib.check(L.mk_mapper_update(canvas.data_ptr(), 1280, cmask.data_ptr(), 512, None, 0, Hc, Wc, view.data_ptr(), h, w, pitch,
+                                         None, 0, Hm.ctypes.data, 0.5, 1, 0, 0.0, None, torch.cuda.current_stream().cuda_stream))
+        orc.mapper_update(ocanvas, omask, img, H, 0.5, 1)
+    assert np.array_equal(canvas[:, : Wc * 3].cpu().numpy().reshape(Hc, Wc, 3), ocanvas)
+    assert np.array_equal(cmask[:, :Wc].cpu().numpy(), omask)
+
+
+@pytest.mark.parametrize("interp,code", [("linear", 1), ("cubic", 2)])
+def test_mapper_strong_perspective_and_horizon(interp, code):
+    """Homographies whose denominator changes sign inside the canvas (tiles fall back to global sampling, W = 0 -> 0 like
+    cv2), extreme minification (staged rectangle larger than shared memory) and magnification."""
+    rng = np.random.default_rng(43)
+    img = _img(rng, 120, 160)
+    Hs = [np.array([[1.0, 0.1, 30.0], [0.05, 1.0, 20.0], [4e-3, 1e-3, 1.0]]),           # horizon crosses the canvas
+          np.array([[1.0, 0.0, 100.0], [0.0, 1.0, 80.0], [-6e-3, 2e-3, 1.0]]),
+          np.array([[0.05, 0.0, 150.0], [0.0, 0.05, 100.0], [0.0, 0.0, 1.0]]),           # 20x minification
+          np.array([[3.7, 0.4, -50.0], [-0.3, 3.9, -40.0], [1e-4, 0.0, 1.0]])]           # magnification
+    mp = mb.Mapper(517, 333, alpha_blend=0.5, interp=interp)
+    canvas = np.zeros((333, 517, 3), np.uint8); cmask = np.zeros((333, 517), np.uint8)
+    for k, H in enumerate(Hs):
+        mp.update(img, H)
+        orc.mapper_update(canvas, cmask, img, H, 0.5, code)
+        assert np.array_equal(mp.output, canvas), k
+        assert np.array_equal(mp.mask, cmask), k
