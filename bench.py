@@ -11,9 +11,10 @@ N = 1  : BASELINE configs[1] -- 1920x1080 synthetic sequence with known homograp
          5000 x 32 B descriptors (Hamming), 16384 x 16384 canvas.  Blend = Mapper alpha semantics
          (the reference's own, parity-checked bit for bit); the feather extension is timed too and
          reported under "feather".
-N > 1  : BASELINE configs[3] -- the canvas is a grid of 16384 x 16384 tiles sharded over the ranks
-         (mosaic.py:595-622 tiling), every rank ingests its own 3840x2160 frame stream, frames are routed
-         by warped footprint (NCCL send/recv), homographies are all-gathered.  Weak scaling.
+N > 1  : the same per-GPU workload, tile-sharded like BASELINE configs[3]: the canvas is a grid of
+         16384 x 16384 tiles owned by the ranks (mosaic.py:595-622 tiling), every rank ingests its own
+         1920x1080 frame stream over its own tile, frames whose warped footprint crosses a seam are also
+         sent to the neighbour (NCCL send/recv), all poses are all-gathered once.  Weak scaling.
 
 value  : frames/s with inputs resident in HBM, per-step CUDA events, L2 flushed between steps.
 e2e    : frames/s through the reference-facing API (Matcher.knn_match_arrays + Mapper.update) with
@@ -152,7 +153,7 @@ def run_b200(args):
     K, W = args.steps, args.warmup
     nframes = K + W
     multi = world > 1
-    fw, fh = (3840, 2160) if multi else (1920, 1080)
+    fw, fh = 1920, 1080      # the same per-GPU workload at every N (weak scaling): BASELINE configs[1] frames
     # ---------------- data (all resident in HBM before any timed region) ----------------
     tile = (CANVAS, CANVAS)
     if multi:
@@ -167,7 +168,7 @@ def run_b200(args):
     for k in range(nframes):
         H = trajectory(k, fw, fh, CANVAS)
         if multi:   # shift the path so that it straddles the seam to the right-hand / lower neighbour
-            H = H.copy(); H[0, 2] += origin[0] + 0.25 * CANVAS; H[1, 2] += origin[1]
+            H = H.copy(); H[0, 2] += origin[0] + 0.38 * CANVAS; H[1, 2] += origin[1]   # ~25 % of the frames straddle the seam
             H[0, 2] = min(H[0, 2], grid[0] * CANVAS - 1.2 * fw)
         Hs.append(H)
     frames = []
@@ -302,8 +303,8 @@ def run_b200(args):
             "workload": ("BASELINE configs[1]: 1920x1080 synthetic sequence, 5000x32B ORB-like descriptors (Hamming kNN k=2 + ratio 0.7), "
                          "fused warp(INTER_LINEAR)+blend(alpha=0.5, reference Mapper semantics) into a 16384x16384 canvas")
             if not multi else
-            (f"BASELINE configs[3]: {grid[0]}x{grid[1]} tiles of 16384^2 sharded over {world} GPUs, 3840x2160 frames per rank routed by "
-             "warped footprint (NCCL send/recv), homographies all-gathered, 5000x32B Hamming kNN per frame"),
+            (f"BASELINE configs[1] per GPU, tile-sharded as in configs[3]: {grid[0]}x{grid[1]} tiles of 16384^2 over {world} GPUs, one 1920x1080 "
+             "frame stream per rank, frames routed by warped footprint (NCCL send/recv), poses all-gathered once, 5000x32B Hamming kNN per frame"),
             "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events); inputs {nframes * fh * fw * 3 / 1e9:.2f} GB > L2",
             "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
             "blend": "alpha", "interp": "linear", "canvas": [grid[0] * CANVAS, grid[1] * CANVAS], "frame": [fw, fh],
