@@ -22,7 +22,7 @@ BLEND_ALPHA, BLEND_FEATHER = 0, 1
 EXPORTS = (
     "mk_abi_version", "mk_version_string", "mk_last_error", "mk_launch_count",
     "mk_knn2_workspace_bytes", "mk_knn2_uses_tensor_cores", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
-    "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
+    "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
 )
 
 
@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
     L.mk_mapper_update.restype = i32
     L.mk_mapper_update.argtypes = [vp, sz, vp, sz, vp, sz, i32, i32, vp, i32, i32, sz, vp, sz, vp, f64, i32, i32,
                                    C.c_float, vp, vp]
+    L.mk_mapper_update_batch.restype = i32
+    L.mk_mapper_update_batch.argtypes = [vp, sz, vp, sz, vp, sz, i32, i32, i32, vp, vp, vp, vp, vp, f64, i32, i32, C.c_float, vp]
     L.mk_upload_2d.restype = i32
     L.mk_upload_2d.argtypes = [vp, sz, vp, sz, sz, sz, vp]
     L.mk_download_2d.restype = i32

@@ -21,8 +21,12 @@
 #include "mk_sample.cuh"
 
 #include <math.h>
+
+#include <algorithm>
+#include <array>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 namespace mk {
 
@@ -35,19 +39,31 @@ constexpr int MTHREADS = 256;       // K4 (512 threads per tile measured 30-50 %
 constexpr int ROWB = TW * 3;       // canvas bytes per tile row
 constexpr int ROWV = ROWB / 16;    // 16-byte vectors per tile row
 
+// one frame to composite
+struct FrameDesc {
+    const uint8_t *src, *roi;
+    unsigned long long spitch, rpitch;
+    int h, w;
+    int src_aligned;     // src 16-byte aligned with pitch % 16 == 0 (needed for the bulk-copy staging)
+    int pad_;
+    InvMap M;
+};
+
 struct MapperParams {
     uint8_t *canvas, *cmask;
     float *wacc;
-    const uint8_t *src, *roi;
     const short *cubic;
     const uint2 *lut;
-    unsigned long long cpitch, mpitch, wpitch, spitch, rpitch;
-    int Hc, Wc, h, w;
+    unsigned long long cpitch, mpitch, wpitch;
+    int Hc, Wc;
     int tx0, ty0;
-    InvMap M;
     float alpha, beta, ramp;
     int src_smem_bytes;  // dynamic shared memory available for the staged source rectangle
-    int src_aligned;     // src 16-byte aligned with pitch % 16 == 0 (needed for 16-byte cp.async)
+    FrameDesc f0;        // single-frame launch: the frame, passed by value
+    // batched launch (mk_mapper_update_batch): CTA b owns canvas tile tile_xy[b] and applies, in order, the frames
+    // tile_frame[tile_ptr[b] .. tile_ptr[b+1])  -- the "gather" formulation: the canvas tile is read and written once
+    const FrameDesc *frames;
+    const int *tile_ptr, *tile_frame, *tile_xy;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int nbytes)
@@ -147,7 +163,7 @@ __device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float 
     return o0 | (o1 << 8) | (o2 << 16);
 }
 
-template <int INTERP, int BLEND, bool ROI>
+template <int INTERP, int BLEND, bool ROI, bool BATCH>
 __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
@@ -165,16 +181,37 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
     __shared__ float s_wgt[BLEND == MK_BLEND_FEATHER ? TH : 1][BLEND == MK_BLEND_FEATHER ? TW : 1];
     extern __shared__ __align__(16) uint8_t s_src[];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tileX = (p.tx0 + (int)blockIdx.x) * TW, tileY = (p.ty0 + (int)blockIdx.y) * TH;
-    const int nvec = min(ROWV, ((p.Wc - tileX) * 3 + 15) >> 4);  // 16-byte vectors holding canvas pixels
+    __shared__ FrameDesc s_frame;
+    __shared__ unsigned s_rowchg;   // bit r: canvas row r of the tile changed (write-back mask)
 
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tileX, tileY, nfr = 1, list0 = 0;
+    if constexpr (BATCH) {
+        tileX = p.tile_xy[2 * blockIdx.x] * TW; tileY = p.tile_xy[2 * blockIdx.x + 1] * TH;
+        list0 = p.tile_ptr[blockIdx.x]; nfr = p.tile_ptr[blockIdx.x + 1] - list0;
+    } else {
+        tileX = (p.tx0 + (int)blockIdx.x) * TW; tileY = (p.ty0 + (int)blockIdx.y) * TH;
+    }
+    const int nvec = min(ROWV, ((p.Wc - tileX) * 3 + 15) >> 4);  // 16-byte vectors holding canvas pixels
+    const FrameDesc &F = *(BATCH ? &s_frame : &p.f0);
+    if (tid == 160) { mbar_init(&s_bar, 1); s_rowchg = 0u; }
+    bool canvas_loaded = false;
+    uint32_t parity = 0;
+
+#pragma unroll 1
+    for (int fi = 0; fi < nfr; ++fi) {
+    if constexpr (BATCH) {
+        __syncthreads();            // everyone is done with the previous frame's shared state
+        if (tid < (int)(sizeof(FrameDesc) / 4))
+            reinterpret_cast<uint32_t *>(&s_frame)[tid] = reinterpret_cast<const uint32_t *>(p.frames + p.tile_frame[list0 + fi])[tid];
+        __syncthreads();
+    }
     // ---- per-row coordinate bases for the left / centre / right 64-px blocks, and the source
     //      positions of the four corners of the haloed tile ---------------------------------------
     if (tid < 3 * EH) {
         const int b = tid / EH, r = tid - b * EH;
         double X0, Y0, W0;
-        row_base(p.M, tileX + (b - 1) * BLOCK_W, tileY - HALO + r, X0, Y0, W0);
+        row_base(F.M, tileX + (b - 1) * BLOCK_W, tileY - HALO + r, X0, Y0, W0);
         s_row[b][r][0] = X0; s_row[b][r][1] = Y0; s_row[b][r][2] = W0;
         if (b == 0) s_m0[r] = ~0ull;   // rows / columns outside the canvas count as set (cv2.erode's default border)
     } else if (tid >= 128 && tid < 132) {
@@ -182,15 +219,13 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         const int x0 = (c & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (c & 1) ? HALO - 1 : BLOCK_W - HALO;
         const int y = (c & 2) ? tileY + TH + HALO - 1 : tileY - HALO;
         double X0, Y0, W0;
-        row_base(p.M, x0, y, X0, Y0, W0);
+        row_base(F.M, x0, y, X0, Y0, W0);
         const double dx1 = (double)x1;
         int X, Y;
-        quantize(p.M, X0, Y0, W0, dmul(p.M.m[0], dx1), dmul(p.M.m[3], dx1), dmul(p.M.m[6], dx1), X, Y);
-        const double W = p.M.affine ? p.M.m[8] : dadd(W0, dmul(p.M.m[6], dx1));
+        quantize(F.M, X0, Y0, W0, dmul(F.M.m[0], dx1), dmul(F.M.m[3], dx1), dmul(F.M.m[6], dx1), X, Y);
+        const double W = F.M.affine ? F.M.m[8] : dadd(W0, dmul(F.M.m[6], dx1));
         const bool sane = abs(X) < (1 << 30) && abs(Y) < (1 << 30);   // far from cvt saturation
         s_corner[c][0] = X; s_corner[c][1] = Y; s_corner[c][2] = !sane ? 0 : ((W > 0.0) ? 1 : ((W < 0.0) ? -1 : 0));
-    } else if (tid == 160) {
-        mbar_init(&s_bar, 1);
     }
     __syncthreads();
 
@@ -207,14 +242,14 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         int sy_hi = max(max(s_corner[0][1], s_corner[1][1]), max(s_corner[2][1], s_corner[3][1])) >> 5;
         constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;  // tap reach + 1 px safety ring
         sx_lo -= LO; sy_lo -= LO; sx_hi += HI; sy_hi += HI;
-        if (convex && (sx_hi < 0 || sy_hi < 0 || sx_lo > p.w - 1 || sy_lo > p.h - 1)) return;  // tile misses the frame
+        if (convex && (sx_hi < 0 || sy_hi < 0 || sx_lo > F.w - 1 || sy_lo > F.h - 1)) continue;  // tile misses this frame
         // the rectangle is NOT clamped to the frame: the part outside is zero-filled below, so that the fast sampler can
         // skip all containment tests (it is tile-sized by construction; the budget test below still guards the size)
         T.s = s_src; T.sy0 = sy_lo;
         T.bx0 = ((sx_lo * 3) >> 4) << 4;
         T.rowbytes = ((sx_hi * 3 + 3 - T.bx0) + 15) & ~15;
         T.R = sy_hi - sy_lo + 1;
-        use_smem = convex && p.src_aligned && T.R > 1 && T.R < 4096 && T.rowbytes > 0 && T.rowbytes < 16384 &&
+        use_smem = convex && F.src_aligned && T.R > 1 && T.R < 4096 && T.rowbytes > 0 && T.rowbytes < 16384 &&
                    T.R * T.rowbytes <= p.src_smem_bytes;
     }
 
@@ -223,35 +258,35 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
     //      ordinary stores (BORDER_CONSTANT 0), which only happens for tiles on the frame's edge ----
     {
         // bytes [c_lo, c_hi) of every staged row come from the frame by bulk copy
-        const int row_end16 = (p.w * 3) & ~15;
+        const int row_end16 = (F.w * 3) & ~15;
         const int c_lo = use_smem ? max(0, -T.bx0) : 0;
         const int c_hi = use_smem ? max(c_lo, min(T.rowbytes, row_end16 - T.bx0)) : 0;
-        const int r_lo = use_smem ? max(0, -T.sy0) : 0, r_hi = use_smem ? min(T.R, p.h - T.sy0) : 0;   // rows inside the frame
+        const int r_lo = use_smem ? max(0, -T.sy0) : 0, r_hi = use_smem ? min(T.R, F.h - T.sy0) : 0;   // rows inside the frame
         if (warp == 0) {
             if (c_hi > c_lo)
                 for (int r = r_lo + lane; r < r_hi; r += 32)
-                    bulk_g2s(s_src + r * T.rowbytes + c_lo, p.src + (size_t)(T.sy0 + r) * p.spitch + (T.bx0 + c_lo),
+                    bulk_g2s(s_src + r * T.rowbytes + c_lo, F.src + (size_t)(T.sy0 + r) * F.spitch + (T.bx0 + c_lo),
                              (uint32_t)(c_hi - c_lo), &s_bar);
         } else if (warp == 1) {
             const int y = tileY + lane;
-            if (y < p.Hc)
+            if (!canvas_loaded && y < p.Hc)
                 bulk_g2s(&s_canvas[lane][0], p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, (uint32_t)nvec * 16u, &s_bar);
         } else if (tid == 64) {
-            const int nrows_c = min(TH, p.Hc - tileY);
+            const int nrows_c = canvas_loaded ? 0 : min(TH, p.Hc - tileY);
             const uint32_t tx = (uint32_t)nrows_c * (uint32_t)nvec * 16u +
                                 ((c_hi > c_lo && r_hi > r_lo) ? (uint32_t)(r_hi - r_lo) * (uint32_t)(c_hi - c_lo) : 0u);
             mbar_arrive_expect_tx(&s_bar, tx);
         }
         if (use_smem && (c_lo > 0 || c_hi < T.rowbytes || r_lo > 0 || r_hi < T.R)) {
-            const int row_end = p.w * 3, nch = T.rowbytes >> 4;
+            const int row_end = F.w * 3, nch = T.rowbytes >> 4;
             for (int i = tid; i < T.R * nch; i += MTHREADS) {
                 const int r = i / nch, c = (i - r * nch) << 4;
                 if (r >= r_lo && r < r_hi && c >= c_lo && c < c_hi) continue;   // covered by the bulk copy
                 const int gy = T.sy0 + r, gb = T.bx0 + c;
                 uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                if (gy >= 0 && gy < p.h && gb + 15 >= 0 && gb < row_end) {       // chunk straddles the frame edge
+                if (gy >= 0 && gy < F.h && gb + 15 >= 0 && gb < row_end) {       // chunk straddles the frame edge
                     uint8_t *zb = reinterpret_cast<uint8_t *>(&z);
-                    const uint8_t *g = p.src + (size_t)gy * p.spitch;
+                    const uint8_t *g = F.src + (size_t)gy * F.spitch;
 #pragma unroll
                     for (int b = 0; b < 16; ++b)
                         if (gb + b >= 0 && gb + b < row_end) zb[b] = __ldg(g + gb + b);
@@ -259,7 +294,9 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
                 *reinterpret_cast<uint4 *>(s_src + r * T.rowbytes + c) = z;
             }
         }
-        mbar_wait(&s_bar, 0);
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        canvas_loaded = true;
         __syncthreads();
     }
 
@@ -268,7 +305,7 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         const int cx = (warp & 1) * 32 + lane, x = tileX + cx;
         const bool xvalid = x < p.Wc;
         const double dx1 = (double)cx;
-        const double mx = dmul(p.M.m[0], dx1), my = dmul(p.M.m[3], dx1), mw = dmul(p.M.m[6], dx1);
+        const double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
         // rows of the haloed tile that lie inside the canvas (the others keep their all-ones bit rows)
         const int r_lo = max(0, HALO - tileY), r_hi = min(EH, p.Hc - tileY + HALO);
         constexpr int RSTEP = MTHREADS / 64;   // rows advanced per pass: two warps cover one 64-px row
@@ -276,23 +313,23 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         if (r0 < r_lo) r0 += (r_lo - r0 + RSTEP - 1) / RSTEP * RSTEP;
         auto body = [&](auto fast_tag, auto affine_tag) {
             constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
-            const double wr = p.M.wr;
+            const double wr = F.M.wr;
 #pragma unroll 1
             for (int r = r0; r < r_hi; r += RSTEP) {
                 uint32_t px = 0, mv = 255;
                 float wg = 0.f;
                 if (xvalid) {
                     int X, Y;
-                    if constexpr (FAST) quantize_fast_t<AFF>(p.M, wr, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
-                    else quantize(p.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                    if constexpr (FAST) quantize_fast_t<AFF>(F.M, wr, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
+                    else quantize(F.M, s_row[1][r][0], s_row[1][r][1], s_row[1][r][2], mx, my, mw, X, Y);
                     if constexpr (FAST && INTERP == 1) px = sample_linear_c3_smem_fast(T, X, Y, p.lut);
-                    else px = sample_c3_tile<INTERP>(FAST, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
-                    if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
+                    else px = sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
+                    if constexpr (ROI) mv = sample<INTERP, 1>(F.roi, F.rpitch, F.h, F.w, X, Y, p.cubic);
                     else mv = px ? 255u : 0u;
                     if constexpr (BLEND == MK_BLEND_FEATHER) {
                         const float u = (float)X * 0.03125f, v = (float)Y * 0.03125f;
-                        const float e = fminf(fminf(__fadd_rn(u, 0.5f), __fsub_rn(__fsub_rn((float)p.w, 0.5f), u)),
-                                              fminf(__fadd_rn(v, 0.5f), __fsub_rn(__fsub_rn((float)p.h, 0.5f), v)));
+                        const float e = fminf(fminf(__fadd_rn(u, 0.5f), __fsub_rn(__fsub_rn((float)F.w, 0.5f), u)),
+                                              fminf(__fadd_rn(v, 0.5f), __fsub_rn(__fsub_rn((float)F.h, 0.5f), v)));
                         wg = fminf(1.f, fmaxf(0.f, __fdiv_rn(e, p.ramp)));
                     }
                 }
@@ -306,7 +343,7 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
             }
         };
         if (use_smem) {
-            if (p.M.affine) body(std::true_type{}, std::true_type{});
+            if (F.M.affine) body(std::true_type{}, std::true_type{});
             else body(std::true_type{}, std::false_type{});
         } else {
             body(std::false_type{}, std::false_type{});
@@ -325,10 +362,10 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
             const double dx1 = (double)x1;
             int X, Y;
-            quantize(p.M, s_row[b][r][0], s_row[b][r][1], s_row[b][r][2], dmul(p.M.m[0], dx1), dmul(p.M.m[3], dx1),
-                     dmul(p.M.m[6], dx1), X, Y);
-            if constexpr (ROI) mv = sample<INTERP, 1>(p.roi, p.rpitch, p.h, p.w, X, Y, p.cubic);
-            else mv = sample_c3_tile<INTERP>(use_smem, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
+            quantize(F.M, s_row[b][r][0], s_row[b][r][1], s_row[b][r][2], dmul(F.M.m[0], dx1), dmul(F.M.m[3], dx1),
+                     dmul(F.M.m[6], dx1), X, Y);
+            if constexpr (ROI) mv = sample<INTERP, 1>(F.roi, F.rpitch, F.h, F.w, X, Y, p.cubic);
+            else mv = sample_c3_tile<INTERP>(use_smem, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
         }
         s_side[r][c] = (uint8_t)mv;
         if constexpr (ROI) s_mval[r][(c < 2) ? c : TW + HALO + (c - 2)] = (uint8_t)mv;
@@ -426,13 +463,17 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
             if constexpr (BLEND == MK_BLEND_FEATHER) *reinterpret_cast<float4 *>(wp) = wa;
         }
     }
+    if (tid < TH && s_v[tid] != 0ull) atomicOr(&s_rowchg, 1u << tid);
+    }   // frames of this tile
+
+    if (!canvas_loaded) return;   // no frame touched this tile
     fence_proxy_async();   // make the generic-proxy writes to s_canvas visible to the bulk store engine
     __syncthreads();
 
     // ---- write back the rows that changed: one bulk store per row ------------------------------
     if (warp == 0) {
         const int y = tileY + lane;
-        if (y < p.Hc && s_v[lane] != 0ull)
+        if (y < p.Hc && ((s_rowchg >> lane) & 1u))
             bulk_s2g(p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, &s_canvas[lane][0], (uint32_t)nvec * 16u);
         bulk_commit_wait_read();
     }
@@ -646,29 +687,40 @@ static void footprint(int Hc, int Wc, int h, int w, const double *H, int interp,
 
 constexpr int MAX_SRC_SMEM = 96 * 1024;
 
-template <int INTERP, int BLEND, bool ROI>
+template <int INTERP, int BLEND, bool ROI, bool BATCH>
 static cudaError_t launch_mapper_inst(dim3 grid, cudaStream_t st, const MapperParams &P)
 {
     static std::atomic<int> configured{-1};  // device the attribute was last set on
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured.load(std::memory_order_acquire) != dev) {
-        cudaError_t e = cudaFuncSetAttribute(mapper_update_kernel<INTERP, BLEND, ROI>,
+        cudaError_t e = cudaFuncSetAttribute(mapper_update_kernel<INTERP, BLEND, ROI, BATCH>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SRC_SMEM);
         if (e != cudaSuccess) return e;
         configured.store(dev, std::memory_order_release);
     }
-    mapper_update_kernel<INTERP, BLEND, ROI><<<grid, MTHREADS, (size_t)P.src_smem_bytes, st>>>(P);
+    mapper_update_kernel<INTERP, BLEND, ROI, BATCH><<<grid, MTHREADS, (size_t)P.src_smem_bytes, st>>>(P);
     return cudaSuccess;
 }
 
 template <int INTERP, int BLEND>
-static cudaError_t launch_mapper(bool roi, dim3 grid, cudaStream_t st, const MapperParams &P)
+static cudaError_t launch_mapper(bool roi, bool batch, dim3 grid, cudaStream_t st, const MapperParams &P)
 {
+    if (batch) return launch_mapper_inst<INTERP, BLEND, false, true>(grid, st, P);
     if constexpr (BLEND == MK_BLEND_ALPHA) {
-        if (roi) return launch_mapper_inst<INTERP, BLEND, true>(grid, st, P);
+        if (roi) return launch_mapper_inst<INTERP, BLEND, true, false>(grid, st, P);
     }
-    return launch_mapper_inst<INTERP, BLEND, false>(grid, st, P);
+    return launch_mapper_inst<INTERP, BLEND, false, false>(grid, st, P);
+}
+
+static cudaError_t launch_mapper_any(int interp, int blend, bool roi, bool batch, dim3 grid, cudaStream_t st, const MapperParams &P)
+{
+    if (interp == MK_INTER_LINEAR) {
+        if (blend == MK_BLEND_ALPHA) return launch_mapper<MK_INTER_LINEAR, MK_BLEND_ALPHA>(roi, batch, grid, st, P);
+        return launch_mapper<MK_INTER_LINEAR, MK_BLEND_FEATHER>(false, batch, grid, st, P);
+    }
+    if (blend == MK_BLEND_ALPHA) return launch_mapper<MK_INTER_CUBIC, MK_BLEND_ALPHA>(roi, batch, grid, st, P);
+    return launch_mapper<MK_INTER_CUBIC, MK_BLEND_FEATHER>(false, batch, grid, st, P);
 }
 
 // Shared memory needed to stage the source rectangle of one haloed tile: evaluated (in plain double
@@ -758,11 +810,12 @@ extern "C" int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *c
     if (region_host) { region_host[0] = rect[0]; region_host[1] = rect[1]; region_host[2] = rect[2]; region_host[3] = rect[3]; }
     if (rect[2] <= rect[0]) return MK_OK;  // footprint misses the canvas: nothing to do
 
-    MapperParams P;
-    P.canvas = canvas; P.cmask = cmask; P.wacc = wacc; P.src = src; P.roi = roi; P.cubic = nullptr; P.lut = nullptr;
-    P.cpitch = canvas_pitch; P.mpitch = cmask_pitch; P.wpitch = wacc_pitch; P.spitch = src_pitch; P.rpitch = roi_pitch;
-    P.Hc = canvas_h; P.Wc = canvas_w; P.h = src_h; P.w = src_w;
-    make_invmap(H_host, P.M);
+    MapperParams P{};
+    P.canvas = canvas; P.cmask = cmask; P.wacc = wacc;
+    P.cpitch = canvas_pitch; P.mpitch = cmask_pitch; P.wpitch = wacc_pitch;
+    P.Hc = canvas_h; P.Wc = canvas_w;
+    P.f0.src = src; P.f0.roi = roi; P.f0.spitch = src_pitch; P.f0.rpitch = roi_pitch; P.f0.h = src_h; P.f0.w = src_w;
+    make_invmap(H_host, P.f0.M);
     P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp;
     {
         DeviceTables tb;
@@ -773,19 +826,113 @@ extern "C" int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *c
     P.tx0 = rect[0] / TW; P.ty0 = rect[1] / TH;
     const int tx1 = (rect[2] + TW - 1) / TW, ty1 = (rect[3] + TH - 1) / TH;
     dim3 grid(tx1 - P.tx0, ty1 - P.ty0);
-    P.src_aligned = (aligned(src, 16) && (src_pitch & 15) == 0) ? 1 : 0;
-    P.src_smem_bytes = P.src_aligned ? estimate_src_smem(P.M, rect, interp) : 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t le;
-    if (interp == MK_INTER_LINEAR) {
-        if (blend == MK_BLEND_ALPHA) le = launch_mapper<MK_INTER_LINEAR, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
-        else le = launch_mapper<MK_INTER_LINEAR, MK_BLEND_FEATHER>(false, grid, st, P);
-    } else {
-        if (blend == MK_BLEND_ALPHA) le = launch_mapper<MK_INTER_CUBIC, MK_BLEND_ALPHA>(roi != nullptr, grid, st, P);
-        else le = launch_mapper<MK_INTER_CUBIC, MK_BLEND_FEATHER>(false, grid, st, P);
-    }
+    P.f0.src_aligned = (aligned(src, 16) && (src_pitch & 15) == 0) ? 1 : 0;
+    P.src_smem_bytes = P.f0.src_aligned ? estimate_src_smem(P.f0.M, rect, interp) : 0;
+    const cudaError_t le = launch_mapper_any(interp, blend, roi != nullptr, false, grid, (cudaStream_t)stream, P);
     if (le != cudaSuccess) return cuda_fail(le, "cudaFuncSetAttribute(mapper_update_kernel)");
     MK_LAUNCH_CHECK("mapper_update_kernel");
+    return MK_OK;
+}
+
+extern "C" int mk_mapper_update_batch(uint8_t *canvas, size_t canvas_pitch, uint8_t *cmask, size_t cmask_pitch, float *wacc,
+                                      size_t wacc_pitch, int canvas_h, int canvas_w, int nframes, const uint8_t *const *src_host,
+                                      const int *src_h_host, const int *src_w_host, const size_t *src_pitch_host,
+                                      const double *H_host, double alpha, int interp, int blend, float feather_ramp, void *stream)
+{
+    if (!canvas || !cmask || nframes < 0 || canvas_h <= 0 || canvas_w <= 0 || (nframes && (!src_host || !src_h_host || !src_w_host || !src_pitch_host || !H_host))) {
+        set_error("mk_mapper_update_batch: null pointer or empty shape");
+        return MK_ERR_ARG;
+    }
+    if (nframes == 0) return MK_OK;
+    if (interp != MK_INTER_LINEAR && interp != MK_INTER_CUBIC) { set_error("mk_mapper_update_batch: bad interp %d", interp); return MK_ERR_ARG; }
+    if (blend != MK_BLEND_ALPHA && blend != MK_BLEND_FEATHER) { set_error("mk_mapper_update_batch: bad blend %d", blend); return MK_ERR_ARG; }
+    if (blend == MK_BLEND_ALPHA && !(alpha >= 0.0 && alpha <= 1.0)) { set_error("mk_mapper_update_batch: alpha outside [0,1]"); return MK_ERR_ARG; }
+    if (blend == MK_BLEND_FEATHER && (!wacc || !(feather_ramp > 0.f))) { set_error("mk_mapper_update_batch: feather mode needs wacc and ramp > 0"); return MK_ERR_ARG; }
+    if (canvas_pitch < (size_t)canvas_w * 3 || cmask_pitch < (size_t)canvas_w || (blend == MK_BLEND_FEATHER && wacc_pitch < (size_t)canvas_w * 4)) {
+        set_error("mk_mapper_update_batch: pitch smaller than a row");
+        return MK_ERR_ARG;
+    }
+    if (!aligned(canvas, 16) || !aligned(cmask, 16) || (canvas_pitch & 15) || (cmask_pitch & 15) ||
+        (blend == MK_BLEND_FEATHER && (!aligned(wacc, 16) || (wacc_pitch & 15)))) {
+        set_error("mk_mapper_update_batch: alignment (canvas/cmask/wacc 16 B + pitch %% 16)");
+        return MK_ERR_ALIGN;
+    }
+    // per-frame descriptors + the (tile -> ordered frame list) table
+    const int ntx = (canvas_w + TW - 1) / TW, nty = (canvas_h + TH - 1) / TH;
+    std::vector<FrameDesc> frames((size_t)nframes);
+    std::vector<std::array<int, 4>> rects((size_t)nframes);
+    int smem_need = 0;
+    bool all_aligned = true;
+    std::vector<int> count((size_t)ntx * nty, 0);
+    for (int k = 0; k < nframes; ++k) {
+        const int h = src_h_host[k], w = src_w_host[k];
+        const size_t sp = src_pitch_host[k];
+        if (!src_host[k] || h <= 0 || w <= 0 || h > 32767 || w > 32767 || sp < (size_t)w * 3 || !aligned(src_host[k], 4) || (sp & 3)) {
+            set_error("mk_mapper_update_batch: frame %d: bad pointer, shape, pitch or alignment", k);
+            return MK_ERR_ARG;
+        }
+        FrameDesc &f = frames[k];
+        f.src = src_host[k]; f.roi = nullptr; f.spitch = sp; f.rpitch = 0; f.h = h; f.w = w; f.pad_ = 0;
+        f.src_aligned = (aligned(src_host[k], 16) && (sp & 15) == 0) ? 1 : 0;
+        all_aligned = all_aligned && f.src_aligned;
+        make_invmap(H_host + 9 * (size_t)k, f.M);
+        int32_t rect[4];
+        footprint(canvas_h, canvas_w, h, w, H_host + 9 * (size_t)k, interp, rect);
+        rects[k] = { rect[0], rect[1], rect[2], rect[3] };
+        if (rect[2] <= rect[0]) continue;
+        if (f.src_aligned) smem_need = std::max(smem_need, estimate_src_smem(f.M, rect, interp));
+        for (int ty = rect[1] / TH; ty < (rect[3] + TH - 1) / TH; ++ty)
+            for (int tx = rect[0] / TW; tx < (rect[2] + TW - 1) / TW; ++tx) ++count[(size_t)ty * ntx + tx];
+    }
+    std::vector<int> tile_xy, tile_ptr(1, 0), slot((size_t)ntx * nty, -1);
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+            const int c = count[(size_t)ty * ntx + tx];
+            if (!c) continue;
+            slot[(size_t)ty * ntx + tx] = tile_ptr.back();
+            tile_xy.push_back(tx); tile_xy.push_back(ty);
+            tile_ptr.push_back(tile_ptr.back() + c);
+        }
+    const int ntiles = (int)tile_xy.size() / 2;
+    if (ntiles == 0) return MK_OK;
+    std::vector<int> tile_frame((size_t)tile_ptr.back());
+    for (int k = 0; k < nframes; ++k) {          // frames are appended in order: every tile sees them in sequence order
+        const auto &r = rects[k];
+        if (r[2] <= r[0]) continue;
+        for (int ty = r[1] / TH; ty < (r[3] + TH - 1) / TH; ++ty)
+            for (int tx = r[0] / TW; tx < (r[2] + TW - 1) / TW; ++tx) tile_frame[(size_t)slot[(size_t)ty * ntx + tx]++] = k;
+    }
+    // one stream-ordered device scratch: [frames][tile_ptr][tile_xy][tile_frame]
+    const size_t b_frames = (sizeof(FrameDesc) * (size_t)nframes + 15) & ~(size_t)15, b_ptr = (sizeof(int) * tile_ptr.size() + 15) & ~(size_t)15,
+                 b_xy = (sizeof(int) * tile_xy.size() + 15) & ~(size_t)15, b_tf = sizeof(int) * tile_frame.size();
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *scratch = nullptr;
+    MK_CUDA_TRY(cudaMallocAsync(&scratch, b_frames + b_ptr + b_xy + b_tf + 16, st));
+    cudaError_t ce = cudaMemcpyAsync(scratch, frames.data(), sizeof(FrameDesc) * (size_t)nframes, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(scratch + b_frames, tile_ptr.data(), sizeof(int) * tile_ptr.size(), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(scratch + b_frames + b_ptr, tile_xy.data(), sizeof(int) * tile_xy.size(), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(scratch + b_frames + b_ptr + b_xy, tile_frame.data(), b_tf, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) { cudaFreeAsync(scratch, st); return cuda_fail(ce, "mk_mapper_update_batch: table upload"); }
+    MapperParams P{};
+    P.canvas = canvas; P.cmask = cmask; P.wacc = wacc;
+    P.cpitch = canvas_pitch; P.mpitch = cmask_pitch; P.wpitch = wacc_pitch;
+    P.Hc = canvas_h; P.Wc = canvas_w;
+    P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp;
+    {
+        DeviceTables tb;
+        const int rc = device_tables(tb);
+        if (rc != MK_OK) { cudaFreeAsync(scratch, st); return rc; }
+        P.cubic = tb.cubic; P.lut = tb.lut;
+    }
+    P.frames = reinterpret_cast<const FrameDesc *>(scratch);
+    P.tile_ptr = reinterpret_cast<const int *>(scratch + b_frames);
+    P.tile_xy = reinterpret_cast<const int *>(scratch + b_frames + b_ptr);
+    P.tile_frame = reinterpret_cast<const int *>(scratch + b_frames + b_ptr + b_xy);
+    P.src_smem_bytes = smem_need;
+    const cudaError_t le = launch_mapper_any(interp, blend, false, true, dim3((unsigned)ntiles), st, P);
+    cudaFreeAsync(scratch, st);      // stream-ordered: released after the kernel
+    if (le != cudaSuccess) return cuda_fail(le, "cudaFuncSetAttribute(mapper_update_kernel)");
+    MK_LAUNCH_CHECK("mapper_update_kernel(batch)");
     return MK_OK;
 }
 

@@ -194,6 +194,37 @@ class Mapper:
         _lib.check(rc)
         self.last_region = tuple(region)
 
+    def update_batch(self, frames: Sequence, Hs: Sequence[np.ndarray]) -> None:
+        """Composite many frames in sequence order with ONE launch (gather formulation: every canvas tile is read once,
+        updated by all the frames that reach it, written once).  Same result as calling update() frame by frame -- the
+        loop SequentialMosaic.generate runs per tile (mosaic.py:678-686).  Frames: uint8 [h, w, 3] arrays / tensors;
+        host frames are uploaded first (they all have to be resident during the launch)."""
+        n = len(frames)
+        if n != len(Hs):
+            raise ValueError("frames and Hs must have the same length")
+        if n == 0:
+            return
+        keep, ptrs, hs, ws, pitches = [], (ctypes.c_void_p * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_size_t * n)()
+        for k, fr in enumerate(frames):
+            if isinstance(fr, np.ndarray):
+                fr = make_bgr_host(fr)
+            t2, h, w = self._as_rows(fr, 3)
+            if not self._usable_in_place(t2):
+                pitch = _round_up(w * 3, 128)
+                buf = torch.empty((h, pitch), dtype=torch.uint8, device=self._device)
+                buf[:, : w * 3].copy_(t2, non_blocking=True)
+                t2 = buf
+            keep.append(t2)
+            ptrs[k], hs[k], ws[k], pitches[k] = t2.data_ptr(), h, w, t2.stride(0)
+        Hm = np.ascontiguousarray(np.stack([np.asarray(H, np.float64).reshape(3, 3) for H in Hs]))
+        ramp = self._ramp if self._ramp is not None else 0.1 * min(int(hs[0]), int(ws[0]))
+        _lib.check(self._lib.mk_mapper_update_batch(
+            self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
+            self._wacc.data_ptr() if self._wacc is not None else None, self._wacc.stride(0) * 4 if self._wacc is not None else 0,
+            self._height, self._width, n, ptrs, hs, ws, pitches, Hm.ctypes.data, self._alpha, self._interp, self._blend, float(ramp),
+            torch.cuda.current_stream(self._device).cuda_stream))
+        self._batch_keepalive = keep      # the launch is asynchronous: keep the staged frames alive until the next call
+
     def update(self, image, H: np.ndarray, stream=None, keypoints=None):
         """mosaic.py:159-172.  `stream` is accepted and ignored, as in the reference."""
         mask = None

@@ -379,3 +379,31 @@ def test_mapper_strong_perspective_and_horizon(interp, code):
         orc.mapper_update(canvas, cmask, img, H, 0.5, code)
         assert np.array_equal(mp.output, canvas), k
         assert np.array_equal(mp.mask, cmask), k
+
+
+@pytest.mark.parametrize("interp,code,blend", [("linear", 1, "alpha"), ("cubic", 2, "alpha"), ("linear", 1, "feather")])
+def test_mapper_update_batch_equals_sequential(interp, code, blend):
+    """mk_mapper_update_batch (one launch, every tile applies its frames in order) == frame-by-frame updates == oracle."""
+    rng = np.random.default_rng(51)
+    Hc, Wc = 333, 517
+    frames, Hs = [], []
+    for k in range(7):
+        h, w = int(rng.integers(40, 160)), int(rng.integers(40, 220))
+        frames.append(_img(rng, h, w))
+        Hs.append(_rand_H(rng, [0, 2e-4][k % 2], 400, 250, 0.7, 1.5))
+    Hs.append(np.array([[1.0, 0, 9000.0], [0, 1.0, 9000.0], [0, 0, 1.0]])); frames.append(_img(rng, 50, 50))   # off-canvas frame
+    kw = dict(interp=interp, blend=blend, feather_ramp=9.0) if blend == "feather" else dict(interp=interp)
+    a = mb.Mapper(Wc, Hc, alpha_blend=0.5, **kw)
+    b = mb.Mapper(Wc, Hc, alpha_blend=0.5, **kw)
+    a.update_batch(frames[:3], Hs[:3])          # two batches on top of each other
+    a.update_batch(frames[3:], Hs[3:])
+    for f, H in zip(frames, Hs):
+        b.update(f, H)
+    assert np.array_equal(a.output, b.output) and np.array_equal(a.mask, b.mask)
+    if blend == "alpha":
+        canvas = np.zeros((Hc, Wc, 3), np.uint8); cmask = np.zeros((Hc, Wc), np.uint8)
+        for f, H in zip(frames, Hs):
+            orc.mapper_update(canvas, cmask, f, H, 0.5, code)
+        assert np.array_equal(a.output, canvas) and np.array_equal(a.mask, cmask)
+    else:
+        assert np.array_equal(a.weights, b.weights)
