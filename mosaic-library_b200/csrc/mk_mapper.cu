@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float 
 }
 
 template <int INTERP, int BLEND, bool ROI, bool BATCH>
-__global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_constant__ MapperParams p)
+__global__ void __launch_bounds__(MTHREADS, (BATCH && INTERP == 1) ? 5 : 1) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
     __shared__ __align__(16) uint32_t s_warp[TH][TW];
@@ -205,6 +205,29 @@ __global__ void __launch_bounds__(MTHREADS) mapper_update_kernel(const __grid_co
         if (tid < (int)(sizeof(FrameDesc) / 4))
             reinterpret_cast<uint32_t *>(&s_frame)[tid] = reinterpret_cast<const uint32_t *>(p.frames + p.tile_frame[list0 + fi])[tid];
         __syncthreads();
+    }
+    // ---- alpha == 1 ("keep the canvas where it is already set", the reference CLI default, utils.py:124): a pixel whose
+    //      mask byte is 255 can change neither its colour (fmaf(c, 1, w * 0) == c) nor its mask (255 | m == 255), so a tile
+    //      whose in-canvas mask bytes are all 255 is finished for good and every later frame skips it ------------------
+    if constexpr (BLEND == MK_BLEND_ALPHA) {
+        if (p.alpha == 1.0f && p.beta == 0.0f) {
+            bool full = true;
+            if (tid < TH * (TW / 16)) {
+                const int y = tileY + (tid >> 2), x0 = tileX + 16 * (tid & 3);
+                if (y < p.Hc && x0 < p.Wc) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(p.cmask + (size_t)y * p.mpitch + x0);
+                    if (x0 + 16 <= p.Wc) {
+                        full = (v.x & v.y & v.z & v.w) == 0xFFFFFFFFu;
+                    } else {
+                        const uint32_t wds[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int b = 0; b < 16; ++b)
+                            if (x0 + b < p.Wc) full = full && (((wds[b >> 2] >> (8 * (b & 3))) & 255u) == 255u);
+                    }
+                }
+            }
+            if (__syncthreads_and(full)) continue;
+        }
     }
     // ---- per-row coordinate bases for the left / centre / right 64-px blocks, and the source
     //      positions of the four corners of the haloed tile ---------------------------------------

@@ -407,3 +407,26 @@ def test_mapper_update_batch_equals_sequential(interp, code, blend):
         assert np.array_equal(a.output, canvas) and np.array_equal(a.mask, cmask)
     else:
         assert np.array_equal(a.weights, b.weights)
+
+
+def test_mapper_alpha_one_skips_finished_tiles_exactly():
+    """alpha = 1 (reference CLI default): tiles whose mask is already all 255 are skipped; the result must still equal the
+    oracle, including tiles that are only partly covered, black source pixels (holes) and the ROI path (non-binary mask)."""
+    import cv2
+    rng = np.random.default_rng(61)
+    Hc, Wc = 300, 420
+    mp = mb.Mapper(Wc, Hc, alpha_blend=1.0, interp="linear")
+    canvas = np.zeros((Hc, Wc, 3), np.uint8); cmask = np.zeros((Hc, Wc), np.uint8)
+    for k in range(8):
+        img = _img(rng, 200, 280, black=0.01 if k % 2 else 0.0)
+        H = np.array([[1.0, 0.02 * k, 20.0 + 12 * k], [-0.01 * k, 1.0, 15.0 + 9 * k], [0, 0, 1.0]])
+        kps = None
+        roi = None
+        if k == 5:
+            pts = np.stack([rng.uniform(5, 270, 30), rng.uniform(5, 190, 30)], 1).astype(np.float32)
+            kps = [cv2.KeyPoint(float(x), float(y), 1) for x, y in pts]
+            roi = mp._create_keypoint_mask(cv2.KeyPoint.convert(kps), (280, 200))
+        mp.update(img, H, None, kps)
+        orc.mapper_update(canvas, cmask, img, H, 1.0, 1, roi)
+        assert np.array_equal(mp.output, canvas), k
+        assert np.array_equal(mp.mask, cmask), k
