@@ -164,7 +164,7 @@ __device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float 
 }
 
 template <int INTERP, int BLEND, bool ROI, bool BATCH>
-__global__ void __launch_bounds__(MTHREADS, (BATCH && INTERP == 1) ? 5 : 1) mapper_update_kernel(const __grid_constant__ MapperParams p)
+__global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
     __shared__ __align__(16) uint32_t s_warp[TH][TW];
