@@ -273,14 +273,8 @@ class Matcher:
         if len(query) == 0:
             return ()
         idx, dist, _ = self.knn_match_arrays(query, train, ratio=0.0)
-        out = []
-        for i in range(idx.shape[0]):
-            row = []
-            for k in range(2):
-                if idx[i, k] >= 0:
-                    row.append(DMatch(i, int(idx[i, k]), 0, float(dist[i, k])))
-            out.append(tuple(row))
-        return tuple(out)
+        il, dl = idx.tolist(), dist.tolist()      # plain Python numbers: far cheaper than numpy scalar indexing
+        return tuple(tuple(DMatch(i, j, 0, d) for j, d in zip(ir, dr) if j >= 0) for i, (ir, dr) in enumerate(zip(il, dl)))
 
     def match(self, query: np.ndarray, train: np.ndarray, mask: np.ndarray = None) -> Sequence[DMatch]:
         """registration.py:244-253: best match per query row (rows without any match are dropped)."""

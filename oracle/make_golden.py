@@ -14,6 +14,8 @@ What produces each expected value:
   mapper_*   mosaicking.mosaic.Mapper.update (mosaic.py:159-172 -> _update_cpu :111-138), as shipped
              (INTER_CUBIC) and with the flag patched to INTER_LINEAR (the north-star kernel), with and
              without the keypoint-hull ROI (mosaic.py:140-157); canvas + mask after every update.
+  pipeline   the reference's own integration test (tests/test_mosaic.py:28-73) run for real on its test video: the
+             first Mapper.update calls of SequentialMosaic.generate (mosaic.py:665-691) and the canvas they produce.
   routing    mosaicking.mosaic.get_corners / get_mosaic_dimensions (mosaic.py:708-768),
              registration.bbox_overlap on int-truncated corners (mosaic.py:614), and
              splitter.calculate_tiles / assign_image_to_tiles (splitter.py:11-58).
@@ -250,6 +252,52 @@ def gen_routing(reg, mos):
     print("routing.npz")
 
 
+def gen_pipeline(reg, mos):
+    """The reference's own integration test (tests/test_mosaic.py:28-73: ORB, keypoint_roi=True, alpha=1.0, CLAHE, tile
+    4096x4096) run for real on tests/data/sparus_snippet.mp4, with Mapper.update instrumented: the first NUPD calls
+    (frame after preprocessing, tile-local H, inlier keypoints) and the canvas / mask they produce are recorded."""
+    import tempfile
+    import yaml
+    NUPD = 6
+    data = ref_shim.REFERENCE_SRC.parent / "tests" / "data"
+    with open(data / "sparus_time_offset.yaml") as f:
+        offset = yaml.safe_load(f)["video"]
+    K = np.array([405.6384738851233, 0, 189.9054317917407, 0, 405.588335378204, 139.9149578253755, 0, 0, 1]).reshape((3, 3))
+    D = np.array([-0.3670656233416921, 0.203001968694465, 0.003336917744124004, -0.000487426354679637, 0])
+    rec = {"calls": [], "canvas": None, "mask": None}
+    real_update = mos.Mapper.update
+
+    def spy(self, image, H, stream=None, keypoints=None):
+        real_update(self, image, H, stream, keypoints)
+        if len(rec["calls"]) < NUPD:
+            kp = None if not keypoints else np.array(cv2.KeyPoint.convert(keypoints), np.float32)
+            rec["calls"].append((np.ascontiguousarray(image).copy(), np.array(H, np.float64), kp))
+            if len(rec["calls"]) == NUPD:
+                rec["canvas"], rec["mask"] = self._canvas.copy(), self._canvas_mask.copy()
+
+    mos.Mapper.update = spy
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            m = mos.SequentialMosaic(data_path=data / "sparus_snippet.mp4", project_path=Path(tmp), feature_types=("ORB",),
+                                     intrinsics={"K": K, "D": D}, orientation_path=data / "sparus_snippet.csv",
+                                     orientation_time_offset=offset, force_cpu=True, keypoint_roi=True, bovw_clusters=5, alpha=1.0)
+            m.extract_features(); m.match_features(); m.registration(); m.global_registration()
+            m.generate((4096, 4096))
+    finally:
+        mos.Mapper.update = real_update
+    assert len(rec["calls"]) == NUPD, "the reference pipeline produced fewer updates than expected"
+    ys, xs = np.nonzero(rec["mask"])
+    y0, y1, x0, x1 = max(0, ys.min() - 8), ys.max() + 9, max(0, xs.min() - 8), xs.max() + 9
+    out = {"n": np.array(NUPD), "alpha": np.array(1.0), "tile": np.array([4096, 4096]), "crop": np.array([y0, y1, x0, x1]),
+           "canvas_crop": rec["canvas"][y0:y1, x0:x1], "mask_crop": rec["mask"][y0:y1, x0:x1],
+           "outside_is_zero": np.array(int(rec["canvas"].sum() == rec["canvas"][y0:y1, x0:x1].sum()))}
+    for k, (img, H, kp) in enumerate(rec["calls"]):
+        out[f"img{k}"], out[f"H{k}"] = img, H
+        out[f"kp{k}"] = kp if kp is not None else np.zeros((0, 2), np.float32)
+    np.savez_compressed(OUT / "pipeline.npz", **out)
+    print("pipeline.npz", NUPD, "updates, crop", (y0, y1, x0, x1), "frame", rec["calls"][0][0].shape)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     reg, mos = ref_shim.import_reference()
@@ -258,6 +306,7 @@ def main():
     gen_warp()
     gen_mapper(mos)
     gen_routing(reg, mos)
+    gen_pipeline(reg, mos)
     (OUT / "PROVENANCE.txt").write_text(
         f"generated by oracle/make_golden.py\ncv2 {cv2.__version__}, numpy {np.__version__}\n"
         f"reference: DTUAqua-ObsTek/mosaic-library checkout at {ref_shim.REFERENCE_SRC.parent}\n")

@@ -430,3 +430,21 @@ def test_mapper_alpha_one_skips_finished_tiles_exactly():
         orc.mapper_update(canvas, cmask, img, H, 1.0, 1, roi)
         assert np.array_equal(mp.output, canvas), k
         assert np.array_equal(mp.mask, cmask), k
+
+
+def test_reference_pipeline_golden_on_gpu(golden):
+    """Drop-in check against the reference's own end-to-end run (tests/golden/pipeline.npz, see oracle/make_golden.py):
+    the Mapper.update calls SequentialMosaic.generate made on the reference's test video -- default Mapper arguments,
+    cv2.KeyPoint ROI, alpha = 1, 4096 x 4096 tile -- replayed through the CUDA Mapper give the reference's canvas bit for bit."""
+    import cv2
+    g = golden.pipeline
+    Wt, Ht = (int(v) for v in g["tile"])
+    y0, y1, x0, x1 = (int(v) for v in g["crop"])
+    mp = mb.Mapper(Wt, Ht, alpha_blend=float(g["alpha"]))        # interp defaults to the reference's INTER_CUBIC
+    for k in range(int(g["n"])):
+        kps = [cv2.KeyPoint(float(x), float(y), 1) for x, y in g[f"kp{k}"]]
+        mp.update(g[f"img{k}"], g[f"H{k}"], None, kps or None)
+    out, mask = mp.output, mp.mask
+    assert np.array_equal(out[y0:y1, x0:x1], g["canvas_crop"])
+    assert np.array_equal(mask[y0:y1, x0:x1], g["mask_crop"])
+    assert int(out.sum(dtype=np.int64)) == int(g["canvas_crop"].sum(dtype=np.int64))

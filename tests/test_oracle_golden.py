@@ -72,3 +72,24 @@ def test_oracle_vs_live_cv2():
         idx, dist = orc.knn2(q, t, name)
         assert [[mm.trainIdx for mm in r] for r in m] == idx.tolist()
         assert np.array_equal(np.array([[mm.distance for mm in r] for r in m], np.float32), dist)
+
+
+def test_reference_pipeline_golden(golden):
+    """The reference's own integration test run for real (SequentialMosaic on its test video, ORB + keypoint ROI, alpha = 1,
+    INTER_CUBIC as shipped): the recorded Mapper.update calls replayed through the oracle give the reference's canvas."""
+    cv2 = pytest.importorskip("cv2")
+    g = golden.pipeline
+    Wt, Ht = (int(v) for v in g["tile"])
+    y0, y1, x0, x1 = (int(v) for v in g["crop"])
+    canvas = np.zeros((Ht, Wt, 3), np.uint8)
+    cmask = np.zeros((Ht, Wt), np.uint8)
+    for k in range(int(g["n"])):
+        img, kp = g[f"img{k}"], g[f"kp{k}"]
+        roi = None
+        if len(kp):                                            # mosaic.py:140-157
+            roi = np.zeros(img.shape[:2], np.uint8)
+            roi = cv2.fillConvexPoly(roi, cv2.convexHull(kp.astype(np.int32)), 255)
+        orc.mapper_update(canvas, cmask, img, g[f"H{k}"], float(g["alpha"]), orc.INTER_CUBIC, roi)
+    assert np.array_equal(canvas[y0:y1, x0:x1], g["canvas_crop"])
+    assert np.array_equal(cmask[y0:y1, x0:x1], g["mask_crop"])
+    assert int(canvas.sum()) == int(g["canvas_crop"].sum())    # nothing outside the recorded crop
