@@ -632,16 +632,14 @@ static void build_cubic_table(short *tab)
         }
 }
 
-// Bilinear weight LUT for lerp3_dp4a: entry [ay*32+ax] = (hi bytes, lo bytes) of the four integer
-// weights (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax*ay split as w = hi*32 + lo.
+// Bilinear weight LUT for lerp3_dp4a: entry [ay*32+ax] = ((w00 | w01 << 16), (w10 | w11 << 16)) with the integer weights
+// (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax*ay (<= 1024) as int16 pairs for IDP.2A.
 static void build_lerp_lut(uint2 *lut)
 {
     for (int ay = 0; ay < 32; ++ay)
         for (int ax = 0; ax < 32; ++ax) {
-            const int w[4] = { (32 - ax) * (32 - ay), ax * (32 - ay), (32 - ax) * ay, ax * ay };
-            uint32_t hi = 0, lo = 0;
-            for (int k = 0; k < 4; ++k) { hi |= (uint32_t)(w[k] >> 5) << (8 * k); lo |= (uint32_t)(w[k] & 31) << (8 * k); }
-            lut[ay * 32 + ax] = make_uint2(hi, lo);
+            const uint32_t w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+            lut[ay * 32 + ax] = make_uint2(w00 | (w01 << 16), w10 | (w11 << 16));
         }
 }
 

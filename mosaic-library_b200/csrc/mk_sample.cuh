@@ -229,9 +229,23 @@ struct SrcTile {
     int sy0, bx0, R, rowbytes;
 };
 
-// Bilinear weights as two byte-packed words (taps p00, p01, p10, p11): w = hi * 32 + lo, so that
-//   sum(v * w) + 512 = dp4a(V, hi) * 32 + dp4a(V, lo, 512)      (exact integer identity)
-// lut[ay * 32 + ax] = (hi, lo).  Filled on the host (mk_mapper.cu).
+// signed 16-bit weight pairs x unsigned bytes: d = a.lo * b.byte[0|2] + a.hi * b.byte[1|3] + c   (SASS IDP.2A)
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// Bilinear weights as two int16 pairs: lut[ay * 32 + ax] = ((w00 | w01 << 16), (w10 | w11 << 16)), weights (32-ax)(32-ay) ...
+// <= 1024.  Per channel the 2x2 quad sits in one register as bytes (v00, v01, v10, v11), so
+//   sum(v * w) + 512 = dp2a.hi(w_bottom, V, dp2a.lo(w_top, V, 512))            (exact integer arithmetic, 2 IDP.2A)
 __device__ __forceinline__ uint32_t lerp3_dp4a(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint2 wt)
 {
     // alo = [B0 G0 R0 B1], ahi = [G1 R1 . .] (row sy), blo / bhi the same for row sy + 1
@@ -240,9 +254,9 @@ __device__ __forceinline__ uint32_t lerp3_dp4a(uint32_t alo, uint32_t ahi, uint3
     const uint32_t rb = __byte_perm(blo, bhi, 0x5241);          // G0' G1' R0' R1'
     const uint32_t vg = __byte_perm(ra, rb, 0x5410);            // G0 G1 G0' G1'
     const uint32_t vr = __byte_perm(ra, rb, 0x7632);            // R0 R1 R0' R1'
-    const uint32_t b = (__dp4a(vb, wt.x, 0u) * 32u + __dp4a(vb, wt.y, 512u)) >> 10;
-    const uint32_t g = (__dp4a(vg, wt.x, 0u) * 32u + __dp4a(vg, wt.y, 512u)) >> 10;
-    const uint32_t r = (__dp4a(vr, wt.x, 0u) * 32u + __dp4a(vr, wt.y, 512u)) >> 10;
+    const uint32_t b = (uint32_t)dp2a_hi_su(wt.y, vb, dp2a_lo_su(wt.x, vb, 512)) >> 10;
+    const uint32_t g = (uint32_t)dp2a_hi_su(wt.y, vg, dp2a_lo_su(wt.x, vg, 512)) >> 10;
+    const uint32_t r = (uint32_t)dp2a_hi_su(wt.y, vr, dp2a_lo_su(wt.x, vr, 512)) >> 10;
     return b | (g << 8) | (r << 16);
 }
 
@@ -298,22 +312,28 @@ __device__ __forceinline__ bool sample_cubic_c3_smem(const SrcTile &T, int X, in
     const int ax = X & 31, ay = Y & 31;
     const int r = (Y >> 5) - 1 - T.sy0, cb = ((X >> 5) - 1) * 3 - T.bx0;
     if (r < 0 || r + 3 >= T.R || cb < 0 || cb + 16 > T.rowbytes) return false;
-    const short *wt = tab + (ay * 32 + ax) * 16;
+    // 16 int16 weights = two 16-byte loads; word k of row ky holds the weight pair (w[2k], w[2k+1])
+    const uint4 *wq = reinterpret_cast<const uint4 *>(tab + (ay * 32 + ax) * 16);
+    const uint4 wa = __ldg(wq), wb = __ldg(wq + 1);
+    const uint32_t wp[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
     const unsigned sh = (unsigned)(cb & 3) * 8;
     const uint8_t *base = T.s + r * T.rowbytes + (cb & ~3);
-    int acc0 = 0, acc1 = 0, acc2 = 0;
+    int acc0 = 1 << 14, acc1 = 1 << 14, acc2 = 1 << 14;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(base + ky * T.rowbytes);
         const uint32_t r0 = q[0], r1 = q[1], r2 = q[2], r3 = q[3];
+        // 12 bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
         const uint32_t d0 = __funnelshift_r(r0, r1, sh), d1 = __funnelshift_r(r1, r2, sh), d2 = __funnelshift_r(r2, r3, sh);
-        const int w0 = wt[ky * 4 + 0], w1 = wt[ky * 4 + 1], w2 = wt[ky * 4 + 2], w3 = wt[ky * 4 + 3];
-        acc0 += (int)(d0 & 255u) * w0 + (int)(d0 >> 24) * w1 + (int)((d1 >> 16) & 255u) * w2 + (int)((d2 >> 8) & 255u) * w3;
-        acc1 += (int)((d0 >> 8) & 255u) * w0 + (int)(d1 & 255u) * w1 + (int)(d1 >> 24) * w2 + (int)((d2 >> 16) & 255u) * w3;
-        acc2 += (int)((d0 >> 16) & 255u) * w0 + (int)((d1 >> 8) & 255u) * w1 + (int)(d2 & 255u) * w2 + (int)(d2 >> 24) * w3;
+        const uint32_t vb = __byte_perm(__byte_perm(d0, d1, 0x0630), d2, 0x5210);   // B0 B1 B2 B3
+        const uint32_t vg = __byte_perm(__byte_perm(d0, d1, 0x0741), d2, 0x6210);   // G0 G1 G2 G3
+        const uint32_t vr = __byte_perm(__byte_perm(d0, d1, 0x0052), d2, 0x7410);   // R0 R1 R2 R3
+        const uint32_t w01 = wp[2 * ky], w23 = wp[2 * ky + 1];
+        acc0 = dp2a_hi_su(w23, vb, dp2a_lo_su(w01, vb, acc0));
+        acc1 = dp2a_hi_su(w23, vg, dp2a_lo_su(w01, vg, acc1));
+        acc2 = dp2a_hi_su(w23, vr, dp2a_lo_su(w01, vr, acc2));
     }
-    out = (uint32_t)clamp_u8((acc0 + (1 << 14)) >> 15) | ((uint32_t)clamp_u8((acc1 + (1 << 14)) >> 15) << 8) |
-          ((uint32_t)clamp_u8((acc2 + (1 << 14)) >> 15) << 16);
+    out = (uint32_t)clamp_u8(acc0 >> 15) | ((uint32_t)clamp_u8(acc1 >> 15) << 8) | ((uint32_t)clamp_u8(acc2 >> 15) << 16);
     return true;
 }
 
