@@ -163,6 +163,63 @@ __device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float 
     return o0 | (o1 << 8) | (o2 << 16);
 }
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE-rn lanes per instruction -------------------------
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, uint32_t &lo, uint32_t &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// cv2.addWeighted (mosaic.py:133) for TWO pixels at once: per channel rint(fmaf(c, a32, w * b32)), the two pixels in the
+// two lanes of the f32x2 instructions.  Same rounding sequence as blend_px_fast, so the result is identical bit for bit.
+template <int CH>
+__device__ __forceinline__ void blend_pair_ch(uint32_t ca, uint32_t cb, uint32_t wa, uint32_t wb, unsigned long long a2,
+                                              unsigned long long b2, uint32_t &ra, uint32_t &rb)
+{
+    const unsigned long long NEG = pack2(0xCB000000u, 0xCB000000u);      // -2^23
+    const unsigned long long MAGIC = pack2(0x4B400000u, 0x4B400000u);    // 1.5 * 2^23
+    unsigned long long cf = pack2(__byte_perm(ca, 0x4B000000u, 0x7650u | CH), __byte_perm(cb, 0x4B000000u, 0x7650u | CH));
+    unsigned long long wf = pack2(__byte_perm(wa, 0x4B000000u, 0x7650u | CH), __byte_perm(wb, 0x4B000000u, 0x7650u | CH));
+    cf = fadd2(cf, NEG);
+    wf = fadd2(wf, NEG);
+    const unsigned long long r = fadd2(ffma2(cf, a2, fmul2(wf, b2)), MAGIC);
+    unpack2(r, ra, rb);
+}
+__device__ __forceinline__ void blend_pair(uint32_t ca, uint32_t cb, uint32_t wa, uint32_t wb, unsigned long long a2,
+                                           unsigned long long b2, uint32_t &oa, uint32_t &ob)
+{
+    uint32_t a0, b0, a1, b1, a2r, b2r;
+    blend_pair_ch<0>(ca, cb, wa, wb, a2, b2, a0, b0);
+    blend_pair_ch<1>(ca, cb, wa, wb, a2, b2, a1, b1);
+    blend_pair_ch<2>(ca, cb, wa, wb, a2, b2, a2r, b2r);
+    // low byte of every result (0..255: t <= 255.00003 rounds to at most 255) -> B | G << 8 | R << 16
+    oa = __byte_perm(__byte_perm(a0, a1, 0x0040), a2r, 0x3410) & 0xFFFFFFu;
+    ob = __byte_perm(__byte_perm(b0, b1, 0x0040), b2r, 0x3410) & 0xFFFFFFu;
+}
+
 template <int INTERP, int BLEND, bool ROI, bool BATCH>
 __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update_kernel(const __grid_constant__ MapperParams p)
 {
@@ -454,13 +511,26 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
             wa = *reinterpret_cast<const float4 *>(wp);
         }
         bool touched = false;
+        uint32_t bl[4] = { 0u, 0u, 0u, 0u };
+        unsigned oldb = 0;
+        if constexpr (BLEND == MK_BLEND_ALPHA) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oldb |= (((mk4 >> (8 * j)) & 255u) > 1u ? 1u : 0u) << j;      // mosaic.py:123
+            const unsigned need = (keep_old || take_new) ? 0u : (mb & oldb);
+            if (need) {
+                const uint32_t ab = __float_as_uint(p.alpha), bb = __float_as_uint(p.beta);
+                const unsigned long long a2 = pack2(ab, ab), b2 = pack2(bb, bb);
+                if (need & 3u) blend_pair(px[0], px[1], wv[0], wv[1], a2, b2, bl[0], bl[1]);
+                if (need & 12u) blend_pair(px[2], px[3], wv[2], wv[3], a2, b2, bl[2], bl[3]);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (!((mb >> j) & 1u)) continue;
             if constexpr (BLEND == MK_BLEND_ALPHA) {
-                const bool old = ((mk4 >> (8 * j)) & 255u) > 1u;
+                const bool old = (oldb >> j) & 1u;
                 if (!old || take_new) px[j] = wv[j];
-                else if (!keep_old) px[j] = blend_px_fast(px[j], wv[j], p.alpha, p.beta);
+                else if (!keep_old) px[j] = bl[j];
                 if constexpr (ROI) mk4 |= (uint32_t)s_mval[r][4 * g + j] << (8 * j);
                 else mk4 |= 255u << (8 * j);
                 touched = true;
