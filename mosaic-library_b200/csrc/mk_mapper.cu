@@ -66,35 +66,6 @@ struct MapperParams {
     const int *tile_ptr, *tile_frame, *tile_xy;
 };
 
-__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, int nbytes)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(nbytes) : "memory");
-}
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// cv2.addWeighted on uint8: both scalars narrowed to fp32, rint(fmaf(c, a, w*b)), saturate.
-__device__ __forceinline__ uint32_t blend_u8(uint32_t c, uint32_t w, float a, float b)
-{
-    const float t = __fmaf_rn((float)c, a, __fmul_rn((float)w, b));
-    return (uint32_t)min(255, max(0, __float2int_rn(t)));
-}
-
-__device__ __forceinline__ uint32_t blend_px(uint32_t c, uint32_t w, float a, float b)
-{
-    return blend_u8(c & 255u, w & 255u, a, b) | (blend_u8((c >> 8) & 255u, (w >> 8) & 255u, a, b) << 8) |
-           (blend_u8((c >> 16) & 255u, (w >> 16) & 255u, a, b) << 16);
-}
-
 // feather: canvas = sat_u8(rint((canvas*Wacc + warped*g) / (Wacc + g)))  
 __device__ __forceinline__ uint32_t feather_u8(uint32_t c, uint32_t w, float acc, float g, float s)
 {
@@ -142,27 +113,6 @@ __device__ __forceinline__ void bulk_commit_wait_read()
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// byte k of x as float, and round-to-nearest-even back to an integer, both on the FP32 pipe
-// (2^23 / 1.5 * 2^23 magic constants) instead of the 16-lane I2F / F2I unit.  Exact for 0..255.
-template <int K>
-__device__ __forceinline__ float byte_to_float(uint32_t x)
-{
-    return __fadd_rn(__int_as_float((int)__byte_perm(x, 0x4B000000u, 0x7650u | K)), -8388608.0f);
-}
-__device__ __forceinline__ uint32_t rint_u8(float t)   // t in [0, 255.4]
-{
-    return (uint32_t)__float_as_int(__fadd_rn(t, 12582912.0f)) & 0x1FFu;
-}
-
-// cv2.addWeighted on uint8 (mosaic.py:133): rint(fmaf(c, a32, w * b32)), saturate.
-__device__ __forceinline__ uint32_t blend_px_fast(uint32_t c, uint32_t w, float a, float b)
-{
-    const uint32_t o0 = min(255u, rint_u8(__fmaf_rn(byte_to_float<0>(c), a, __fmul_rn(byte_to_float<0>(w), b))));
-    const uint32_t o1 = min(255u, rint_u8(__fmaf_rn(byte_to_float<1>(c), a, __fmul_rn(byte_to_float<1>(w), b))));
-    const uint32_t o2 = min(255u, rint_u8(__fmaf_rn(byte_to_float<2>(c), a, __fmul_rn(byte_to_float<2>(w), b))));
-    return o0 | (o1 << 8) | (o2 << 16);
-}
-
 // ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two IEEE-rn lanes per instruction -------------------------
 __device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi)
 {
@@ -194,7 +144,8 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 }
 
 // cv2.addWeighted (mosaic.py:133) for TWO pixels at once: per channel rint(fmaf(c, a32, w * b32)), the two pixels in the
-// two lanes of the f32x2 instructions.  Same rounding sequence as blend_px_fast, so the result is identical bit for bit.
+// two lanes of the f32x2 instructions.  Bytes become floats by OR-ing them into 2^23 and subtracting 2^23, and the result
+// is rounded to nearest-even by adding 1.5 * 2^23 (exact for 0..255): no I2F / F2I on the 16-lane conversion unit.
 template <int CH>
 __device__ __forceinline__ void blend_pair_ch(uint32_t ca, uint32_t cb, uint32_t wa, uint32_t wb, unsigned long long a2,
                                               unsigned long long b2, uint32_t &ra, uint32_t &rb)
@@ -702,7 +653,7 @@ static void build_cubic_table(short *tab)
         }
 }
 
-// Bilinear weight LUT for lerp3_dp4a: entry [ay*32+ax] = ((w00 | w01 << 16), (w10 | w11 << 16)) with the integer weights
+// Bilinear weight LUT for lerp3_dp2a: entry [ay*32+ax] = ((w00 | w01 << 16), (w10 | w11 << 16)) with the integer weights
 // (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax*ay (<= 1024) as int16 pairs for IDP.2A.
 static void build_lerp_lut(uint2 *lut)
 {

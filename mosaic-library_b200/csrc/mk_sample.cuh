@@ -51,25 +51,10 @@ __device__ __forceinline__ void quantize(const InvMap &M, double X0, double Y0, 
     Y = __double2int_rn(dmul(dadd(Y0, my), W));
 }
 
-// Same as quantize() for |value| < 2^31 (guaranteed by the caller: the tile corners bound every
-// pixel of the tile and were checked to be far from saturation): adding 1.5 * 2^52 rounds to the
-// nearest-even integer exactly like cvt.rni.s32.f64, but runs on the FP64 pipe instead of the
-// 16-lane conversion unit.
+// Same as quantize() for |value| < 2^31 (guaranteed by the caller: the tile corners bound every pixel of the tile and
+// were checked to be far from saturation): adding 1.5 * 2^52 rounds to the nearest-even integer exactly like
+// cvt.rni.s32.f64, but runs on the FP64 pipe instead of the 16-lane conversion unit.
 __device__ __forceinline__ int round_magic(double v) { return __double2loint(__dadd_rn(v, 6755399441055744.0)); }
-
-__device__ __forceinline__ void quantize_fast(const InvMap &M, double X0, double Y0, double W0, double mx, double my,
-                                              double mw, int &X, int &Y)
-{
-    double W;
-    if (M.affine) {
-        W = M.wr;
-    } else {
-        W = dadd(W0, mw);
-        W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
-    }
-    X = round_magic(dmul(dadd(X0, mx), W));
-    Y = round_magic(dmul(dadd(Y0, my), W));
-}
 
 template <bool AFFINE>
 __device__ __forceinline__ void quantize_fast_t(const InvMap &M, double wr, double X0, double Y0, double W0, double mx, double my,
@@ -246,7 +231,7 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
 // Bilinear weights as two int16 pairs: lut[ay * 32 + ax] = ((w00 | w01 << 16), (w10 | w11 << 16)), weights (32-ax)(32-ay) ...
 // <= 1024.  Per channel the 2x2 quad sits in one register as bytes (v00, v01, v10, v11), so
 //   sum(v * w) + 512 = dp2a.hi(w_bottom, V, dp2a.lo(w_top, V, 512))            (exact integer arithmetic, 2 IDP.2A)
-__device__ __forceinline__ uint32_t lerp3_dp4a(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint2 wt)
+__device__ __forceinline__ uint32_t lerp3_dp2a(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint2 wt)
 {
     // alo = [B0 G0 R0 B1], ahi = [G1 R1 . .] (row sy), blo / bhi the same for row sy + 1
     const uint32_t vb = __byte_perm(alo, blo, 0x7430);          // B0 B1 B0' B1'
@@ -270,7 +255,7 @@ __device__ __forceinline__ bool sample_linear_c3_smem_lut(const SrcTile &T, int 
     const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
     const unsigned sh = (unsigned)(cb & 3) * 8;
     const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
-    out = lerp3_dp4a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
+    out = lerp3_dp2a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
                      __funnelshift_r(b1, b2, sh), wt);
     return true;
 }
@@ -286,24 +271,8 @@ __device__ __forceinline__ uint32_t sample_linear_c3_smem_fast(const SrcTile &T,
     const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
     const unsigned sh = (unsigned)(cb & 3) * 8;
     const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
-    return lerp3_dp4a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
+    return lerp3_dp2a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
                       __funnelshift_r(b1, b2, sh), wt);
-}
-
-__device__ __forceinline__ bool sample_linear_c3_smem(const SrcTile &T, int X, int Y, uint32_t &out)
-{
-    const int ax = X & 31, ay = Y & 31;
-    const int r = (Y >> 5) - T.sy0, cb = (X >> 5) * 3 - T.bx0;
-    if ((unsigned)r >= (unsigned)(T.R - 1) || cb < 0 || cb + 12 > T.rowbytes) return false;
-    const uint32_t *q0 = reinterpret_cast<const uint32_t *>(T.s + r * T.rowbytes + (cb & ~3));
-    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(q0) + T.rowbytes);
-    const unsigned sh = (unsigned)(cb & 3) * 8;
-    const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], b0 = q1[0], b1 = q1[1], b2 = q1[2];
-    const uint32_t alo = __funnelshift_r(a0, a1, sh), ahi = __funnelshift_r(a1, a2, sh);
-    const uint32_t blo = __funnelshift_r(b0, b1, sh), bhi = __funnelshift_r(b1, b2, sh);
-    out = lerp3(alo & 0xFFFFFFu, (alo >> 24) | ((ahi & 0xFFFFu) << 8), blo & 0xFFFFFFu, (blo >> 24) | ((bhi & 0xFFFFu) << 8),
-                ax, ay);
-    return true;
 }
 
 __device__ __forceinline__ bool sample_cubic_c3_smem(const SrcTile &T, int X, int Y, const short *__restrict__ tab,
