@@ -58,6 +58,7 @@ struct MapperParams {
     int Hc, Wc;
     int tx0, ty0;
     float alpha, beta, ramp;
+    uint32_t magic;      // 0x4B000000, see blend_pair_ch
     int src_smem_bytes;  // dynamic shared memory available for the staged source rectangle
     FrameDesc f0;        // single-frame launch: the frame, passed by value
     // batched launch (mk_mapper_update_batch): CTA b owns canvas tile tile_xy[b] and applies, in order, the frames
@@ -146,26 +147,28 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 // cv2.addWeighted (mosaic.py:133) for TWO pixels at once: per channel rint(fmaf(c, a32, w * b32)), the two pixels in the
 // two lanes of the f32x2 instructions.  Bytes become floats by OR-ing them into 2^23 and subtracting 2^23, and the result
 // is rounded to nearest-even by adding 1.5 * 2^23 (exact for 0..255): no I2F / F2I on the 16-lane conversion unit.
+// `magic` = 0x4B000000 (2^23) comes from the kernel parameters (MapperParams::magic), i.e. from the constant bank: with a
+// literal the compiler puts it in PRMT's immediate slot and spends one IMAD.MOV per PRMT to materialise the selector.
 template <int CH>
 __device__ __forceinline__ void blend_pair_ch(uint32_t ca, uint32_t cb, uint32_t wa, uint32_t wb, unsigned long long a2,
-                                              unsigned long long b2, uint32_t &ra, uint32_t &rb)
+                                              unsigned long long b2, uint32_t magic, uint32_t &ra, uint32_t &rb)
 {
     const unsigned long long NEG = pack2(0xCB000000u, 0xCB000000u);      // -2^23
     const unsigned long long MAGIC = pack2(0x4B400000u, 0x4B400000u);    // 1.5 * 2^23
-    unsigned long long cf = pack2(__byte_perm(ca, 0x4B000000u, 0x7650u | CH), __byte_perm(cb, 0x4B000000u, 0x7650u | CH));
-    unsigned long long wf = pack2(__byte_perm(wa, 0x4B000000u, 0x7650u | CH), __byte_perm(wb, 0x4B000000u, 0x7650u | CH));
+    unsigned long long cf = pack2(__byte_perm(ca, magic, 0x7650u | CH), __byte_perm(cb, magic, 0x7650u | CH));
+    unsigned long long wf = pack2(__byte_perm(wa, magic, 0x7650u | CH), __byte_perm(wb, magic, 0x7650u | CH));
     cf = fadd2(cf, NEG);
     wf = fadd2(wf, NEG);
     const unsigned long long r = fadd2(ffma2(cf, a2, fmul2(wf, b2)), MAGIC);
     unpack2(r, ra, rb);
 }
 __device__ __forceinline__ void blend_pair(uint32_t ca, uint32_t cb, uint32_t wa, uint32_t wb, unsigned long long a2,
-                                           unsigned long long b2, uint32_t &oa, uint32_t &ob)
+                                           unsigned long long b2, uint32_t magic, uint32_t &oa, uint32_t &ob)
 {
     uint32_t a0, b0, a1, b1, a2r, b2r;
-    blend_pair_ch<0>(ca, cb, wa, wb, a2, b2, a0, b0);
-    blend_pair_ch<1>(ca, cb, wa, wb, a2, b2, a1, b1);
-    blend_pair_ch<2>(ca, cb, wa, wb, a2, b2, a2r, b2r);
+    blend_pair_ch<0>(ca, cb, wa, wb, a2, b2, magic, a0, b0);
+    blend_pair_ch<1>(ca, cb, wa, wb, a2, b2, magic, a1, b1);
+    blend_pair_ch<2>(ca, cb, wa, wb, a2, b2, magic, a2r, b2r);
     // low byte of every result (0..255: t <= 255.00003 rounds to at most 255) -> B | G << 8 | R << 16
     oa = __byte_perm(__byte_perm(a0, a1, 0x0040), a2r, 0x3410) & 0xFFFFFFu;
     ob = __byte_perm(__byte_perm(b0, b1, 0x0040), b2r, 0x3410) & 0xFFFFFFu;
@@ -471,8 +474,9 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
             if (need) {
                 const uint32_t ab = __float_as_uint(p.alpha), bb = __float_as_uint(p.beta);
                 const unsigned long long a2 = pack2(ab, ab), b2 = pack2(bb, bb);
-                if (need & 3u) blend_pair(px[0], px[1], wv[0], wv[1], a2, b2, bl[0], bl[1]);
-                if (need & 12u) blend_pair(px[2], px[3], wv[2], wv[3], a2, b2, bl[2], bl[3]);
+                const uint32_t magic = p.magic;
+                if (need & 3u) blend_pair(px[0], px[1], wv[0], wv[1], a2, b2, magic, bl[0], bl[1]);
+                if (need & 12u) blend_pair(px[2], px[3], wv[2], wv[3], a2, b2, magic, bl[2], bl[3]);
             }
         }
 #pragma unroll
@@ -858,7 +862,7 @@ extern "C" int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *c
     P.Hc = canvas_h; P.Wc = canvas_w;
     P.f0.src = src; P.f0.roi = roi; P.f0.spitch = src_pitch; P.f0.rpitch = roi_pitch; P.f0.h = src_h; P.f0.w = src_w;
     make_invmap(H_host, P.f0.M);
-    P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp;
+    P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp; P.magic = 0x4B000000u;
     {
         DeviceTables tb;
         const int st = device_tables(tb);
@@ -959,7 +963,7 @@ extern "C" int mk_mapper_update_batch(uint8_t *canvas, size_t canvas_pitch, uint
     P.canvas = canvas; P.cmask = cmask; P.wacc = wacc;
     P.cpitch = canvas_pitch; P.mpitch = cmask_pitch; P.wpitch = wacc_pitch;
     P.Hc = canvas_h; P.Wc = canvas_w;
-    P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp;
+    P.alpha = (float)alpha; P.beta = (float)(1.0 - alpha); P.ramp = feather_ramp; P.magic = 0x4B000000u;
     {
         DeviceTables tb;
         const int rc = device_tables(tb);
