@@ -201,15 +201,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    s_match = torch.cuda.Stream(device=dev)     # matching and compositing of a frame are independent: two streams
+    main = torch.cuda.current_stream(dev)
+
     def one_step(k, mp, ev=None):
-        if ev: ev[0].record()
-        matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
-        if ev: ev[1].record()
+        """ev = [start, match done, compositing done, step done] recorded on the streams that run the work."""
+        if ev: ev[0].record(main)
+        s_match.wait_stream(main)
+        with torch.cuda.stream(s_match):
+            matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
+            if ev: ev[1].record(s_match)
         if multi:
             mosaic.step_planned(k, frames[k])
         else:
             mp.update_device(frames[k], Hs[k])
-        if ev: ev[2].record()
+        if ev: ev[2].record(main)
+        main.wait_stream(s_match)
+        if ev: ev[3].record(main)
 
     # ---------------- device-resident throughput ("value") ----------------
     def timed_pass(mp, collect_bytes, do_flush=True):
@@ -219,7 +227,7 @@ def run_b200(args):
         clocks = ClockSampler(local)
         clocks.start()
         time.sleep(0.25)
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
         n0 = mb.launch_count()
         barrier()
         t0 = time.perf_counter()
@@ -231,15 +239,36 @@ def run_b200(args):
         t1 = time.perf_counter()
         launches = mb.launch_count() - n0
         ck = clocks.stop(t0, t1)
-        step_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
-        match_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
-        blend_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
+        step_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
+        match_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])      # both measured from the common start: they overlap
+        blend_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
         nbytes = None
         if collect_bytes and not multi:
             nbytes = np.array([mp.footprint_bytes(fh, fw, Hs[W + k]) for k in range(K)], np.float64)
         return step_ms, match_ms, blend_ms, nbytes, launches, ck
 
     step_ms, match_ms, blend_ms, nbytes, launches, clocks = timed_pass(mapper, True)
+    overlapped = {"match": float(match_ms.mean()), "warp_blend": float(blend_ms.mean())}
+    def isolated_times(make_mapper, time_match=True):
+        """The two kernels of a step, each timed ALONE on the same inputs (L2 flushed before every launch): roofline inputs."""
+        iso_m, iso_b = [], []
+        mp_iso = make_mapper()
+        for k in range(W):
+            mp_iso.update_device(frames[k], Hs[k])
+        for k in range(K):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if time_match:
+                flush.zero_()
+                e[0].record(); matcher.knn_match_device(desc_d[W + k + 1], desc_d[W + k], RATIO); e[1].record()
+            flush.zero_()
+            e[2].record(); mp_iso.update_device(frames[W + k], Hs[W + k]); e[3].record()
+            torch.cuda.synchronize()
+            iso_m.append(e[0].elapsed_time(e[1]) if time_match else 0.0); iso_b.append(e[2].elapsed_time(e[3]))
+        mp_iso.release()
+        return np.array(iso_m), np.array(iso_b)
+
+    if not multi:
+        match_ms, blend_ms = isolated_times(lambda: factory(CANVAS, CANVAS))
     total_ms = float(step_ms.sum())
     if multi:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -252,8 +281,9 @@ def run_b200(args):
         mapper.release(); mapper = None
         torch.cuda.empty_cache()
         fm = factory(CANVAS, CANVAS, blend="feather")
-        f_step, f_match, f_blend, _, _, _ = timed_pass(fm, False)
+        f_step, _, _, _, _, _ = timed_pass(fm, False)
         fbytes = np.array([fm.footprint_bytes(fh, fw, Hs[W + k]) for k in range(K)], np.float64)
+        _, f_blend = isolated_times(lambda: factory(CANVAS, CANVAS, blend="feather"), time_match=False)
         feather = {"value": K / (float(f_step.sum()) * 1e-3), "unit": "frames/s", "ms_per_step": float(f_step.mean()),
                    "roofline": roofline(fbytes, f_blend), "oracle": "numpy/C restatement of SURVEY A.4b (extension, no reference code)"}
         fm.release()
@@ -306,11 +336,12 @@ def run_b200(args):
             (f"BASELINE configs[1] per GPU, tile-sharded as in configs[3]: {grid[0]}x{grid[1]} tiles of 16384^2 over {world} GPUs, one 1920x1080 "
              "frame stream per rank, frames routed by warped footprint (NCCL send/recv), poses all-gathered once, 5000x32B Hamming kNN per frame"),
             "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events); inputs {nframes * fh * fw * 3 / 1e9:.2f} GB > L2",
-            "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+            "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching runs on its own stream next to compositing",
             "blend": "alpha", "interp": "linear", "canvas": [grid[0] * CANVAS, grid[1] * CANVAS], "frame": [fw, fh],
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "breakdown_ms": {"match": float(match_ms.mean()), "warp_blend": float(blend_ms.mean())},
+        "breakdown_ms": {"match_alone": float(match_ms.mean()), "warp_blend_alone": float(blend_ms.mean()),
+                         "match_overlapped": overlapped["match"], "warp_blend_overlapped": overlapped["warp_blend"]},
         "match_pairs_per_s": NDESC * NDESC / (float(match_ms.mean()) * 1e-3),
     }
     if not multi:
