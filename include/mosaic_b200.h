@@ -41,7 +41,9 @@ typedef enum mk_status {
 typedef enum mk_norm {
     MK_NORM_HAMMING = 0,  /* cv2.NORM_HAMMING on uint8 rows (north-star ORB metric)  */
     MK_NORM_L2_U8 = 1,    /* cv2.NORM_L2 on uint8 rows  (what registration.py:231 does for ORB) */
-    MK_NORM_L2_F32 = 2    /* cv2.NORM_L2 on float32 rows (SIFT)                      */
+    MK_NORM_L2_F32 = 2,   /* cv2.NORM_L2 on float32 rows (SIFT)                      */
+    MK_NORM_HAMMING_TC = 3 /* MK_NORM_HAMMING, same results, optional engine: bit-expanded rows (<= 32 bytes) through the
+                             tcgen05 fp8 GEMM when the problem is large; otherwise the XOR+POPC kernel */
 } mk_norm;
 
 typedef enum mk_interp {

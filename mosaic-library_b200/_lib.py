@@ -15,7 +15,7 @@ LIB_PATH = PKG_DIR / "libmosaic_b200.so"
 CSRC = PKG_DIR / "csrc"
 
 MK_OK = 0
-NORM_HAMMING, NORM_L2_U8, NORM_L2_F32 = 0, 1, 2
+NORM_HAMMING, NORM_L2_U8, NORM_L2_F32, NORM_HAMMING_TC = 0, 1, 2, 3
 INTER_LINEAR, INTER_CUBIC = 1, 2
 BLEND_ALPHA, BLEND_FEATHER = 0, 1
 

@@ -46,8 +46,8 @@ struct KnnParams {
 };
 
 // tensor-core path (mk_knn_tc.cu)
-size_t knn_tc_workspace_bytes(int nq, int nt, int dim);
-size_t knn_tc_batched_workspace_bytes(int npairs, int max_nq, int max_nt, int dim, int total_rows);
+size_t knn_tc_workspace_bytes(int norm, int nq, int nt, int dim);
+size_t knn_tc_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim, int total_rows);
 bool knn_tc_supported(int norm, int nq, int nt, int dim);
 int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
                const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
@@ -500,6 +500,9 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
 
 using namespace mk;
 
+// MK_NORM_HAMMING_TC is MK_NORM_HAMMING with the optional tensor-core engine: everywhere except the engine choice it is Hamming.
+static inline int base_norm(int norm) { return norm == MK_NORM_HAMMING_TC ? MK_NORM_HAMMING : norm; }
+
 // Problems large enough to amortise the extra launches go through the tensor-core GEMM.
 static bool use_tc(int norm, int nq, int nt, int dim)
 {
@@ -508,9 +511,9 @@ static bool use_tc(int norm, int nq, int nt, int dim)
 
 extern "C" size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim)
 {
-    const KnnPlan pl = make_plan(norm, 1, nq, nt);
+    const KnnPlan pl = make_plan(base_norm(norm), 1, nq, nt);
     size_t bytes = pl.ticket_bytes + pl.part_bytes;
-    if (use_tc(norm, nq, nt, dim)) bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_workspace_bytes(nq, nt, dim);
+    if (use_tc(norm, nq, nt, dim)) bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_workspace_bytes(norm, nq, nt, dim);
     return bytes;
 }
 
@@ -523,10 +526,10 @@ static bool use_tc_batched(int norm, int npairs, int max_nq, int max_nt, int dim
 
 extern "C" size_t mk_knn2_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim, int total_rows)
 {
-    const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
+    const KnnPlan pl = make_plan(base_norm(norm), npairs, max_nq, max_nt);
     size_t bytes = pl.ticket_bytes + pl.part_bytes;
     if (use_tc_batched(norm, npairs, max_nq, max_nt, dim))
-        bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_batched_workspace_bytes(npairs, max_nq, max_nt, dim, total_rows);
+        bytes = ((bytes + 255) & ~(size_t)255) + knn_tc_batched_workspace_bytes(norm, npairs, max_nq, max_nt, dim, total_rows);
     return bytes;
 }
 
@@ -534,7 +537,8 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
                        float *dist, double ratio, uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes,
                        void *stream)
 {
-    int rc = check_knn_args(norm, dim, row_stride);
+    const int bn = base_norm(norm);
+    int rc = check_knn_args(bn, dim, row_stride);
     if (rc != MK_OK) return rc;
     if (nq < 0 || nt < 0 || (nq > 0 && (!q || !idx || !dist)) || (nt > 0 && !t)) { set_error("mk_knn2: null pointer or negative size"); return MK_ERR_ARG; }
     if ((q && !aligned(q, 16)) || (t && !aligned(t, 16))) { set_error("mk_knn2: descriptor base must be 16-byte aligned"); return MK_ERR_ALIGN; }
@@ -545,17 +549,18 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
     if (use_tc(norm, nq, nt, dim)) {
         // [SIMT scratch][tensor-core scratch]; the SIMT kernel only runs if the prep pass found values that
         // bf16 cannot hold exactly (never the case for uint8 rows, so it is not even launched for them)
-        const KnnPlan pl = make_plan(norm, 1, nq, nt);
+        const KnnPlan pl = make_plan(bn, 1, nq, nt);
         const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
         rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, nullptr, nullptr, 1, nullptr, 0, idx, dist, ratio, keep, n_keep,
                         static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags);
-        if (rc != MK_OK || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;   // dim*255^2 < 2^22: the TC result always stands
+        // uint8 rows: dim*255^2 < 2^22, bit counts <= 256: the TC result always stands
+        if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
         P.guard = flags;
-        return run_knn(norm, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+        return run_knn(bn, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
     }
-    return run_knn(norm, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_knn(bn, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int dim, size_t row_stride, const int32_t *set_off,
@@ -563,7 +568,8 @@ extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int d
                                float *dist, double ratio, uint8_t *keep, int32_t *n_keep, void *workspace,
                                size_t workspace_bytes, void *stream)
 {
-    int rc = check_knn_args(norm, dim, row_stride);
+    const int bn = base_norm(norm);
+    int rc = check_knn_args(bn, dim, row_stride);
     if (rc != MK_OK) return rc;
     if (npairs < 0 || max_nq < 0 || max_nt < 0 || (npairs > 0 && (!desc || !set_off || !pairs || !out_off || !idx || !dist))) {
         set_error("mk_knn2_batched: null pointer or negative size");
@@ -577,16 +583,16 @@ extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int d
     P.nq = max_nq; P.nt = max_nt; P.dim = dim; P.stride = row_stride;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
     if (total_rows > 0 && use_tc_batched(norm, npairs, max_nq, max_nt, dim)) {
-        const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
+        const KnnPlan pl = make_plan(bn, npairs, max_nq, max_nt);
         const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2_batched: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
         rc = knn_tc_run(norm, desc, max_nq, nullptr, max_nt, dim, row_stride, set_off, pairs, npairs, out_off, total_rows, idx, dist,
                         ratio, keep, n_keep, static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes,
                         (cudaStream_t)stream, &flags);
-        if (rc != MK_OK || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
+        if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
         P.guard = flags;
-        return run_knn(norm, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+        return run_knn(bn, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
     }
-    return run_knn(norm, P, npairs, max_nq, max_nt, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_knn(bn, P, npairs, max_nq, max_nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -39,12 +39,15 @@ constexpr int TC_CW = TC_N / TC_CSPLIT;         // columns scanned per epilogue 
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2.. epilogue
 constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
+constexpr int TC_TABS = 4;         // ring of per-tile column tables (written two tiles ahead by the epilogue threads)
 
 struct TcParams {
-    const __nv_bfloat16 *qb, *tb;   // bf16 copies [n][KP]
+    const void *qb, *tb;            // operand copies: bf16 [n][kp] (L2) or fp8-e4m3 0/1 bytes [n][kp] (Hamming on bit-expanded rows)
     const float *qn, *tn;           // squared norms
     int *flags;                     // see mk_common.cuh: flags[0] inputs not exact in bf16, flags[3] result needs the SIMT recompute
     int nq, nt, kp, dim;            // single pair: sizes; batched: upper bounds
+    int row_bytes, atom_elems;      // operand row = row_bytes (128 or 256) = kp * element size; elements per 128-byte swizzle atom
+    int hamming;                    // 1: scores are Hamming counts (distance = count), 0: squared L2 (distance = sqrtf)
     const int32_t *set_off, *pairs, *out_off;   // batched tables (device) or null: rows of qb == rows of tb == all sets
     int splits, nqb;
     unsigned long long *part;
@@ -107,15 +110,28 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
 // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// same geometry, A = B = E4M3 (format code 0): 0/1 bytes of bit-expanded binary descriptors, K = 32 per instruction
+constexpr uint32_t TC_IDESC_F8 = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+template <int KIND>   // 0: kind::f16 (bf16 operands), 1: kind::f8f6f4 (e4m3 operands); both consume 32 bytes of K per instruction
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (KIND == 0)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(TC_IDESC_F8), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned long long *bar)
 {
@@ -131,6 +147,90 @@ __device__ __forceinline__ void umma_commit(unsigned long long *bar)
                    "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
                    "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
                  : "r"(taddr))
+
+// tcgen05.wait::ld tied to the registers of one load, so the compiler cannot move their uses above the wait
+#define TC_WAIT_LD(r)                                                                                                          \
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"                                                                            \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),   \
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),        \
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),      \
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])                    \
+                 :: "memory")
+
+__device__ __forceinline__ int4 lds128(uint32_t saddr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
+// ---- epilogue scans: 32 accumulator columns of one query row against the per-column table of the tile ------------------------
+// KIND 0 (L2): S = q.t is an exact integer < 2^23, so bits(S + 2^23) = 0x4B000000 + S and
+//     key = -256 * bits + (|t|^2 * 128 + col)  ==  (|t|^2 - 2 S) * 128 + col      (mod 2^32; 256 * 0x4B000000 == 0)
+// is ONE IMAD per element; it orders candidates by (d^2, column) because |q|^2 is a per-row constant, it fits int32
+// (|.| <= 2^30 + 127), and min / second-min over keys needs no branch, hence no warp divergence.
+template <bool PARTIAL>
+__device__ __forceinline__ void scan32_i32(const uint32_t (&r)[32], uint32_t tsaddr, int &b1, int &b2)
+{
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const int4 t4 = lds128(tsaddr + j * 4);
+        const int tv[4] = { t4.x, t4.y, t4.z, t4.w };
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int bits = __float_as_int(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
+            int key = bits * -256 + tv[u];
+            if (PARTIAL) key = (tv[u] == 0x7fffffff) ? 0x7fffffff : key;   // tail columns: another set (batched) or zero fill
+            b2 = min(b2, max(b1, key));
+            b1 = min(b1, key);
+        }
+    }
+}
+
+// KIND 1 (Hamming): S <= 256 and popc(t) - 2 S lies in [-256, 256], so a candidate fits 16 bits:
+//     key16 = (popc(t) + 256 - 2 S) << 6 | pair       pair = chunk * 16 + j  (the thread's 64 columns as 32 column pairs)
+// Two columns (j, j + 16 of the same 32-column chunk) share one register: PRMT packs the two S, one IMAD forms both keys
+// (T2 - 128 * S2: both halves stay in [0, 0xFFFF], so no borrow crosses them) and VIMNMX.U16x2 keeps the two best of each
+// half.  0xFFFF marks columns beyond the train set.
+template <bool PARTIAL>
+__device__ __forceinline__ void scan32_u16(const uint32_t (&r)[32], uint32_t tsaddr, uint32_t &b1, uint32_t &b2)
+{
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const int4 t4 = lds128(tsaddr + j * 4);
+        const uint32_t tv[4] = { (uint32_t)t4.x, (uint32_t)t4.y, (uint32_t)t4.z, (uint32_t)t4.w };
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t a = __float_as_uint(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
+            const uint32_t b = __float_as_uint(__fadd_rn(__uint_as_float(r[j + u + 16]), 8388608.0f));
+            const uint32_t s2 = __byte_perm(a, b, 0x5410);
+            uint32_t key = s2 * 0xFFFFFF80u + tv[u];                       // T2 - 128 * S2
+            if (PARTIAL)
+                key |= ((tv[u] & 0xFFFFu) == 0xFFFFu ? 0xFFFFu : 0u) | ((tv[u] >> 16) == 0xFFFFu ? 0xFFFF0000u : 0u);
+            b2 = __vminu2(b2, __vmaxu2(b1, key));
+            b1 = __vminu2(b1, key);
+        }
+    }
+}
+
+// One tile for one thread: 64 columns as two tcgen05.ld of 32, the second in flight while the first is scanned.
+template <int KIND, bool PARTIAL>
+__device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t tsaddr, uint32_t &b1, uint32_t &b2)
+{
+    constexpr uint32_t CH = KIND == 1 ? 64 : 128;     // table bytes per 32-column chunk
+    uint32_t ra[32], rb[32];
+    auto scan = [&](const uint32_t (&r)[32], uint32_t ts) {
+        if constexpr (KIND == 1) scan32_u16<PARTIAL>(r, ts, b1, b2);
+        else scan32_i32<PARTIAL>(r, ts, reinterpret_cast<int &>(b1), reinterpret_cast<int &>(b2));
+    };
+    TC_LD32(taddr, ra);
+    TC_WAIT_LD(ra);
+    TC_LD32(taddr + 32u, rb);
+    scan(ra, tsaddr);
+    TC_WAIT_LD(rb);
+    scan(rb, tsaddr + CH);
+}
+static_assert(TC_CW == 64, "scan_tile walks two 32-column chunks");
 
 struct TcKey {
     using Key = unsigned long long;
@@ -148,12 +248,13 @@ struct TcSmem {
     static constexpr int B_BYTES = TC_N * 128;                  // one k-half of one B stage
     static __host__ __device__ constexpr int a_off(int half) { return half * A_BYTES; }
     static __host__ __device__ constexpr int b_off(int stage, int half) { return 2 * A_BYTES + (stage * 2 + half) * B_BYTES; }
-    static __host__ __device__ constexpr int tn_off(int stage) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + stage * TC_N * 4; }
-    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + 2 * TC_N * 4;      // [TC_CSPLIT][128][2] u64
+    static __host__ __device__ constexpr int tn_off(int slot) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + slot * TC_N * 4; }   // TC_TABS slots
+    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + TC_TABS * TC_N * 4;      // [TC_CSPLIT][128][2] u64
     static constexpr int bar_off = keys_off + TC_CSPLIT * TC_M * 2 * 8;
     static constexpr int total = bar_off + 128;
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ TcParams p)
 {
@@ -162,8 +263,10 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TcSmem::bar_off);
     unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_STAGES,
-                       *bar_tfull = bars + 1 + 2 * TC_STAGES, *bar_tempty = bars + 3 + 2 * TC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + 2 * TC_STAGES);
+                       *bar_tfull = bars + 1 + 2 * TC_STAGES, *bar_tempty = bars + 3 + 2 * TC_STAGES,
+                       *bar_tab = bars + 5 + 2 * TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + TC_TABS + 2 * TC_STAGES);
+    static_assert((6 + TC_TABS + 2 * TC_STAGES) * 8 <= 128, "barrier block");
     __shared__ int s_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,7 +281,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     const int q0 = qblk * TC_M;
     if (q0 >= nq) return;
-    const int nhalf = p.kp / TC_KA;                      // 1 (K <= 64) or 2 (K = 128)
+    const int nhalf = p.row_bytes / 128;                 // 128-byte swizzle atoms per operand row: 1 or 2
     // train tiles of this split
     const int ntiles = (nt + TC_N - 1) / TC_N;
     const int per = (ntiles + p.splits - 1) / p.splits;
@@ -189,6 +292,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_init(bar_a, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, TC_EPI_THREADS); }
+        for (int s = 0; s < TC_TABS; ++s) mbar_init(bar_tab + s, KIND == 1 ? TC_N / 2 : TC_N);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {   // allocate all 512 TMEM columns (2 accumulator stages x 256)
@@ -204,13 +308,13 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
-            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * TC_KA, qrow0 + q0, bar_a);
+            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * p.atom_elems, qrow0 + q0, bar_a);
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % TC_STAGES, use = i / TC_STAGES;
                 if (use > 0) mbar_wait(bar_bempty + s, (use - 1) & 1);
                 mbar_expect_tx(bar_bfull + s, (uint32_t)(nhalf * TcSmem::B_BYTES));
                 for (int h = 0; h < nhalf; ++h)
-                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * TC_KA, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
+                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * p.atom_elems, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
             }
         }
     } else if (warp == 1) {
@@ -229,8 +333,8 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     const uint64_t ad = make_sw128_desc(smem_addr(smem + TcSmem::a_off(h)));
                     const uint64_t bd = make_sw128_desc(smem_addr(smem + TcSmem::b_off(s, h)));
 #pragma unroll
-                    for (int k = 0; k < TC_KA / 16; ++k) {
-                        umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), TC_IDESC, accumulate);   // +32 B per K step
+                    for (int k = 0; k < 4; ++k) {
+                        umma<KIND>(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), accumulate);   // +32 B per K step
                         accumulate = 1;
                     }
                 }
@@ -239,63 +343,102 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue: one query row x one 128-column half per thread =====================
-        // S = q.t is an exact integer < 2^23, so bits(S + 2^23) = 0x4B000000 + S and
-        //     key = -256 * bits + (|t|^2 * 128 + col)  ==  (|t|^2 - 2 S) * 128 + col      (mod 2^32; 256 * 0x4B000000 == 0)
-        // is ONE IMAD per element; it orders candidates by (d^2, column) because |q|^2 is a per-row constant, it fits
-        // int32 (|.| <= 2^30 + 127) and min / second-min over keys needs no branch, hence no warp divergence.
+        // ===================== epilogue: one query row x one 128-column group per thread (see scan32_*) =====================
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
         const int chalf = (warp - 2) >> 2;                 // which column group of every tile this warp scans
         const int row = quarter * 32 + lane;
-        const int et = tid - 64;                           // index among the epilogue threads
         const int qi = q0 + row;
         const int qn = (qi < nq) ? (int)p.qn[qrow0 + qi] : 0;    // exact integer
         unsigned long long k1 = TcKey::NONE, k2 = TcKey::NONE;   // running (d^2 << 32 | train index)
-        int *s_T0 = reinterpret_cast<int *>(smem + TcSmem::tn_off(0));
+        auto fold = [&](uint32_t d, uint32_t col) {
+            const unsigned long long key = ((unsigned long long)d << 32) | col;
+            const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
+        };
+        // Per-tile column tables.  The first TC_N (Hamming: TC_N / 2) epilogue threads each own one entry; the entry of tile
+        // i + 2 is LOADED before tile i is scanned and STORED after it, so the global-load latency hides behind the scan.
+        // Slot (i + 2) % 4 was last read for tile i - 2, which every thread left before tile i could start (its accumulator
+        // is the one tile i - 2 released), and the readers of tile i + 2 wait for tile i's release anyway: no extra coupling.
+        const int et = tid - 64;
+        const bool tab_writer = et < (KIND == 1 ? TC_N / 2 : TC_N);
+        // raw loads first (table_load), arithmetic on them only when the entry is stored (table_store): nothing between the
+        // two touches the loaded registers, so the scan never waits on the global load
+        const int pid = et % (TC_CW / 2);                  // Hamming: pair owned by this thread ...
+        const int pcol = (et / (TC_CW / 2)) * TC_CW + (pid >> 4) * 32 + (pid & 15);   // ... = columns pcol (low half), pcol + 16 (high)
+        auto table_load = [&](int i, float &ta, float &tb) {
+            const int col0 = (tile_lo + i) * TC_N;
+            if constexpr (KIND == 1) {
+                ta = (col0 + pcol < nt) ? __ldg(p.tn + trow0 + col0 + pcol) : -1.0f;
+                tb = (col0 + pcol + 16 < nt) ? __ldg(p.tn + trow0 + col0 + pcol + 16) : -1.0f;
+            } else {
+                ta = (col0 + et < nt) ? __ldg(p.tn + trow0 + col0 + et) : -1.0f;
+                tb = 0.0f;
+            }
+        };
+        auto table_store = [&](int i, float ta, float tb) {
+            int v;
+            if constexpr (KIND == 1) {       // (popc(t) + 256) << 6 | pair per half; 0xFFFF beyond nt
+                const uint32_t lo = ta >= 0.0f ? ((((uint32_t)ta + 256u) << 6) | (uint32_t)pid) : 0xFFFFu;
+                const uint32_t hi = tb >= 0.0f ? ((((uint32_t)tb + 256u) << 6) | (uint32_t)pid) : 0xFFFFu;
+                v = (int)(lo | (hi << 16));
+            } else {                         // |t|^2 * 128 + (col & 63); INT_MAX beyond nt
+                v = ta >= 0.0f ? ((int)ta * 128 + (et % TC_CW)) : 0x7fffffff;
+            }
+            reinterpret_cast<int *>(smem + TcSmem::tn_off(i % TC_TABS))[et] = v;
+            mbar_arrive(bar_tab + i % TC_TABS);
+        };
+        if (tab_writer) {
+            float ta, tb;
+            if (my_tiles > 0) { table_load(0, ta, tb); table_store(0, ta, tb); }
+            if (my_tiles > 1) { table_load(1, ta, tb); table_store(1, ta, tb); }
+        }
+        // Hamming: running best two of each 16-bit half as 32-bit keys (count + 256) << 22 | tile << 6 | pair, ordered like
+        // (count, column) within the half; unpacked once after the last tile
+        uint32_t run[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };   // [half][rank]
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1, acc_use = i >> 1;
             const int col0 = (tile_lo + i) * TC_N;
-            int *s_T = s_T0 + acc * TC_N;
-            // per-column constant |t|^2 * 128 + (col & 127); INT_MAX beyond nt (S = 0 there, so the key stays INT_MAX)
-            if (et < TC_N) s_T[et] = (col0 + et < nt) ? ((int)p.tn[trow0 + col0 + et] * 128 + (et % TC_CW)) : 0x7fffffff;
-            const bool partial = col0 + TC_N > nt;        // the tile's tail columns belong to another set (batched) or are zero fill
-            asm volatile("bar.sync 1, %0;\n" ::"n"(TC_EPI_THREADS) : "memory");
+            const bool partial = col0 + TC_N > nt;        // warp-uniform, last tile of a set only
+            const uint32_t tsaddr = smem_addr(smem + TcSmem::tn_off(i % TC_TABS)) + (uint32_t)chalf * (uint32_t)(KIND == 1 ? TC_CW * 2 : TC_CW * 4);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * TC_CW);
+            const bool prefetch = tab_writer && i + 2 < my_tiles;
+            float ta = 0.0f, tb = 0.0f;
+            if (prefetch) table_load(i + 2, ta, tb);
+            mbar_wait(bar_tab + i % TC_TABS, (i / TC_TABS) & 1);
             mbar_wait(bar_tfull + acc, acc_use & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * TC_CW);
-            int b1 = 0x7fffffff, b2 = 0x7fffffff;
-#pragma unroll 1
-            for (int c = 0; c < TC_CW; c += 32) {
-                uint32_t r[32];
-                TC_LD32(taddr + (uint32_t)c, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                const int *T = s_T + chalf * TC_CW + c;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int4 t4 = *reinterpret_cast<const int4 *>(T + j);
-                    const int tv[4] = { t4.x, t4.y, t4.z, t4.w };
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int bits = __float_as_int(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
-                        int key = bits * -256 + tv[u];
-                        if (partial) key = (tv[u] == 0x7fffffff) ? 0x7fffffff : key;   // warp-uniform branch, last tile only
-                        b2 = min(b2, max(b1, key));
-                        b1 = min(b1, key);
-                    }
-                }
-            }
+            uint32_t b1 = KIND == 1 ? 0xFFFFFFFFu : 0x7fffffffu, b2 = b1;
+            if (partial) scan_tile<KIND, true>(taddr, tsaddr, b1, b2);
+            else scan_tile<KIND, false>(taddr, tsaddr, b1, b2);
             tc_fence_before();
             mbar_arrive(bar_tempty + acc);                 // all epilogue threads release the accumulator stage
-            // fold the tile's two best into the running keys (key >> 7 = d^2 - |q|^2, key & 127 = column in this half)
-            if (b1 != 0x7fffffff) {
-                const unsigned long long key = ((unsigned long long)(uint32_t)((b1 >> 7) + qn) << 32) |
-                                               (uint32_t)(col0 + chalf * TC_CW + (b1 & 127));
-                const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
+            if (prefetch) table_store(i + 2, ta, tb);
+            // fold the tile's best candidates into the running keys
+            if constexpr (KIND == 1) {
+                const uint32_t tl = (uint32_t)i << 6;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const uint32_t b = r ? b2 : b1;
+                        const uint32_t key = (h ? (b & 0xFFC00000u) : ((b << 16) & 0xFFC00000u)) | tl | ((h ? (b >> 16) : b) & 63u);
+                        const uint32_t mx = max(run[2 * h], key);
+                        run[2 * h] = min(run[2 * h], key);
+                        run[2 * h + 1] = min(run[2 * h + 1], mx);
+                    }
+                }
+            } else {                                       // key >> 7 = d^2 - |q|^2, key & 127 = column in this group
+                const uint32_t cbase = (uint32_t)(col0 + chalf * TC_CW);
+                if (b1 != 0x7fffffffu) fold((uint32_t)(((int)b1 >> 7) + qn), cbase + (b1 & 127u));
+                if (b2 != 0x7fffffffu) fold((uint32_t)(((int)b2 >> 7) + qn), cbase + (b2 & 127u));
             }
-            if (b2 != 0x7fffffff) {
-                const unsigned long long key = ((unsigned long long)(uint32_t)((b2 >> 7) + qn) << 32) |
-                                               (uint32_t)(col0 + chalf * TC_CW + (b2 & 127));
-                const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
+        }
+        if constexpr (KIND == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t r = run[e], dpart = r >> 22, pr = r & 63u, tile = (r >> 6) & 0xFFFFu;
+                if (dpart != 1023u)
+                    fold(dpart - 256u + (uint32_t)qn,
+                         (uint32_t)((tile_lo + (int)tile) * TC_N + chalf * TC_CW) + (pr >> 4) * 32u + (pr & 15u) + (uint32_t)(e >> 1) * 16u);
             }
         }
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
@@ -352,7 +495,11 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         int i1, i2; float d1, d2;
         TcKey::decode(k1, i1, d1);
         TcKey::decode(k2, i2, d2);
-        if ((k1 != TcKey::NONE && (uint32_t)(k1 >> 32) >= 4194304u) || (k2 != TcKey::NONE && (uint32_t)(k2 >> 32) >= 4194304u))
+        if (p.hamming) {                                   // the score is the Hamming count itself
+            if (k1 != TcKey::NONE) d1 = (float)(uint32_t)(k1 >> 32);
+            if (k2 != TcKey::NONE) d2 = (float)(uint32_t)(k2 >> 32);
+        }
+        if (!p.hamming && ((k1 != TcKey::NONE && (uint32_t)(k1 >> 32) >= 4194304u) || (k2 != TcKey::NONE && (uint32_t)(k2 >> 32) >= 4194304u)))
             atomicOr(p.flags + 3, 1);                      // sqrtf no longer injective: let the SIMT kernel redo the call
         p.idx[2 * o] = i1; p.idx[2 * o + 1] = i2;
         p.dist[2 * o] = d1; p.dist[2 * o + 1] = d2;
@@ -394,6 +541,30 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ 
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
 }
 
+// ---- prep for Hamming: bits -> e4m3 bytes (1.0 = 0x38 / 0), popcounts as "norms" -----------------------------------------
+__global__ void __launch_bounds__(256) knn_tc_prep_bits_kernel(const uint8_t *__restrict__ q, int nq, const uint8_t *__restrict__ t, int nt,
+                                                               size_t stride_bytes, int nbytes, int kp, uint8_t *__restrict__ qb,
+                                                               uint8_t *__restrict__ tb, float *__restrict__ qn, float *__restrict__ tn,
+                                                               int32_t *n_keep)
+{
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row == 0 && lane == 0 && n_keep) *n_keep = 0;
+    if (row >= nq + nt) return;
+    const bool is_q = row < nq;
+    if (!is_q) row -= nq;
+    const uint8_t *src = (is_q ? q : t) + (size_t)row * stride_bytes;
+    uint8_t *dst = (is_q ? qb : tb) + (size_t)row * kp;
+    int cnt = 0;
+    for (int k = lane; k < kp; k += 32) {
+        const int bit = (k < nbytes * 8) ? ((src[k >> 3] >> (k & 7)) & 1) : 0;
+        dst[k] = bit ? 0x38 : 0x00;
+        cnt += bit;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) (is_q ? qn : tn)[row] = (float)cnt;
+}
+
 // ---- host -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -412,15 +583,16 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int box_rows)
+// esz = 2: bf16 rows, 64 elements per 128-byte atom; esz = 1: e4m3 bytes, 128 elements per atom
+static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int box_rows, int esz)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MK_ERR_CUDA; }
     const cuuint64_t dims[2] = { (cuuint64_t)kp, (cuuint64_t)rows };
-    const cuuint64_t strides[1] = { (cuuint64_t)kp * 2 };
-    const cuuint32_t box[2] = { (cuuint32_t)TC_KA, (cuuint32_t)box_rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)kp * esz };
+    const cuuint32_t box[2] = { (cuuint32_t)(128 / esz), (cuuint32_t)box_rows };
     const cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = fn(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MK_ERR_CUDA; }
@@ -428,15 +600,16 @@ static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int bo
 }
 
 struct TcPlan {
-    int kp, nqb, splits;
+    int kp, esz, nqb, splits;
     size_t off_qb, off_tb, off_qn, off_tn, off_flags, off_tickets, off_part, total;
 };
 
 // rows_q / rows_t: rows of the bf16 copies (batched: both = all rows of all sets and the copies are shared)
-static TcPlan tc_plan(int npairs, int max_nq, int max_nt, int dim, long rows_q, long rows_t, bool shared)
+static TcPlan tc_plan(int norm, int npairs, int max_nq, int max_nt, int dim, long rows_q, long rows_t, bool shared)
 {
     TcPlan pl;
-    pl.kp = dim <= 64 ? 64 : 128;
+    if (norm == MK_NORM_HAMMING_TC) { pl.esz = 1; pl.kp = dim * 8 <= 128 ? 128 : 256; }   // one e4m3 byte per descriptor bit
+    else { pl.esz = 2; pl.kp = dim <= 64 ? 64 : 128; }
     pl.nqb = (max_nq + TC_M - 1) / TC_M;
     const int ntiles = (max_nt + TC_N - 1) / TC_N;
     // one CTA per SM (165 KB of shared memory).  Cost model: waves x (tiles per CTA + 4); the constant stands for the A tile,
@@ -454,8 +627,8 @@ static TcPlan tc_plan(int npairs, int max_nq, int max_nt, int dim, long rows_q, 
     pl.splits = pl.nqb > 0 ? best : 1;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-    pl.off_qb = take((size_t)rows_q * pl.kp * 2);
-    pl.off_tb = shared ? pl.off_qb : take((size_t)rows_t * pl.kp * 2);
+    pl.off_qb = take((size_t)rows_q * pl.kp * pl.esz);
+    pl.off_tb = shared ? pl.off_qb : take((size_t)rows_t * pl.kp * pl.esz);
     pl.off_qn = take((size_t)rows_q * 4);
     pl.off_tn = shared ? pl.off_qn : take((size_t)rows_t * 4);
     pl.off_flags = take(256);
@@ -466,14 +639,15 @@ static TcPlan tc_plan(int npairs, int max_nq, int max_nt, int dim, long rows_q, 
     return pl;
 }
 
-size_t knn_tc_workspace_bytes(int nq, int nt, int dim) { return tc_plan(1, nq, nt, dim, nq, nt, false).total; }
-size_t knn_tc_batched_workspace_bytes(int npairs, int max_nq, int max_nt, int dim, int total_rows)
+size_t knn_tc_workspace_bytes(int norm, int nq, int nt, int dim) { return tc_plan(norm, 1, nq, nt, dim, nq, nt, false).total; }
+size_t knn_tc_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_nt, int dim, int total_rows)
 {
-    return tc_plan(npairs, max_nq, max_nt, dim, total_rows, total_rows, true).total;
+    return tc_plan(norm, npairs, max_nq, max_nt, dim, total_rows, total_rows, true).total;
 }
 
 bool knn_tc_supported(int norm, int nq, int nt, int dim)
 {
+    if (norm == MK_NORM_HAMMING_TC) return dim <= 32 && nq >= 1 && nt >= 2 && nt < (1 << 22);   // 256 bits = two 128-byte atoms of e4m3 bytes
     if (norm != MK_NORM_L2_F32 && norm != MK_NORM_L2_U8) return false;
     if (dim > TC_MAX_KP || nq < 1 || nt < 2) return false;
     return true;
@@ -486,11 +660,11 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out)
 {
     const bool batched = pairs != nullptr;
-    const TcPlan pl = batched ? tc_plan(npairs, nq, nt, dim, total_rows, total_rows, true) : tc_plan(1, nq, nt, dim, nq, nt, false);
+    const TcPlan pl = batched ? tc_plan(norm, npairs, nq, nt, dim, total_rows, total_rows, true) : tc_plan(norm, 1, nq, nt, dim, nq, nt, false);
     if (workspace_bytes < pl.total) { set_error("mk_knn2: workspace too small for the tensor-core path (%zu < %zu)", workspace_bytes, pl.total); return MK_ERR_WORKSPACE; }
     uint8_t *ws = static_cast<uint8_t *>(workspace);
     if (!aligned(ws, 256)) { set_error("mk_knn2: workspace must be 256-byte aligned for the tensor-core path"); return MK_ERR_ALIGN; }
-    __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_qb), *tb = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_tb);
+    void *qb = ws + pl.off_qb, *tb = ws + pl.off_tb;
     float *qn = reinterpret_cast<float *>(ws + pl.off_qn), *tn = reinterpret_cast<float *>(ws + pl.off_tn);
     int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
     const int np = batched ? npairs : 1;
@@ -499,21 +673,27 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
     const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
     const int wpb = 8, rows = rows_q + rows_t;
-    if (norm == MK_NORM_L2_F32)
+    if (norm == MK_NORM_HAMMING_TC)
+        knn_tc_prep_bits_kernel<<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t, stride,
+                                                                        dim, pl.kp, static_cast<uint8_t *>(qb), static_cast<uint8_t *>(tb), qn, tn,
+                                                                        batched ? nullptr : n_keep);
+    else if (norm == MK_NORM_L2_F32)
         knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), rows_q, static_cast<const float *>(t), rows_t,
-                                                                          stride, dim, pl.kp, qb, tb, qn, tn, flags, batched ? nullptr : n_keep);
+                                                                          stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep);
     else
         knn_tc_prep_kernel<uint8_t><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t,
-                                                                            stride, dim, pl.kp, qb, tb, qn, tn, flags, batched ? nullptr : n_keep);
+                                                                            stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep);
     MK_LAUNCH_CHECK("knn_tc_prep_kernel");
     alignas(64) CUtensorMap map_q, map_t;
-    int rc = make_map(&map_q, qb, rows_q, pl.kp, TC_M);
+    int rc = make_map(&map_q, qb, rows_q, pl.kp, TC_M, pl.esz);
     if (rc != MK_OK) return rc;
-    rc = make_map(&map_t, tb, batched ? total_rows : nt, pl.kp, TC_N);
+    rc = make_map(&map_t, tb, batched ? total_rows : nt, pl.kp, TC_N, pl.esz);
     if (rc != MK_OK) return rc;
     TcParams P;
     P.qb = qb; P.tb = tb; P.qn = qn; P.tn = tn; P.flags = flags;
-    P.nq = nq; P.nt = nt; P.kp = pl.kp; P.dim = dim; P.splits = pl.splits; P.nqb = pl.nqb;
+    P.nq = nq; P.nt = nt; P.kp = pl.kp; P.dim = dim;
+    P.row_bytes = pl.kp * pl.esz; P.atom_elems = 128 / pl.esz; P.hamming = norm == MK_NORM_HAMMING_TC;
+    P.splits = pl.splits; P.nqb = pl.nqb;
     P.set_off = set_off; P.pairs = pairs; P.out_off = out_off;
     P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
@@ -522,11 +702,13 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     cudaGetDevice(&dev);
     const int smem = TcSmem::total + 1024;
     if (configured.load() != dev) {
-        MK_CUDA_TRY(cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MK_CUDA_TRY(cudaFuncSetAttribute(knn2_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MK_CUDA_TRY(cudaFuncSetAttribute(knn2_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured.store(dev);
     }
     dim3 grid(pl.nqb, pl.splits, np);
-    knn2_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
+    if (P.hamming) knn2_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
+    else knn2_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
     MK_LAUNCH_CHECK("knn2_tc_kernel");
     *flags_out = flags;
     return MK_OK;

@@ -46,10 +46,10 @@ def _bad_input(msg: str):
     return ValueError(msg)
 
 
-def _norm_code(norm: str, dtype) -> int:
+def _norm_code(norm: str, dtype, engine: str = "popc") -> int:
     if dtype == np.uint8:
         if norm == "hamming":
-            return _lib.NORM_HAMMING
+            return _lib.NORM_HAMMING_TC if engine == "tensor" else _lib.NORM_HAMMING
         if norm == "l2":
             return _lib.NORM_L2_U8
     elif dtype == np.float32:
@@ -88,10 +88,15 @@ def upload_descriptors(desc, device=None) -> tuple[torch.Tensor, int]:
 class Matcher:
     """Brute-force k=2 matcher (reference: registration.py:226-264)."""
 
-    def __init__(self, norm: str = "l2", device=None):
+    def __init__(self, norm: str = "l2", device=None, engine: str = "popc"):
+        """engine only matters for norm="hamming": "popc" (default, the XOR+POPC kernel) or "tensor" (same results
+        from the tcgen05 fp8 GEMM on bit-expanded rows, descriptors <= 32 bytes, large problems only)."""
         if norm not in ("l2", "hamming"):
             raise ValueError("norm must be 'l2' (reference behaviour) or 'hamming'")
+        if engine not in ("popc", "tensor"):
+            raise ValueError("engine must be 'popc' or 'tensor'")
         self._norm = norm
+        self._engine = engine
         self._device = device
         self._matcher = self._create_matcher()
 
@@ -127,7 +132,7 @@ class Matcher:
             raise _bad_input("query and train descriptors must have the same type")
         if dim != dim_t:
             raise _bad_input("query and train descriptors must have the same width")
-        code = _norm_code(self._norm, np.uint8 if q.dtype == torch.uint8 else np.float32)
+        code = _norm_code(self._norm, np.uint8 if q.dtype == torch.uint8 else np.float32, self._engine)
         nq, nt = q.shape[0], t.shape[0]
         idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
         dist = torch.empty((nq, 2), dtype=torch.float32, device=device)
@@ -184,7 +189,7 @@ class Matcher:
             raise _bad_input("query and train descriptors must have the same type")
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1]:
             raise _bad_input("query and train descriptors must have the same width")
-        code = _norm_code(self._norm, q.dtype)
+        code = _norm_code(self._norm, q.dtype, self._engine)
         nq, nt = q.shape[0], t.shape[0]
         if nq == 0:
             return np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool)
@@ -233,7 +238,7 @@ class Matcher:
         dtype, dim = arrs[0].dtype, arrs[0].shape[1]
         if any(a.dtype != dtype or a.ndim != 2 or a.shape[1] != dim for a in arrs):
             raise _bad_input("all descriptor sets must share dtype and width")
-        code = _norm_code(self._norm, dtype)
+        code = _norm_code(self._norm, dtype, self._engine)
         sizes = np.array([a.shape[0] for a in arrs], np.int64)
         total = int(sizes.sum())
         desc, _ = upload_descriptors(np.concatenate(arrs) if total else np.zeros((0, dim), dtype), device)

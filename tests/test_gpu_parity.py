@@ -93,6 +93,28 @@ def test_knn_f32_vs_oracle(nq, nt, dim, integer):
     assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
 
 
+@pytest.mark.parametrize("nq,nt,nbytes", [(5000, 5000, 32), (2000, 2000, 32), (700, 900, 16), (513, 4099, 24), (1000, 3, 32),
+                                           (300, 4000, 64)])
+def test_knn_hamming_tensor_engine(nq, nt, nbytes):
+    """Optional engine: Hamming = popc(q) + popc(t) - 2 q.t on bit-expanded e4m3 rows through the tcgen05 GEMM.
+    Same indices, distances and keep flags as the XOR+POPC kernel / cv2.BFMatcher(NORM_HAMMING)."""
+    rng = np.random.default_rng(nq * 3 + nt)
+    q = rng.integers(0, 256, (nq, nbytes), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, nbytes), dtype=np.uint8)
+    for i in range(0, min(nq, nt) // 100):
+        t[(i * 37) % nt] = q[i]; t[(i * 37 + 5) % nt] = q[i]
+    L = mb._lib.lib()
+    expect_tc = nbytes <= 32 and nq * nt >= 256 * 1024
+    assert L.mk_knn2_uses_tensor_cores(3, nq, nt, nbytes) == int(expect_tc)
+    n0 = mb.launch_count()
+    idx, dist, keep = mb.Matcher(norm="hamming", engine="tensor").knn_match_arrays(q, t, 0.7)
+    assert mb.launch_count() - n0 == (2 if expect_tc else 1)
+    oi, od = orc.knn2(q, t, "hamming")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+    assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+
+
 def test_tensor_core_path_is_the_one_that_runs():
     """SIFT-sized L2 problems go through the tcgen05 GEMM: the call launches prep + the TC kernel (+ the guarded
     SIMT kernel for float rows) and the result is still bit-exact; small problems stay on the SIMT kernels."""

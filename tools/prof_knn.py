@@ -15,7 +15,7 @@ if norm == "f32":
 else:
     q = torch.from_numpy(rng.integers(0, 256, (n, 32), dtype=np.uint8)).cuda()
     t = torch.from_numpy(rng.integers(0, 256, (n, 32), dtype=np.uint8)).cuda()
-    m = mb.Matcher(norm=norm)
+    m = mb.Matcher(norm="hamming", engine="tensor") if norm == "hamming_tc" else mb.Matcher(norm=norm)
 for _ in range(5):
     m.knn_match_device(q, t, 0.7)
 torch.cuda.synchronize()
