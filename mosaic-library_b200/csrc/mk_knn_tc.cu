@@ -20,6 +20,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include <mutex>
@@ -32,11 +33,15 @@ struct KnnParams;  // defined in mk_knn.cu (same translation-unit-independent la
 constexpr int TC_M = 128;          // queries per CTA
 constexpr int TC_N = 256;          // train rows per tile
 constexpr int TC_KA = 64;          // bf16 elements per 128-byte swizzle atom
-constexpr int TC_STAGES = 2;       // B tile ring
-constexpr int TC_EPI_WARPS = 16;   // four warps per TMEM lane quarter, each takes a quarter of the tile's columns
-constexpr int TC_CSPLIT = TC_EPI_WARPS / 4;      // column groups per tile
-constexpr int TC_CW = TC_N / TC_CSPLIT;         // columns scanned per epilogue thread and tile (<= 128: 7 key bits)
+constexpr int TC_STAGES = 2;       // B tile ring when a row is two swizzle atoms (256 B); twice as deep for 128-byte rows
+constexpr int TC_MAX_STAGES = 2 * TC_STAGES;
+constexpr int TC_EPI_WARPS = 16;   // two teams of 8 warps; team t scans the tiles i = t (mod 2), i.e. accumulator stage t
+constexpr int TC_TEAMS = 2;
+constexpr int TC_GROUPS = TC_EPI_WARPS / 4;      // warp groups (4 warps = 128 TMEM lanes each): [team][column half]
+constexpr int TC_CSPLIT = TC_GROUPS / TC_TEAMS;  // column groups per tile
+constexpr int TC_CW = TC_N / TC_CSPLIT;         // columns scanned per epilogue thread and tile (128: 7 key bits)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_TEAM_THREADS = TC_EPI_THREADS / TC_TEAMS;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2.. epilogue
 constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
 constexpr int TC_TABS = 4;         // ring of per-tile column tables (written two tiles ahead by the epilogue threads)
@@ -110,8 +115,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr)
 // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-// same geometry, A = B = E4M3 (format code 0): 0/1 bytes of bit-expanded binary descriptors, K = 32 per instruction
-constexpr uint32_t TC_IDESC_F8 = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// same geometry, A = B = E4M3 (format code 0): 0/1 bytes of bit-expanded binary descriptors, K = 32 per instruction,
+// D = F16 (format code 0): q.t <= 256 is exact in fp16 and two accumulators share one 32-bit TMEM column, which halves the
+// tensor-memory read (64 B / cycle / SM, the bound of this kernel) per candidate
+constexpr uint32_t TC_IDESC_F8 = ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+template <int KIND> __host__ __device__ constexpr int tc_acc_cols() { return TC_N; }   // TMEM columns of one accumulator stage (fp16 accumulators still take a 32-bit column each)
 
 template <int KIND>   // 0: kind::f16 (bf16 operands), 1: kind::f8f6f4 (e4m3 operands); both consume 32 bytes of K per instruction
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
@@ -140,6 +148,17 @@ __device__ __forceinline__ void umma_commit(unsigned long long *bar)
 
 #define TC_LD32(taddr, r)                                                                                                      \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                    \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+                 : "r"(taddr))
+
+// the same load with .pack::16b: register j = (column 2j, column 2j + 1) low halves, i.e. 64 fp16 accumulators per thread
+#define TC_LD32_PACK16(taddr, r)                                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.pack::16b.x32.b32 "                                                           \
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                    \
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
@@ -188,49 +207,64 @@ __device__ __forceinline__ void scan32_i32(const uint32_t (&r)[32], uint32_t tsa
 }
 
 // KIND 1 (Hamming): S <= 256 and popc(t) - 2 S lies in [-256, 256], so a candidate fits 16 bits:
-//     key16 = (popc(t) + 256 - 2 S) << 6 | pair       pair = chunk * 16 + j  (the thread's 64 columns as 32 column pairs)
-// Two columns (j, j + 16 of the same 32-column chunk) share one register: PRMT packs the two S, one IMAD forms both keys
-// (T2 - 128 * S2: both halves stay in [0, 0xFFFF], so no borrow crosses them) and VIMNMX.U16x2 keeps the two best of each
-// half.  0xFFFF marks columns beyond the train set.
+//     key16 = (popc(t) + 256 - 2 S) << 6 | pair       pair = 0..63, the thread's 128 columns as 64 (even, odd) column pairs
+// The fp16 accumulators of columns 2p and 2p+1 arrive in one register.  HADD2 with 1024 turns both into 0x6400 + S, one
+// IMAD forms both keys (T2 - 128 * bits2: 128 * 0x6400 vanishes mod 2^16 and the low half's borrow of 0x32 is pre-added
+// to the table's high half) and VIMNMX.U16x2 keeps the two best of each half.  0xFFFF marks columns beyond the train set.
 template <bool PARTIAL>
 __device__ __forceinline__ void scan32_u16(const uint32_t (&r)[32], uint32_t tsaddr, uint32_t &b1, uint32_t &b2)
 {
+    const __half2 magic = __float2half2_rn(1024.0f);
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
+    for (int j = 0; j < 32; j += 4) {
         const int4 t4 = lds128(tsaddr + j * 4);
         const uint32_t tv[4] = { (uint32_t)t4.x, (uint32_t)t4.y, (uint32_t)t4.z, (uint32_t)t4.w };
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint32_t a = __float_as_uint(__fadd_rn(__uint_as_float(r[j + u]), 8388608.0f));
-            const uint32_t b = __float_as_uint(__fadd_rn(__uint_as_float(r[j + u + 16]), 8388608.0f));
-            const uint32_t s2 = __byte_perm(a, b, 0x5410);
-            uint32_t key = s2 * 0xFFFFFF80u + tv[u];                       // T2 - 128 * S2
+            const __half2 s2 = __hadd2(*reinterpret_cast<const __half2 *>(&r[j + u]), magic);
+            uint32_t key = *reinterpret_cast<const uint32_t *>(&s2) * 0xFFFFFF80u + tv[u];
             if (PARTIAL)
-                key |= ((tv[u] & 0xFFFFu) == 0xFFFFu ? 0xFFFFu : 0u) | ((tv[u] >> 16) == 0xFFFFu ? 0xFFFF0000u : 0u);
+                key |= ((tv[u] & 0xFFFFu) == 0xFFFFu ? 0xFFFFu : 0u) | ((tv[u] >> 16) == 0x0031u ? 0xFFFF0000u : 0u);
             b2 = __vminu2(b2, __vmaxu2(b1, key));
             b1 = __vminu2(b1, key);
         }
     }
 }
 
-// One tile for one thread: 64 columns as two tcgen05.ld of 32, the second in flight while the first is scanned.
+// One tile for one thread: 128 candidates = four (fp32) or two (packed fp16) tcgen05.ld of 32 columns, the next load in
+// flight while the previous one is scanned.
 template <int KIND, bool PARTIAL>
 __device__ __forceinline__ void scan_tile(uint32_t taddr, uint32_t tsaddr, uint32_t &b1, uint32_t &b2)
 {
-    constexpr uint32_t CH = KIND == 1 ? 64 : 128;     // table bytes per 32-column chunk
+    constexpr uint32_t CH = 128;                      // table bytes per 32-column load
     uint32_t ra[32], rb[32];
     auto scan = [&](const uint32_t (&r)[32], uint32_t ts) {
         if constexpr (KIND == 1) scan32_u16<PARTIAL>(r, ts, b1, b2);
         else scan32_i32<PARTIAL>(r, ts, reinterpret_cast<int &>(b1), reinterpret_cast<int &>(b2));
     };
-    TC_LD32(taddr, ra);
-    TC_WAIT_LD(ra);
-    TC_LD32(taddr + 32u, rb);
-    scan(ra, tsaddr);
-    TC_WAIT_LD(rb);
-    scan(rb, tsaddr + CH);
+    if constexpr (KIND == 1) {
+        TC_LD32_PACK16(taddr, ra);
+        TC_WAIT_LD(ra);
+        TC_LD32_PACK16(taddr + 64u, rb);
+        scan(ra, tsaddr);
+        TC_WAIT_LD(rb);
+        scan(rb, tsaddr + CH);
+    } else {
+        TC_LD32(taddr, ra);
+        TC_WAIT_LD(ra);
+        TC_LD32(taddr + 32u, rb);
+        scan(ra, tsaddr);
+        TC_WAIT_LD(rb);
+        TC_LD32(taddr + 64u, ra);
+        scan(rb, tsaddr + CH);
+        TC_WAIT_LD(ra);
+        TC_LD32(taddr + 96u, rb);
+        scan(ra, tsaddr + 2 * CH);
+        TC_WAIT_LD(rb);
+        scan(rb, tsaddr + 3 * CH);
+    }
 }
-static_assert(TC_CW == 64, "scan_tile walks two 32-column chunks");
+static_assert(TC_CW == 128, "scan_tile walks 128 candidates per thread");
 
 struct TcKey {
     using Key = unsigned long long;
@@ -247,11 +281,11 @@ struct TcSmem {
     static constexpr int A_BYTES = TC_M * 128;                  // one k-half of A (128 rows x 128 B)
     static constexpr int B_BYTES = TC_N * 128;                  // one k-half of one B stage
     static __host__ __device__ constexpr int a_off(int half) { return half * A_BYTES; }
-    static __host__ __device__ constexpr int b_off(int stage, int half) { return 2 * A_BYTES + (stage * 2 + half) * B_BYTES; }
+    static __host__ __device__ constexpr int b_slot(int slot) { return 2 * A_BYTES + slot * B_BYTES; }          // 2 * TC_STAGES slots of one atom
     static __host__ __device__ constexpr int tn_off(int slot) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + slot * TC_N * 4; }   // TC_TABS slots
-    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + TC_TABS * TC_N * 4;      // [TC_CSPLIT][128][2] u64
-    static constexpr int bar_off = keys_off + TC_CSPLIT * TC_M * 2 * 8;
-    static constexpr int total = bar_off + 128;
+    static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + TC_TABS * TC_N * 4;      // [TC_GROUPS][128][2] u64
+    static constexpr int bar_off = keys_off + TC_GROUPS * TC_M * 2 * 8;
+    static constexpr int total = bar_off + 256;
 };
 
 template <int KIND>
@@ -262,11 +296,11 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (!knn_tc_inputs_ok(p.flags)) return;   // not exact on this path: the guarded SIMT kernel handles this call
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TcSmem::bar_off);
-    unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_STAGES,
-                       *bar_tfull = bars + 1 + 2 * TC_STAGES, *bar_tempty = bars + 3 + 2 * TC_STAGES,
-                       *bar_tab = bars + 5 + 2 * TC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + TC_TABS + 2 * TC_STAGES);
-    static_assert((6 + TC_TABS + 2 * TC_STAGES) * 8 <= 128, "barrier block");
+    unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_MAX_STAGES,
+                       *bar_tfull = bars + 1 + 2 * TC_MAX_STAGES, *bar_tempty = bars + 3 + 2 * TC_MAX_STAGES,
+                       *bar_tab = bars + 5 + 2 * TC_MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5 + TC_TABS + 2 * TC_MAX_STAGES);
+    static_assert((6 + TC_TABS + 2 * TC_MAX_STAGES) * 8 <= 256, "barrier block");
     __shared__ int s_flag;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -282,6 +316,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int q0 = qblk * TC_M;
     if (q0 >= nq) return;
     const int nhalf = p.row_bytes / 128;                 // 128-byte swizzle atoms per operand row: 1 or 2
+    const int nstages = TC_MAX_STAGES / nhalf;           // B ring depth: the same shared memory holds 2 tiles of 64 KB or 4 of 32 KB
     // train tiles of this split
     const int ntiles = (nt + TC_N - 1) / TC_N;
     const int per = (ntiles + p.splits - 1) / p.splits;
@@ -290,9 +325,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     if (tid == 0) {
         mbar_init(bar_a, 1);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, TC_EPI_THREADS); }
-        for (int s = 0; s < TC_TABS; ++s) mbar_init(bar_tab + s, KIND == 1 ? TC_N / 2 : TC_N);
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, TC_TEAM_THREADS); }
+        for (int s = 0; s < TC_TABS; ++s) mbar_init(bar_tab + s, KIND == 1 ? TC_N / 2 : TC_N);   // one arrival per table entry
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {   // allocate all 512 TMEM columns (2 accumulator stages x 256)
@@ -310,11 +345,11 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
             for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * p.atom_elems, qrow0 + q0, bar_a);
             for (int i = 0; i < my_tiles; ++i) {
-                const int s = i % TC_STAGES, use = i / TC_STAGES;
+                const int s = i % nstages, use = i / nstages;
                 if (use > 0) mbar_wait(bar_bempty + s, (use - 1) & 1);
                 mbar_expect_tx(bar_bfull + s, (uint32_t)(nhalf * TcSmem::B_BYTES));
                 for (int h = 0; h < nhalf; ++h)
-                    tma_load_2d(smem + TcSmem::b_off(s, h), &map_t, h * p.atom_elems, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
+                    tma_load_2d(smem + TcSmem::b_slot(s * nhalf + h), &map_t, h * p.atom_elems, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
             }
         }
     } else if (warp == 1) {
@@ -322,16 +357,16 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (lane == 0) {
             mbar_wait(bar_a, 0);
             for (int i = 0; i < my_tiles; ++i) {
-                const int s = i % TC_STAGES, use = i / TC_STAGES;
+                const int s = i % nstages, use = i / nstages;
                 const int acc = i & 1, acc_use = i >> 1;
                 if (acc_use > 0) mbar_wait(bar_tempty + acc, (acc_use - 1) & 1);   // epilogue drained this accumulator
                 mbar_wait(bar_bfull + s, use & 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * tc_acc_cols<KIND>());
                 uint32_t accumulate = 0;
                 for (int h = 0; h < nhalf; ++h) {
                     const uint64_t ad = make_sw128_desc(smem_addr(smem + TcSmem::a_off(h)));
-                    const uint64_t bd = make_sw128_desc(smem_addr(smem + TcSmem::b_off(s, h)));
+                    const uint64_t bd = make_sw128_desc(smem_addr(smem + TcSmem::b_slot(s * nhalf + h)));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         umma<KIND>(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), accumulate);   // +32 B per K step
@@ -343,9 +378,13 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue: one query row x one 128-column group per thread (see scan32_*) =====================
+        // ===================== epilogue: one query row x one 128-column half per thread (see scan32_*) =====================
+        // Two teams of 8 warps: team t owns accumulator stage t, i.e. the tiles i = t (mod 2).  While one team waits for its
+        // accumulator or its first tcgen05.ld, the other one is in the middle of a scan, so every scheduler keeps both kinds of
+        // warps and the MMA of tile i + 1 runs under the scans of tiles i - 1 and i.
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may access (warp id % 4)
-        const int chalf = (warp - 2) >> 2;                 // which column group of every tile this warp scans
+        const int group = (warp - 2) >> 2;                 // 0..3 = [team][column half]
+        const int team = group / TC_CSPLIT, chalf = group % TC_CSPLIT;
         const int row = quarter * 32 + lane;
         const int qi = q0 + row;
         const int qn = (qi < nq) ? (int)p.qn[qrow0 + qi] : 0;    // exact integer
@@ -354,21 +393,23 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             const unsigned long long key = ((unsigned long long)d << 32) | col;
             const unsigned long long mx = key > k1 ? key : k1; k1 = key < k1 ? key : k1; k2 = mx < k2 ? mx : k2;
         };
-        // Per-tile column tables.  The first TC_N (Hamming: TC_N / 2) epilogue threads each own one entry; the entry of tile
-        // i + 2 is LOADED before tile i is scanned and STORED after it, so the global-load latency hides behind the scan.
-        // Slot (i + 2) % 4 was last read for tile i - 2, which every thread left before tile i could start (its accumulator
-        // is the one tile i - 2 released), and the readers of tile i + 2 wait for tile i's release anyway: no extra coupling.
-        const int et = tid - 64;
+        // Per-tile column tables, two slots per team.  The first TC_N (Hamming: TC_N / 2) threads of a team each own one entry;
+        // the entry of the team's NEXT tile (i + 2) is LOADED before tile i is scanned and STORED after it, so the global-load
+        // latency hides behind the scan.  The slot of tile i + 2 was last read for tile i - 2, which every team mate left
+        // before tile i could start (tile i's MMA waited for that release), and the readers of tile i + 2 wait for tile i's
+        // release anyway: the table barrier adds no coupling of its own.
+        const int et = (tid - 64) % TC_TEAM_THREADS;       // index within the team
         const bool tab_writer = et < (KIND == 1 ? TC_N / 2 : TC_N);
+        auto slot_of = [&](int i) { return (i & 1) * 2 + ((i >> 1) & 1); };
         // raw loads first (table_load), arithmetic on them only when the entry is stored (table_store): nothing between the
         // two touches the loaded registers, so the scan never waits on the global load
         const int pid = et % (TC_CW / 2);                  // Hamming: pair owned by this thread ...
-        const int pcol = (et / (TC_CW / 2)) * TC_CW + (pid >> 4) * 32 + (pid & 15);   // ... = columns pcol (low half), pcol + 16 (high)
+        const int pcol = (et / (TC_CW / 2)) * TC_CW + 2 * pid;    // ... = columns pcol (low half), pcol + 1 (high half)
         auto table_load = [&](int i, float &ta, float &tb) {
             const int col0 = (tile_lo + i) * TC_N;
             if constexpr (KIND == 1) {
                 ta = (col0 + pcol < nt) ? __ldg(p.tn + trow0 + col0 + pcol) : -1.0f;
-                tb = (col0 + pcol + 16 < nt) ? __ldg(p.tn + trow0 + col0 + pcol + 16) : -1.0f;
+                tb = (col0 + pcol + 1 < nt) ? __ldg(p.tn + trow0 + col0 + pcol + 1) : -1.0f;
             } else {
                 ta = (col0 + et < nt) ? __ldg(p.tn + trow0 + col0 + et) : -1.0f;
                 tb = 0.0f;
@@ -376,42 +417,42 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         };
         auto table_store = [&](int i, float ta, float tb) {
             int v;
-            if constexpr (KIND == 1) {       // (popc(t) + 256) << 6 | pair per half; 0xFFFF beyond nt
+            if constexpr (KIND == 1) {       // (popc(t) + 256) << 6 | pair per half, 0xFFFF beyond nt; +0x32 on the high half (scan32_u16)
                 const uint32_t lo = ta >= 0.0f ? ((((uint32_t)ta + 256u) << 6) | (uint32_t)pid) : 0xFFFFu;
                 const uint32_t hi = tb >= 0.0f ? ((((uint32_t)tb + 256u) << 6) | (uint32_t)pid) : 0xFFFFu;
-                v = (int)(lo | (hi << 16));
-            } else {                         // |t|^2 * 128 + (col & 63); INT_MAX beyond nt
+                v = (int)(lo + ((hi + 0x32u) << 16));
+            } else {                         // |t|^2 * 128 + (col & 127); INT_MAX beyond nt
                 v = ta >= 0.0f ? ((int)ta * 128 + (et % TC_CW)) : 0x7fffffff;
             }
-            reinterpret_cast<int *>(smem + TcSmem::tn_off(i % TC_TABS))[et] = v;
-            mbar_arrive(bar_tab + i % TC_TABS);
+            reinterpret_cast<int *>(smem + TcSmem::tn_off(slot_of(i)))[et] = v;
+            mbar_arrive(bar_tab + slot_of(i));
         };
-        if (tab_writer) {
+        if (tab_writer && team < my_tiles) {
             float ta, tb;
-            if (my_tiles > 0) { table_load(0, ta, tb); table_store(0, ta, tb); }
-            if (my_tiles > 1) { table_load(1, ta, tb); table_store(1, ta, tb); }
+            table_load(team, ta, tb);
+            table_store(team, ta, tb);
         }
         // Hamming: running best two of each 16-bit half as 32-bit keys (count + 256) << 22 | tile << 6 | pair, ordered like
         // (count, column) within the half; unpacked once after the last tile
         uint32_t run[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu };   // [half][rank]
-        for (int i = 0; i < my_tiles; ++i) {
-            const int acc = i & 1, acc_use = i >> 1;
+        for (int i = team; i < my_tiles; i += TC_TEAMS) {
+            const int acc = team, acc_use = i >> 1;
             const int col0 = (tile_lo + i) * TC_N;
             const bool partial = col0 + TC_N > nt;        // warp-uniform, last tile of a set only
-            const uint32_t tsaddr = smem_addr(smem + TcSmem::tn_off(i % TC_TABS)) + (uint32_t)chalf * (uint32_t)(KIND == 1 ? TC_CW * 2 : TC_CW * 4);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + chalf * TC_CW);
-            const bool prefetch = tab_writer && i + 2 < my_tiles;
+            const uint32_t tsaddr = smem_addr(smem + TcSmem::tn_off(slot_of(i))) + (uint32_t)chalf * (uint32_t)(KIND == 1 ? TC_CW * 2 : TC_CW * 4);   // one table word per TMEM column
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * TC_CSPLIT + chalf) * (tc_acc_cols<KIND>() / TC_CSPLIT));
+            const bool prefetch = tab_writer && i + TC_TEAMS < my_tiles;
             float ta = 0.0f, tb = 0.0f;
-            if (prefetch) table_load(i + 2, ta, tb);
-            mbar_wait(bar_tab + i % TC_TABS, (i / TC_TABS) & 1);
+            if (prefetch) table_load(i + TC_TEAMS, ta, tb);
+            mbar_wait(bar_tab + slot_of(i), (i >> 2) & 1);
             mbar_wait(bar_tfull + acc, acc_use & 1);
             tc_fence_after();
             uint32_t b1 = KIND == 1 ? 0xFFFFFFFFu : 0x7fffffffu, b2 = b1;
             if (partial) scan_tile<KIND, true>(taddr, tsaddr, b1, b2);
             else scan_tile<KIND, false>(taddr, tsaddr, b1, b2);
             tc_fence_before();
-            mbar_arrive(bar_tempty + acc);                 // all epilogue threads release the accumulator stage
-            if (prefetch) table_store(i + 2, ta, tb);
+            mbar_arrive(bar_tempty + acc);                 // the team releases its accumulator stage
+            if (prefetch) table_store(i + TC_TEAMS, ta, tb);
             // fold the tile's best candidates into the running keys
             if constexpr (KIND == 1) {
                 const uint32_t tl = (uint32_t)i << 6;
@@ -426,7 +467,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         run[2 * h + 1] = min(run[2 * h + 1], mx);
                     }
                 }
-            } else {                                       // key >> 7 = d^2 - |q|^2, key & 127 = column in this group
+            } else {                                       // key >> 7 = d^2 - |q|^2, key & 127 = column in this half
                 const uint32_t cbase = (uint32_t)(col0 + chalf * TC_CW);
                 if (b1 != 0x7fffffffu) fold((uint32_t)(((int)b1 >> 7) + qn), cbase + (b1 & 127u));
                 if (b2 != 0x7fffffffu) fold((uint32_t)(((int)b2 >> 7) + qn), cbase + (b2 & 127u));
@@ -438,11 +479,11 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                 const uint32_t r = run[e], dpart = r >> 22, pr = r & 63u, tile = (r >> 6) & 0xFFFFu;
                 if (dpart != 1023u)
                     fold(dpart - 256u + (uint32_t)qn,
-                         (uint32_t)((tile_lo + (int)tile) * TC_N + chalf * TC_CW) + (pr >> 4) * 32u + (pr & 15u) + (uint32_t)(e >> 1) * 16u);
+                         (uint32_t)((tile_lo + (int)tile) * TC_N + chalf * TC_CW) + 2u * pr + (uint32_t)(e >> 1));
             }
         }
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + TcSmem::keys_off);
-        s_keys[(chalf * TC_M + row) * 2] = k1; s_keys[(chalf * TC_M + row) * 2 + 1] = k2;
+        s_keys[(group * TC_M + row) * 2] = k1; s_keys[(group * TC_M + row) * 2 + 1] = k2;
     }
     tc_fence_before();
     __syncthreads();
@@ -458,7 +499,7 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (is_row_thread) {                                   // merge the column groups of this row
         k1 = s_keys[tid * 2]; k2 = s_keys[tid * 2 + 1];
 #pragma unroll
-        for (int g = 1; g < TC_CSPLIT; ++g) {
+        for (int g = 1; g < TC_GROUPS; ++g) {
             const unsigned long long a = s_keys[(g * TC_M + tid) * 2], b = s_keys[(g * TC_M + tid) * 2 + 1];
             if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
             if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
@@ -542,27 +583,39 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ 
 }
 
 // ---- prep for Hamming: bits -> e4m3 bytes (1.0 = 0x38 / 0), popcounts as "norms" -----------------------------------------
+// One thread per 16 output bytes (two descriptor bytes), kp / 16 threads per row.
+__device__ __forceinline__ uint32_t expand4(uint32_t nib)   // bits 0..3 -> four bytes of 0x38 / 0x00
+{
+    return ((nib * 0x00204081u) & 0x01010101u) * 0x38u;
+}
 __global__ void __launch_bounds__(256) knn_tc_prep_bits_kernel(const uint8_t *__restrict__ q, int nq, const uint8_t *__restrict__ t, int nt,
                                                                size_t stride_bytes, int nbytes, int kp, uint8_t *__restrict__ qb,
                                                                uint8_t *__restrict__ tb, float *__restrict__ qn, float *__restrict__ tn,
-                                                               int32_t *n_keep)
+                                                               int32_t *n_keep, int *zero, int nzero)
 {
-    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row == 0 && lane == 0 && n_keep) *n_keep = 0;
-    if (row >= nq + nt) return;
+    const int tpr = kp >> 4;                                 // threads per row: 8 or 16
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = gid / tpr;
+    const int part = gid % tpr;
+    if (gid == 0 && n_keep) *n_keep = 0;
+    for (int i = gid; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;   // flags + tickets of the TC kernel (no memset node)
+    const bool live = row < nq + nt;
     const bool is_q = row < nq;
     if (!is_q) row -= nq;
-    const uint8_t *src = (is_q ? q : t) + (size_t)row * stride_bytes;
-    uint8_t *dst = (is_q ? qb : tb) + (size_t)row * kp;
-    int cnt = 0;
-    for (int k = lane; k < kp; k += 32) {
-        const int bit = (k < nbytes * 8) ? ((src[k >> 3] >> (k & 7)) & 1) : 0;
-        dst[k] = bit ? 0x38 : 0x00;
-        cnt += bit;
+    uint32_t v = 0;
+    if (live && 2 * part < nbytes) {
+        const uint8_t *src = (is_q ? q : t) + (size_t)row * stride_bytes + 2 * part;
+        v = src[0];
+        if (2 * part + 1 < nbytes) v |= (uint32_t)src[1] << 8;
     }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) (is_q ? qn : tn)[row] = (float)cnt;
+    if (live) {
+        uint4 o;
+        o.x = expand4(v & 15u); o.y = expand4((v >> 4) & 15u); o.z = expand4((v >> 8) & 15u); o.w = expand4(v >> 12);
+        *reinterpret_cast<uint4 *>((is_q ? qb : tb) + (size_t)row * kp + 16 * part) = o;
+    }
+    int cnt = __popc(v);
+    for (int o = tpr >> 1; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (live && part == 0) (is_q ? qn : tn)[row] = (float)cnt;
 }
 
 // ---- host -------------------------------------------------------------------------------------------
@@ -668,15 +721,16 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     float *qn = reinterpret_cast<float *>(ws + pl.off_qn), *tn = reinterpret_cast<float *>(ws + pl.off_tn);
     int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
     const int np = batched ? npairs : 1;
-    // flags and tickets are adjacent in the workspace: one memset
-    MK_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4, st));
+    // flags and tickets are adjacent in the workspace: one memset (the Hamming prep kernel, which sets no flag, zeroes them itself)
+    const size_t zero_bytes = (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4;
+    if (norm != MK_NORM_HAMMING_TC) MK_CUDA_TRY(cudaMemsetAsync(flags, 0, zero_bytes, st));
     if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
     const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
     const int wpb = 8, rows = rows_q + rows_t;
     if (norm == MK_NORM_HAMMING_TC)
-        knn_tc_prep_bits_kernel<<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t, stride,
+        knn_tc_prep_bits_kernel<<<(int)(((long)rows * (pl.kp >> 4) + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t, stride,
                                                                         dim, pl.kp, static_cast<uint8_t *>(qb), static_cast<uint8_t *>(tb), qn, tn,
-                                                                        batched ? nullptr : n_keep);
+                                                                        batched ? nullptr : n_keep, flags, (int)(zero_bytes / 4));
     else if (norm == MK_NORM_L2_F32)
         knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), rows_q, static_cast<const float *>(t), rows_t,
                                                                           stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep);

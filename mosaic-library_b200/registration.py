@@ -137,9 +137,9 @@ class Matcher:
         idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
         dist = torch.empty((nq, 2), dtype=torch.float32, device=device)
         keep = torch.empty((nq,), dtype=torch.uint8, device=device)
-        n_keep = torch.zeros((1,), dtype=torch.int32, device=device)
         if nq == 0:
-            return idx, dist, keep, n_keep
+            return idx, dist, keep, torch.zeros((1,), dtype=torch.int32, device=device)
+        n_keep = torch.empty((1,), dtype=torch.int32, device=device)   # the library zeroes it on the stream
         L = self._matcher["lib"]
         ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device)
         stride = q.stride(0) * q.element_size()
