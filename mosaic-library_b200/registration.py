@@ -46,10 +46,10 @@ def _bad_input(msg: str):
     return ValueError(msg)
 
 
-def _norm_code(norm: str, dtype, engine: str = "popc") -> int:
+def _norm_code(norm: str, dtype, engine: str = "auto") -> int:
     if dtype == np.uint8:
         if norm == "hamming":
-            return _lib.NORM_HAMMING_TC if engine == "tensor" else _lib.NORM_HAMMING
+            return _lib.NORM_HAMMING if engine == "popc" else _lib.NORM_HAMMING_TC
         if norm == "l2":
             return _lib.NORM_L2_U8
     elif dtype == np.float32:
@@ -88,13 +88,14 @@ def upload_descriptors(desc, device=None) -> tuple[torch.Tensor, int]:
 class Matcher:
     """Brute-force k=2 matcher (reference: registration.py:226-264)."""
 
-    def __init__(self, norm: str = "l2", device=None, engine: str = "popc"):
-        """engine only matters for norm="hamming": "popc" (default, the XOR+POPC kernel) or "tensor" (same results
-        from the tcgen05 fp8 GEMM on bit-expanded rows, descriptors <= 32 bytes, large problems only)."""
+    def __init__(self, norm: str = "l2", device=None, engine: str = "auto"):
+        """engine only matters for norm="hamming": "popc" always runs the XOR+POPC kernel; "auto" (default, alias
+        "tensor") lets the library send large problems with descriptors <= 32 bytes through the tcgen05 fp8 GEMM on
+        bit-expanded rows (mk_knn2_uses_tensor_cores tells which) -- the results are identical bit for bit."""
         if norm not in ("l2", "hamming"):
             raise ValueError("norm must be 'l2' (reference behaviour) or 'hamming'")
-        if engine not in ("popc", "tensor"):
-            raise ValueError("engine must be 'popc' or 'tensor'")
+        if engine not in ("auto", "popc", "tensor"):
+            raise ValueError("engine must be 'auto', 'popc' or 'tensor'")
         self._norm = norm
         self._engine = engine
         self._device = device

@@ -67,11 +67,12 @@ def test_knn_u8_vs_oracle(nq, nt, nbytes, norm):
     t = rng.integers(0, 256, (nt, nbytes), dtype=np.uint8)
     for i in range(0, min(nq, nt) // 100):       # planted duplicates -> exact ties
         t[(i * 37) % nt] = q[i]; t[(i * 37 + 5) % nt] = q[i]
-    idx, dist, keep = mb.Matcher(norm=norm).knn_match_arrays(q, t, 0.7)
     oi, od = orc.knn2(q, t, norm)
-    assert np.array_equal(idx, oi)
-    assert np.array_equal(dist, od)
-    assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+    for engine in (("popc", "auto") if norm == "hamming" else ("auto",)):   # both Hamming engines give the same bits
+        idx, dist, keep = mb.Matcher(norm=norm, engine=engine).knn_match_arrays(q, t, 0.7)
+        assert np.array_equal(idx, oi)
+        assert np.array_equal(dist, od)
+        assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
 
 
 @pytest.mark.parametrize("nq,nt,dim,integer", [(1000, 1200, 128, True), (500, 777, 128, False), (70, 65, 64, False),
@@ -170,7 +171,7 @@ def test_knn_batched_vs_single():
             assert np.array_equal(keep[sl], ok) and nk[p] == ok.sum()
 
 
-@pytest.mark.parametrize("kind", ["sift_int", "orb_l2", "orb_hamming", "f32_generic"])
+@pytest.mark.parametrize("kind", ["sift_int", "orb_l2", "orb_hamming", "orb_hamming_popc", "f32_generic"])
 def test_knn_match_sets_vs_oracle(kind):
     """Batched matching (consecutive pairs + a few loop-closure pairs, ragged set sizes) through the Python API; the
     L2 cases run on the batched tcgen05 path (shared bf16 copy, masked partial tiles), generic floats on the SIMT one."""
@@ -184,7 +185,7 @@ def test_knn_match_sets_vs_oracle(kind):
         sets = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in sizes]; norm = "l2" if kind == "orb_l2" else "hamming"
     sets[2][5] = sets[0][9]; sets[2][77] = sets[0][9]          # planted exact ties across sets
     pairs = [(k + 1, k) for k in range(len(sizes) - 1)] + [(0, 2), (5, 0), (2, 2)]
-    res = mb.Matcher(norm=norm).knn_match_sets(sets, pairs, 0.7)
+    res = mb.Matcher(norm=norm, engine="popc" if kind.endswith("popc") else "auto").knn_match_sets(sets, pairs, 0.7)
     assert len(res) == len(pairs)
     for (a, b), (idx, dist, keep) in zip(pairs, res):
         oi, od = orc.knn2(sets[a], sets[b], norm)
