@@ -85,6 +85,38 @@ def upload_descriptors(desc, device=None) -> tuple[torch.Tensor, int]:
     return out, dim
 
 
+class PendingMatch:
+    """Handle of one queued Matcher.knn_match_arrays_async call."""
+
+    DEPTH = 4
+
+    def __init__(self, slot, nq, off_keep, keepalive):
+        self._slot, self._nq, self._off_keep, self._keepalive, self._res = slot, nq, off_keep, keepalive, None
+
+    @classmethod
+    def done(cls, idx, dist, keep):
+        p = cls(None, 0, 0, None)
+        p._res = (idx, dist, keep)
+        return p
+
+    def _resolve(self):
+        if self._res is None:
+            self._slot["event"].synchronize()
+            hb, nq = self._slot["host"].numpy(), self._nq
+            self._res = (hb[: nq * 8].view(np.int32).reshape(nq, 2).copy(), hb[nq * 8: nq * 16].view(np.float32).reshape(nq, 2).copy(),
+                         hb[self._off_keep: self._off_keep + nq].astype(bool))
+            self._slot["owner"] = None
+            self._slot = self._keepalive = None
+        return self._res
+
+    def ready(self) -> bool:
+        return self._res is not None or self._slot["event"].query()
+
+    def result(self):
+        """-> (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool), the values knn_match_arrays returns."""
+        return self._resolve()
+
+
 class Matcher:
     """Brute-force k=2 matcher (reference: registration.py:226-264)."""
 
@@ -185,15 +217,29 @@ class Matcher:
         return buf, dim, stride
 
     def _knn_host(self, q: np.ndarray, t: np.ndarray, ratio: float):
+        return self._knn_host_submit(q, t, ratio).result()
+
+    def knn_match_arrays_async(self, query: np.ndarray, train: np.ndarray, ratio: float = 0.7) -> "PendingMatch":
+        """knn_match_arrays without the wait: uploads, kernels and the packed device->host copy are queued on the matcher's
+        private stream and the call returns a handle; handle.result() -> (idx, dist, keep) waits for that call only.
+        Lets a frame loop queue frame k's matching, hand frame k to Mapper.update and collect frame k-1's matches, so the
+        PCIe uploads never wait for a host round trip.  The input arrays must stay alive and unmodified until result();
+        at most PendingMatch.DEPTH calls are kept in flight (older handles are resolved when their slot is reused)."""
+        if not (isinstance(query, np.ndarray) and isinstance(train, np.ndarray)):
+            raise TypeError("knn_match_arrays_async takes host ndarrays")
+        return self._knn_host_submit(query, train, ratio)
+
+    def _knn_host_submit(self, q: np.ndarray, t: np.ndarray, ratio: float) -> "PendingMatch":
         device = _cuda_device(self._device)
         if q.dtype != t.dtype:
             raise _bad_input("query and train descriptors must have the same type")
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1]:
             raise _bad_input("query and train descriptors must have the same width")
         code = _norm_code(self._norm, q.dtype, self._engine)
+        q, t = np.ascontiguousarray(q), np.ascontiguousarray(t)     # kept alive by the handle until the copies are done
         nq, nt = q.shape[0], t.shape[0]
         if nq == 0:
-            return np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool)
+            return PendingMatch.done(np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool))
         L = self._matcher["lib"]
         # host in, host out: nothing depends on the caller's stream, so the call runs on a private stream and
         # overlaps whatever the caller has in flight (e.g. Mapper's frame upload + fused kernel)
@@ -213,19 +259,24 @@ class Matcher:
             if out is None or out.numel() < total or out.device != device:
                 out = torch.empty(total * 2, dtype=torch.uint8, device=device)
                 st["out"] = out
-                st["out_host"] = torch.empty(total * 2, dtype=torch.uint8).pin_memory()
-            host = st["out_host"]
+            # device buffers are reused call after call (stream order protects them); the page-locked result buffer is the
+            # only thing a later call could overwrite under the reader, so it comes from a small ring
+            ring = st.setdefault("ring", [None] * PendingMatch.DEPTH)
+            k = st["ring_pos"] = (st.get("ring_pos", -1) + 1) % PendingMatch.DEPTH
+            if ring[k] is not None and ring[k]["owner"] is not None:
+                ring[k]["owner"]._resolve()      # an uncollected older call still points at this slot
+            if ring[k] is None or ring[k]["host"].numel() < total:
+                ring[k] = {"host": torch.empty(total * 2, dtype=torch.uint8).pin_memory(), "event": torch.cuda.Event(), "owner": None}
+            slot = ring[k]
             ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace_host_path")
             base = out.data_ptr()
             _lib.check(L.mk_knn2(code, qd.data_ptr(), nq, td.data_ptr() if nt else None, nt, dim, stride, base, base + nq * 8,
                                  float(ratio), base + off_keep, base + off_n, ws.data_ptr(), ws.numel(), stream))
-            _lib.check(L.mk_download_2d(host.data_ptr(), total, base, total, total, 1, stream))
-            cur.synchronize()
-        hb = host.numpy()
-        idx = hb[: nq * 8].view(np.int32).reshape(nq, 2).copy()
-        dist = hb[nq * 8: nq * 16].view(np.float32).reshape(nq, 2).copy()
-        keep = hb[off_keep: off_keep + nq].astype(bool)
-        return idx, dist, keep
+            _lib.check(L.mk_download_2d(slot["host"].data_ptr(), total, base, total, total, 1, stream))
+            slot["event"].record(cur)
+        pending = PendingMatch(slot, nq, off_keep, (q, t))
+        slot["owner"] = pending
+        return pending
 
     def knn_match_sets(self, sets: Sequence[np.ndarray], pairs: Sequence[tuple[int, int]], ratio: float = 0.7):
         """Many (query set, train set) pairs in ONE launch: the consecutive-frame loop of

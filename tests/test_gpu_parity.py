@@ -116,6 +116,23 @@ def test_knn_hamming_tensor_engine(nq, nt, nbytes):
     assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
 
 
+def test_knn_match_arrays_async_ring():
+    """Queued host calls: more calls in flight than the result ring holds, collected out of order; every handle returns
+    exactly what the blocking call returns."""
+    rng = np.random.default_rng(5)
+    m = mb.Matcher(norm="hamming")
+    cases = [(rng.integers(0, 256, (300 + 50 * k, 32), dtype=np.uint8), rng.integers(0, 256, (280 + 70 * k, 32), dtype=np.uint8))
+             for k in range(mb.registration.PendingMatch.DEPTH + 3)]
+    handles = [m.knn_match_arrays_async(q, t, 0.7) for q, t in cases]
+    for k in reversed(range(len(cases))):
+        idx, dist, keep = handles[k].result()
+        oi, od = orc.knn2(cases[k][0], cases[k][1], "hamming")
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od) and np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+        assert handles[k].ready()
+    e = m.knn_match_arrays_async(np.zeros((0, 32), np.uint8), cases[0][1]).result()
+    assert e[0].shape == (0, 2) and e[2].shape == (0,)
+
+
 def test_tensor_core_path_is_the_one_that_runs():
     """SIFT-sized L2 problems go through the tcgen05 GEMM: the call launches prep + the TC kernel (+ the guarded
     SIMT kernel for float rows) and the result is still bit-exact; small problems stay on the SIMT kernels."""
