@@ -74,8 +74,11 @@ class Mapper:
         # host frames are uploaded on a side stream into a small ring of staging buffers so that the
         # H2D copy of frame k+1 overlaps the kernel of frame k
         self._copy_stream = torch.cuda.Stream(device=self._device)
+        self._copy_sptr = self._copy_stream.cuda_stream
+        self._cargs = None          # cached canvas / mask / weight pointers and pitches (they only change on release)
         self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
         self._slot = 0
+        self._region_buf = (ctypes.c_int32 * 4)()
         self._flag = True
         self.last_region = (0, 0, 0, 0)
 
@@ -145,12 +148,13 @@ class Mapper:
                 r2, rh, rw = self._as_rows(roi, 1)
                 assert (rh, rw) == (h, w)
             if self._usable_in_place(t2) and (r2 is None or self._usable_in_place(r2)):
-                self._launch(t2, h, w, r2, H)
+                self._launch(t2, h, w, r2, H, cur)
                 return
         else:
             if image.dtype != np.uint8:
                 raise TypeError("Mapper.update needs uint8 images")
-            image = np.ascontiguousarray(image)
+            if not image.flags.c_contiguous:
+                image = np.ascontiguousarray(image)
             h, w = image.shape[:2]
         slot = self._slots[self._slot]
         self._slot = (self._slot + 1) % len(self._slots)
@@ -163,7 +167,8 @@ class Mapper:
         if host_np:
             # straight cudaMemcpy2DAsync on the copy stream: asynchronous when the array is page-locked
             buf = self._slot_buffer(slot, "buf", h, w * 3)
-            _lib.check(self._lib.mk_upload_2d(buf.data_ptr(), buf.stride(0), image.ctypes.data, w * 3, w * 3, h, cs.cuda_stream))
+            _lib.check(self._lib.mk_upload_2d(buf.data_ptr(), buf.stride(0), image.__array_interface__["data"][0], w * 3, w * 3, h,
+                                              self._copy_sptr))
             if roi is not None:
                 roi = np.ascontiguousarray(roi)
                 rbuf = self._slot_buffer(slot, "roi", h, w)
@@ -176,23 +181,28 @@ class Mapper:
                 rbuf = self._stage_upload(slot, "roi", r2) if r2 is not None else None
         slot["ready"].record(cs)
         cur.wait_event(slot["ready"])
-        self._launch(buf, h, w, rbuf, H)
+        self._launch(buf, h, w, rbuf, H, cur)
         slot["free"].record(cur)
 
-    def _launch(self, buf, h, w, rbuf, H) -> None:
-        Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
-        region = (ctypes.c_int32 * 4)()
+    def _launch(self, buf, h, w, rbuf, H, cur=None) -> None:
+        Hm = H if (isinstance(H, np.ndarray) and H.dtype == np.float64 and H.shape == (3, 3) and H.flags.c_contiguous) else \
+            np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
+        region = self._region_buf
         ramp = self._ramp if self._ramp is not None else 0.1 * min(h, w)
+        ca = self._cargs
+        if ca is None:
+            ca = self._cargs = (self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
+                                self._wacc.data_ptr() if self._wacc is not None else None,
+                                self._wacc.stride(0) * 4 if self._wacc is not None else 0, self._height, self._width)
+        if cur is None:
+            cur = torch.cuda.current_stream(self._device)
         rc = self._lib.mk_mapper_update(
-            self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
-            self._wacc.data_ptr() if self._wacc is not None else None,
-            self._wacc.stride(0) * 4 if self._wacc is not None else 0,
-            self._height, self._width, buf.data_ptr(), h, w, buf.stride(0),
+            *ca, buf.data_ptr(), h, w, buf.stride(0),
             rbuf.data_ptr() if rbuf is not None else None, rbuf.stride(0) if rbuf is not None else 0,
-            Hm.ctypes.data, self._alpha, self._interp, self._blend, float(ramp), region,
-            torch.cuda.current_stream(self._device).cuda_stream)
-        _lib.check(rc)
-        self.last_region = tuple(region)
+            Hm.__array_interface__["data"][0], self._alpha, self._interp, self._blend, float(ramp), region, cur.cuda_stream)
+        if rc:
+            _lib.check(rc)
+        self.last_region = (region[0], region[1], region[2], region[3])
 
     def update_batch(self, frames: Sequence, Hs: Sequence[np.ndarray]) -> None:
         """Composite many frames in sequence order with ONE launch (gather formulation: every canvas tile is read once,
@@ -238,6 +248,7 @@ class Mapper:
 
     def release(self):
         self._canvas = self._canvas_mask = self._wacc = None
+        self._cargs = None
         self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
 
     @property

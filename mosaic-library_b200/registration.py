@@ -192,30 +192,6 @@ class Matcher:
         idx, dist, keep, _ = self.knn_match_device(query, train, ratio)
         return idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool)
 
-    def _dev_rows(self, slot: str, a: np.ndarray, device, stream) -> tuple[torch.Tensor, int, int]:
-        """Upload a host descriptor array into a persistent device buffer whose rows are padded to 16 bytes."""
-        if a.ndim != 2:
-            raise _bad_input("descriptors must be 2-D")
-        if a.dtype not in (np.uint8, np.float32):
-            raise _bad_input(f"unsupported descriptor dtype {a.dtype} (cv2 accepts CV_8U and CV_32F)")
-        a = np.ascontiguousarray(a)
-        n, dim = a.shape
-        row = dim * a.itemsize
-        stride = (row + 15) & ~15
-        st = self._matcher.setdefault("dev", {})
-        buf = st.get(slot)
-        if buf is None or buf.numel() < max(n, 1) * stride or buf.device != device:
-            buf = torch.zeros(max(n, 1) * stride * 2, dtype=torch.uint8, device=device)
-            st[slot] = buf
-            st[slot + "_stride"] = None
-        if st.get(slot + "_stride") != (stride, row):
-            if stride != row:
-                buf.zero_()                       # the padding columns must read as zero (runs on the matcher's stream)
-            st[slot + "_stride"] = (stride, row)
-        if n:
-            _lib.check(self._matcher["lib"].mk_upload_2d(buf.data_ptr(), stride, a.ctypes.data, row, row, n, stream))
-        return buf, dim, stride
-
     def _knn_host(self, q: np.ndarray, t: np.ndarray, ratio: float):
         return self._knn_host_submit(q, t, ratio).result()
 
@@ -229,51 +205,86 @@ class Matcher:
             raise TypeError("knn_match_arrays_async takes host ndarrays")
         return self._knn_host_submit(query, train, ratio)
 
+    def _host_plan(self, device, dtype, dim: int, nq: int, nt: int) -> dict:
+        """Everything the host path reuses call after call: private stream, device row buffers (rows padded to 16 bytes,
+        padding zero), packed output buffer, the ring of page-locked result buffers.  Rebuilt only when the descriptor
+        type / width changes or a set outgrows its buffer, so the per-call path is a handful of C-ABI calls."""
+        hp = self._matcher.get("host_plan")
+        if (hp is not None and hp["key"] == (device, dtype.char, dim) and nq <= hp["cap"] and nt <= hp["cap"]):
+            return hp
+        stream = self._matcher.get("stream")
+        if stream is None or stream.device != device:
+            stream = torch.cuda.Stream(device=device)
+            self._matcher["stream"] = stream
+        if hp is not None:
+            for slot in hp["ring"]:
+                if slot["owner"] is not None:
+                    slot["owner"]._resolve()     # results of queued calls live in the buffers we are about to replace
+            stream.synchronize()
+        row = dim * dtype.itemsize
+        stride = (row + 15) & ~15
+        cap = max(nq, nt, 1)
+        cap = 1 << (cap - 1).bit_length()
+        total_cap = (cap * 17 + 3 & ~3) + 4
+        with torch.cuda.stream(stream):          # allocations and fills happen on the private stream
+            qd = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
+            td = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
+            out = torch.empty(total_cap, dtype=torch.uint8, device=device)
+        ring = [{"host": torch.empty(total_cap, dtype=torch.uint8).pin_memory(), "event": torch.cuda.Event(), "owner": None}
+                for _ in range(PendingMatch.DEPTH)]
+        for slot in ring:
+            slot["host_ptr"] = slot["host"].data_ptr()
+        hp = {"key": (device, dtype.char, dim), "cap": cap, "stream": stream, "sptr": stream.cuda_stream, "row": row, "stride": stride,
+              "q": qd, "t": td, "out": out, "q_ptr": qd.data_ptr(), "t_ptr": td.data_ptr(), "out_ptr": out.data_ptr(),
+              "ring": ring, "pos": 0, "code": _norm_code(self._norm, dtype, self._engine), "ws": {}, "device": device}
+        self._matcher["host_plan"] = hp
+        return hp
+
     def _knn_host_submit(self, q: np.ndarray, t: np.ndarray, ratio: float) -> "PendingMatch":
-        device = _cuda_device(self._device)
         if q.dtype != t.dtype:
             raise _bad_input("query and train descriptors must have the same type")
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1]:
             raise _bad_input("query and train descriptors must have the same width")
-        code = _norm_code(self._norm, q.dtype, self._engine)
-        q, t = np.ascontiguousarray(q), np.ascontiguousarray(t)     # kept alive by the handle until the copies are done
-        nq, nt = q.shape[0], t.shape[0]
+        if q.dtype not in (np.uint8, np.float32):
+            raise _bad_input(f"unsupported descriptor dtype {q.dtype} (cv2 accepts CV_8U and CV_32F)")
+        if not q.flags.c_contiguous:
+            q = np.ascontiguousarray(q)
+        if not t.flags.c_contiguous:
+            t = np.ascontiguousarray(t)          # both stay referenced by the handle until the copies are done
+        (nq, dim), nt = q.shape, t.shape[0]
         if nq == 0:
             return PendingMatch.done(np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool))
-        L = self._matcher["lib"]
         # host in, host out: nothing depends on the caller's stream, so the call runs on a private stream and
         # overlaps whatever the caller has in flight (e.g. Mapper's frame upload + fused kernel)
-        cur = self._matcher.get("stream")
-        if cur is None or cur.device != device:
-            cur = torch.cuda.Stream(device=device)
-            self._matcher["stream"] = cur
-        with torch.cuda.stream(cur):             # every torch-side fill / allocation below runs on the private stream too
-            stream = cur.cuda_stream
-            qd, dim, stride = self._dev_rows("q", q, device, stream)
-            td, _, _ = self._dev_rows("t", t, device, stream)
-            # packed outputs: idx (nq*8) | dist (nq*8) | keep (nq) | pad | n_keep (4)
-            off_keep, off_n = nq * 16, (nq * 17 + 3) & ~3
-            total = off_n + 4
-            st = self._matcher["dev"]
-            out = st.get("out")
-            if out is None or out.numel() < total or out.device != device:
-                out = torch.empty(total * 2, dtype=torch.uint8, device=device)
-                st["out"] = out
-            # device buffers are reused call after call (stream order protects them); the page-locked result buffer is the
-            # only thing a later call could overwrite under the reader, so it comes from a small ring
-            ring = st.setdefault("ring", [None] * PendingMatch.DEPTH)
-            k = st["ring_pos"] = (st.get("ring_pos", -1) + 1) % PendingMatch.DEPTH
-            if ring[k] is not None and ring[k]["owner"] is not None:
-                ring[k]["owner"]._resolve()      # an uncollected older call still points at this slot
-            if ring[k] is None or ring[k]["host"].numel() < total:
-                ring[k] = {"host": torch.empty(total * 2, dtype=torch.uint8).pin_memory(), "event": torch.cuda.Event(), "owner": None}
-            slot = ring[k]
-            ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace_host_path")
-            base = out.data_ptr()
-            _lib.check(L.mk_knn2(code, qd.data_ptr(), nq, td.data_ptr() if nt else None, nt, dim, stride, base, base + nq * 8,
-                                 float(ratio), base + off_keep, base + off_n, ws.data_ptr(), ws.numel(), stream))
-            _lib.check(L.mk_download_2d(slot["host"].data_ptr(), total, base, total, total, 1, stream))
-            slot["event"].record(cur)
+        hp = self._host_plan(_cuda_device(self._device), q.dtype, dim, nq, nt)
+        L, sptr, row, stride, code = self._matcher["lib"], hp["sptr"], hp["row"], hp["stride"], hp["code"]
+        ws = hp["ws"].get((nq, nt))
+        if ws is None:
+            with torch.cuda.stream(hp["stream"]):
+                wt = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), hp["device"], "workspace_host_path")
+            ws = hp["ws"][(nq, nt)] = (wt.data_ptr(), wt.numel())
+            if len(hp["ws"]) > 64:
+                hp["ws"] = {(nq, nt): ws}
+        elif self._matcher["workspace_host_path"].data_ptr() != ws[0]:      # the workspace grew since: refresh
+            wt = self._matcher["workspace_host_path"]
+            ws = hp["ws"][(nq, nt)] = (wt.data_ptr(), wt.numel())
+        # packed outputs: idx (nq*8) | dist (nq*8) | keep (nq) | pad | n_keep (4)
+        off_keep, off_n = nq * 16, (nq * 17 + 3) & ~3
+        total = off_n + 4
+        # device buffers are reused call after call (stream order protects them); the page-locked result buffer is the
+        # only thing a later call could overwrite under the reader, so it comes from a small ring
+        k = hp["pos"] = (hp["pos"] + 1) % PendingMatch.DEPTH
+        slot = hp["ring"][k]
+        if slot["owner"] is not None:
+            slot["owner"]._resolve()             # an uncollected older call still points at this slot
+        base = hp["out_ptr"]
+        _lib.check(L.mk_upload_2d(hp["q_ptr"], stride, q.__array_interface__["data"][0], row, row, nq, sptr))
+        if nt:
+            _lib.check(L.mk_upload_2d(hp["t_ptr"], stride, t.__array_interface__["data"][0], row, row, nt, sptr))
+        _lib.check(L.mk_knn2(code, hp["q_ptr"], nq, hp["t_ptr"] if nt else None, nt, dim, stride, base, base + nq * 8,
+                             float(ratio), base + off_keep, base + off_n, ws[0], ws[1], sptr))
+        _lib.check(L.mk_download_2d(slot["host_ptr"], total, base, total, total, 1, sptr))
+        slot["event"].record(hp["stream"])
         pending = PendingMatch(slot, nq, off_keep, (q, t))
         slot["owner"] = pending
         return pending
