@@ -204,7 +204,7 @@ def run_b200(args):
     s_match = torch.cuda.Stream(device=dev)     # matching and compositing of a frame are independent: two streams
     main = torch.cuda.current_stream(dev)
 
-    def one_step(k, mp, ev=None):
+    def one_step(k, mp, ev=None, last=False):
         """ev = [start, match done, compositing done, step done] recorded on the streams that run the work."""
         if ev: ev[0].record(main)
         s_match.wait_stream(main)
@@ -212,7 +212,7 @@ def run_b200(args):
             matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
             if ev: ev[1].record(s_match)
         if multi:
-            mosaic.step_planned(k, frames[k])
+            mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # frame exchange of step k+1 posted under step k
         else:
             mp.update_device(frames[k], Hs[k])
         if ev: ev[2].record(main)
@@ -222,7 +222,7 @@ def run_b200(args):
     # ---------------- device-resident throughput ("value") ----------------
     def timed_pass(mp, collect_bytes, do_flush=True):
         for k in range(W):
-            one_step(k, mp)
+            one_step(k, mp, last=(k == W - 1))
         barrier()
         clocks = ClockSampler(local)
         clocks.start()
@@ -234,7 +234,7 @@ def run_b200(args):
         for k in range(K):
             if do_flush:
                 flush.zero_()                   # evict L2 (126 MB) between steps, outside the timed events
-            one_step(W + k, mp, evs[k])
+            one_step(W + k, mp, evs[k], last=(k == K - 1))
         barrier()
         t1 = time.perf_counter()
         launches = mb.launch_count() - n0

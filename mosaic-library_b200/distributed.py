@@ -61,7 +61,8 @@ class ShardedMosaic:
         self.h, self.w = frame_shape
         self._factory = mapper_factory
         self.mappers: dict[tuple[int, int], object] = {}
-        self._recv = {}          # source rank -> receive buffer
+        self._recv = {}          # (source rank, step parity) -> receive buffer
+        self._posted = {}        # step -> exchange posted ahead of time (step_planned with next_frame)
         self.frames_applied = 0
         self.bytes_sent = 0
 
@@ -132,9 +133,18 @@ class ShardedMosaic:
         self._plan_H = allH.reshape(self.world, -1, 3, 3)
         self._plan_table = [self.routing([self._plan_H[s, k] for s in range(self.world)]) for k in range(self._plan_H.shape[1])]
 
-    def step_planned(self, k: int, frame: torch.Tensor) -> int:
-        """Step k of a planned sequence: no collective, only the frame send/recv the routing asks for."""
-        return self.step(frame, None, H_all=[self._plan_H[s, k] for s in range(self.world)], table=self._plan_table[k])
+    def step_planned(self, k: int, frame: torch.Tensor, next_frame: torch.Tensor | None = None) -> int:
+        """Step k of a planned sequence: no collective, only the frame send/recv the routing asks for.
+        With `next_frame` (this rank's frame of step k+1, already on the device) the exchange of step k+1 is posted BEFORE
+        step k is composited, so the NVLink transfer runs under the kernels of step k (receive buffers alternate by step
+        parity).  Every rank must then pass next_frame for the same steps, and the next call must be step k+1."""
+        H_all = [self._plan_H[s, k] for s in range(self.world)]
+        posted = self._posted.pop(k, None)
+        if posted is None:
+            posted = self._post(frame, self._plan_table[k], k & 1)
+        if next_frame is not None and k + 1 < len(self._plan_table):
+            self._posted[k + 1] = self._post(next_frame, self._plan_table[k + 1], (k + 1) & 1)
+        return self._composite(frame, H_all, self._plan_table[k], posted)
 
     def step(self, frame: torch.Tensor | None, H: np.ndarray | None, H_all: Sequence | None = None, table=None) -> int:
         """One step: this rank contributes `frame` [h, w, 3] uint8 (already on self.device) with absolute
@@ -144,6 +154,10 @@ class ShardedMosaic:
             H_all = self.exchange_homographies(H)
         if table is None:
             table = self.routing(H_all)
+        return self._composite(frame, H_all, table, self._post(frame, table, 0))
+
+    def _post(self, frame, table, parity: int):
+        """Start the sends / receives one step's routing table asks of this rank -> (requests, {source rank: buffer})."""
         ops, incoming = [], {}
         if self.world > 1:
             for s, dests in enumerate(table):
@@ -153,24 +167,33 @@ class ShardedMosaic:
                             ops.append(dist.P2POp(dist.isend, frame, d))
                             self.bytes_sent += frame.numel()
                 elif self.rank in dests:
-                    buf = self._recv.get(s)
+                    buf = self._recv.get((s, parity))
                     if buf is None:
                         buf = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device)
-                        self._recv[s] = buf
+                        self._recv[(s, parity)] = buf
                     incoming[s] = buf
                     ops.append(dist.P2POp(dist.irecv, buf, s))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
+        return (dist.batch_isend_irecv(ops) if ops else []), incoming
+
+    def _composite(self, frame, H_all, table, posted) -> int:
+        reqs, incoming = posted
+        waited = False
         done = 0
         for s, dests in enumerate(table):
             if self.rank not in dests:
                 continue
+            if s != self.rank and not waited:     # local tiles that come first in source order do not wait for the exchange
+                for req in reqs:
+                    req.wait()
+                waited = True
             src = frame if s == self.rank else incoming[s]
             for (xi, yi) in dests[self.rank]:
                 H_tile = homogeneous_translation(-xi * self.tile_size[0], -yi * self.tile_size[1]) @ H_all[s]   # mosaic.py:617
                 self._mapper((xi, yi)).update_device(src, H_tile)
                 done += 1
+        if not waited:
+            for req in reqs:
+                req.wait()                        # sends must be complete before the caller reuses the frame
         self.frames_applied += done
         return done
 

@@ -68,11 +68,15 @@ def _worker(rank, world, port, q):
         sm = ShardedMosaic(GRID, TILE, OracleMapper, FRAME, torch.device("cpu"))
         sm.connect()
         sm.plan(Hs[:, rank])                 # one all_gather of every pose (the bench path) ...
+        fr = [torch.from_numpy(frames[k, rank]) for k in range(STEPS)]
         for k in range(STEPS):
-            if k % 2 == 0:
-                sm.step_planned(k, torch.from_numpy(frames[k, rank]))
+            if k in (0, 3):                  # planned step that also posts the exchange of step k+1 ahead of time
+                sm.step_planned(k, fr[k], next_frame=fr[k + 1])
+            elif k in (1, 4):                # ... consumed here
+                sm.step_planned(k, fr[k])
             else:                            # ... and the per-step all_gather path
-                sm.step(torch.from_numpy(frames[k, rank]), Hs[k, rank])
+                sm.step(fr[k], Hs[k, rank])
+        assert not sm._posted
         assert all(sm.owner(t) == rank for t in sm.mappers)
         res = sm.gather(0)
         if rank == 0:
