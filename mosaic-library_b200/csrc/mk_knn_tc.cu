@@ -293,7 +293,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
-    if (!knn_tc_inputs_ok(p.flags)) return;   // not exact on this path: the guarded SIMT kernel handles this call
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + TcSmem::bar_off);
     unsigned long long *bar_a = bars + 0, *bar_bfull = bars + 1, *bar_bempty = bars + 1 + TC_MAX_STAGES,
@@ -334,19 +333,41 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_addr(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
+    // Launched with programmatic stream serialization: everything above overlapped the tail of the prep kernel.  Its outputs
+    // (operand copies, norms, zeroed flags and tickets) may only be touched below this line.
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    // the first loads need nothing but the mbarriers thread 0 has just initialised, so they start before the block-wide barrier
+    const int first_loads = min(my_tiles, nstages);
+    if (tid == 0) {
+        mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
+        for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * p.atom_elems, qrow0 + q0, bar_a);
+        for (int i = 0; i < first_loads; ++i) {
+            mbar_expect_tx(bar_bfull + i, (uint32_t)(nhalf * TcSmem::B_BYTES));
+            for (int h = 0; h < nhalf; ++h)
+                tma_load_2d(smem + TcSmem::b_slot(i * nhalf + h), &map_t, h * p.atom_elems, trow0 + (tile_lo + i) * TC_N, bar_bfull + i);
+        }
+    }
+    const bool inexact = KIND == 0 && !knn_tc_inputs_ok(p.flags);   // bf16 would round: the guarded SIMT kernel handles this call
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (inexact) {                           // (the loads above are harmless; they complete into shared memory nobody reads)
+        if (tid == 0) {
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < first_loads; ++i) mbar_wait(bar_bfull + i, 0);
+        }
+        __syncthreads();
+        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+        return;
+    }
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (the first ring fill was issued above) =====================
         if (lane == 0) {
-            mbar_expect_tx(bar_a, (uint32_t)(nhalf * TcSmem::A_BYTES));
-            for (int h = 0; h < nhalf; ++h) tma_load_2d(smem + TcSmem::a_off(h), &map_q, h * p.atom_elems, qrow0 + q0, bar_a);
-            for (int i = 0; i < my_tiles; ++i) {
+            for (int i = first_loads; i < my_tiles; ++i) {
                 const int s = i % nstages, use = i / nstages;
-                if (use > 0) mbar_wait(bar_bempty + s, (use - 1) & 1);
+                mbar_wait(bar_bempty + s, (use - 1) & 1);
                 mbar_expect_tx(bar_bfull + s, (uint32_t)(nhalf * TcSmem::B_BYTES));
                 for (int h = 0; h < nhalf; ++h)
                     tma_load_2d(smem + TcSmem::b_slot(s * nhalf + h), &map_t, h * p.atom_elems, trow0 + (tile_lo + i) * TC_N, bar_bfull + s);
@@ -560,6 +581,7 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ 
                                                           __nv_bfloat16 *__restrict__ tb, float *__restrict__ qn,
                                                           float *__restrict__ tn, int *flags, int32_t *n_keep)
 {
+    asm volatile("griddepcontrol.launch_dependents;\n");     // the GEMM kernel may start its prologue now (it waits before reading)
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row == 0 && lane == 0 && n_keep) *n_keep = 0;
@@ -593,6 +615,7 @@ __global__ void __launch_bounds__(256) knn_tc_prep_bits_kernel(const uint8_t *__
                                                                uint8_t *__restrict__ tb, float *__restrict__ qn, float *__restrict__ tn,
                                                                int32_t *n_keep, int *zero, int nzero)
 {
+    asm volatile("griddepcontrol.launch_dependents;\n");     // the GEMM kernel may start its prologue now (it waits before reading)
     const int tpr = kp >> 4;                                 // threads per row: 8 or 16
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int row = gid / tpr;
@@ -761,8 +784,15 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
         configured.store(dev);
     }
     dim3 grid(pl.nqb, pl.splits, np);
-    if (P.hamming) knn2_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
-    else knn2_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(map_q, map_t, P);
+    // programmatic dependent launch: the GEMM kernel's prologue (barriers, TMEM allocation) runs under the prep kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (P.hamming) MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P));
+    else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P));
     MK_LAUNCH_CHECK("knn2_tc_kernel");
     *flags_out = flags;
     return MK_OK;
