@@ -318,14 +318,23 @@ def run_b200(args):
         """Same calls, software-pipelined by one frame: queue frame k's matching, hand frame k to the mapper, then collect
         frame k-1's matches -- every result is still read on the host inside the timed region."""
         kept, pending = 0, None
+        trace = [0.0, 0.0, 0.0] if os.environ.get("MK_BENCH_TRACE") else None
         for k in range(k0, k0 + n):
             img, q, t = e2e_inputs(k)
+            ta = time.perf_counter()
             nxt = matcher.knn_match_arrays_async(q, t, RATIO)
+            tb = time.perf_counter()
             e2e_update(k, img)
+            tc = time.perf_counter()
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
+            if trace:
+                trace[0] += tb - ta; trace[1] += tc - tb; trace[2] += time.perf_counter() - tc
         kept += int(pending.result()[2].sum())
+        if trace:
+            print(f"[e2e trace] per frame: submit match {trace[0] / n * 1e6:.0f} us, mapper.update {trace[1] / n * 1e6:.0f} us, "
+                  f"collect {trace[2] / n * 1e6:.0f} us", file=sys.stderr)
         return kept
 
     def timed(fn):
@@ -340,7 +349,23 @@ def run_b200(args):
             s = float(tt.item())
         return s
 
-    e2e_loop(0, W)
+    if os.environ.get("MK_BENCH_TRACE") and not multi:
+        dd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
+        for name, fn in (("plain copy of pin_frames", lambda k: dd.copy_(pin_frames[k % 4], non_blocking=True)),
+                         ("mapper.update(host) only", lambda k: e2e_mapper.update(pin_frames[k % 4].numpy(), Hs[k])),
+                         ("update_device only", lambda k: e2e_mapper.update_device(frames[k], Hs[k]))):
+            for k in range(5):
+                fn(k)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for k in range(K):
+                fn(k)
+            torch.cuda.synchronize()
+            print(f"[e2e trace] {name}: {(time.perf_counter() - t0) / K * 1e6:.0f} us/frame", file=sys.stderr)
+    # the host link needs its own warm-up: the first few dozen copies out of freshly page-locked buffers run at about half
+    # speed on this box (tools/pin_probe.py: 150-200 us per 6.2 MB frame, then a steady 117 us), and nothing before this
+    # point has moved data over PCIe
+    for _ in range(max(1, 64 // max(W, 1))):
+        e2e_loop(0, W)
     e2e_s = timed(lambda: e2e_loop(W, K))
     for k in range(W):
         e2e_sync_step(k)
@@ -360,7 +385,7 @@ def run_b200(args):
     link_gbs = 20 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
     e2e = {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
-                    "while frame k is in flight; wall clock incl. Python"),
+                    "while frame k is in flight; wall clock incl. Python; ~64 untimed frames first (PCIe path warm-up)"),
            "host_link": {"h2d_gbs_achieved": (world * K / e2e_s) * h2d / 1e9 / world, "h2d_gbs_plain_copy": link_gbs,
                          "note": "per GPU; plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
            "sync_value": world * K / e2e_sync_s,

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -790,7 +791,8 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("MK_NO_PDL") != nullptr;   // diagnosis switch: plain stream-ordered launch
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
     if (P.hamming) MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P));
     else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P));
     MK_LAUNCH_CHECK("knn2_tc_kernel");
