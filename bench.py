@@ -361,11 +361,15 @@ def run_b200(args):
                 fn(k)
             torch.cuda.synchronize()
             print(f"[e2e trace] {name}: {(time.perf_counter() - t0) / K * 1e6:.0f} us/frame", file=sys.stderr)
-    # the host link needs its own warm-up: the first few dozen copies out of freshly page-locked buffers run at about half
-    # speed on this box (tools/pin_probe.py: 150-200 us per 6.2 MB frame, then a steady 117 us), and nothing before this
-    # point has moved data over PCIe
-    for _ in range(max(1, 64 // max(W, 1))):
-        e2e_loop(0, W)
+    # the host link needs its own warm-up: every freshly page-locked buffer (and fresh staging buffer) runs at about half speed
+    # for its first few dozen copies on this box (tools/pin_probe2.py: 146 -> 132 -> 120 us per 6.2 MB frame) and nothing
+    # before this point has moved data over PCIe.  Warm up in chunks until two consecutive chunks agree within 5 %.
+    chunk, prev = min(32, W + K), None
+    for _ in range(16):
+        cur_s = timed(lambda: e2e_loop(0, chunk)) / chunk
+        if prev is not None and abs(cur_s - prev) < 0.05 * prev:
+            break
+        prev = cur_s
     e2e_s = timed(lambda: e2e_loop(W, K))
     for k in range(W):
         e2e_sync_step(k)
@@ -385,7 +389,7 @@ def run_b200(args):
     link_gbs = 20 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
     e2e = {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
-                    "while frame k is in flight; wall clock incl. Python; ~64 untimed frames first (PCIe path warm-up)"),
+                    "while frame k is in flight; wall clock incl. Python; untimed frames first until the PCIe path is warm"),
            "host_link": {"h2d_gbs_achieved": (world * K / e2e_s) * h2d / 1e9 / world, "h2d_gbs_plain_copy": link_gbs,
                          "note": "per GPU; plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
            "sync_value": world * K / e2e_sync_s,
