@@ -213,3 +213,75 @@ class ShardedMosaic:
                 tiles.update(part)
         tiles.setdefault((self.grid[0] - 1, self.grid[1] - 1), np.zeros((self.tile_size[1], self.tile_size[0], 3), np.uint8))
         return combine_tiles(tiles, self.tile_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# matching: every (query image, train image) pair is an independent unit (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+def all_pairs_blocks(n_images: int, block: int = 8) -> list[list[tuple[int, int]]]:
+    """Upper-triangular pair list (query j > train i, the direction SequentialMosaic.match_features uses for consecutive
+    frames, mosaic.py:402-438: query = later frame) cut into block x block squares of the pair matrix, so that the pairs
+    of one unit of work share their descriptor sets (2 * block sets instead of block^2)."""
+    blocks = []
+    for bi in range(0, n_images, block):
+        for bj in range(bi, n_images, block):
+            pairs = [(j, i) for i in range(bi, min(bi + block, n_images)) for j in range(max(bj, i + 1), min(bj + block, n_images))]
+            if pairs:
+                blocks.append(pairs)
+    return blocks
+
+
+def all_pairs_schedule(n_images: int, world: int, rank: int, block: int = 8) -> list[tuple[int, int]]:
+    """Pairs owned by `rank`: blocks are dealt out longest-first to the least-loaded rank (diagonal blocks hold fewer
+    pairs), which keeps the per-rank pair counts within one block of each other.  Deterministic, identical on all ranks."""
+    block = max(1, min(block, n_images // (2 * world)))          # few images: smaller squares, or one rank would own them all
+    blocks = sorted(all_pairs_blocks(n_images, block), key=lambda b: (-len(b), b[0]))
+    load = [0] * world
+    mine: list[tuple[int, int]] = []
+    for b in blocks:
+        r = min(range(world), key=lambda x: (load[x], x))
+        load[r] += len(b)
+        if r == rank:
+            mine.extend(b)
+    return mine
+
+
+class ShardedMatcher:
+    """All-pairs descriptor matching over the GPUs of one box: descriptor sets replicated on every rank (2000 x 4000 SIFT
+    rows as bf16 = 2 GB), the pair list partitioned by all_pairs_schedule, each rank matching its pairs with ONE batched
+    launch per chunk (Matcher.knn_match_sets -> mk_knn2_batched), and one all_reduce of the [n, n] survivor-count matrix --
+    the loop-closure graph needs "how many ratio-test survivors does pair (j, i) have", the match lists stay on the rank
+    that computed them.  No data-path collective: the pairs are independent.
+
+    matcher: anything with knn_match_sets(sets, pairs, ratio) (mosaicking_b200.Matcher on the GPU; the CPU tests inject
+    an oracle-backed stand-in and run this over gloo)."""
+
+    def __init__(self, matcher, device, rank: int | None = None, world: int | None = None, block: int = 8):
+        self.matcher, self.device, self.block = matcher, device, block
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+
+    def match_all_pairs(self, sets: Sequence[np.ndarray], ratio: float = 0.7, chunk: int = 4096, keep_results: bool = False):
+        """-> (local, counts): counts [n, n] int64 on the host with counts[query, train] = number of ratio-test survivors,
+        summed over ranks; local = {(query, train): (idx, dist, keep)} for the pairs this rank owns when keep_results is
+        set (host copies of the match lists), else just the list of owned pairs.  The descriptor sets are uploaded once
+        per call; without keep_results only 4 bytes per pair leave the device."""
+        n = len(sets)
+        mine = all_pairs_schedule(n, self.world, self.rank, self.block)
+        local = {} if keep_results else list(mine)
+        counts = torch.zeros((n, n), dtype=torch.int64)
+        handle = self.matcher.upload_sets(sets) if mine and hasattr(self.matcher, "upload_sets") else sets
+        for lo in range(0, len(mine), chunk):
+            part = mine[lo:lo + chunk]
+            if keep_results:
+                for (qj, ti), (idx, dist_, keep) in zip(part, self.matcher.knn_match_sets(handle, part, ratio)):
+                    local[(qj, ti)] = (idx, dist_, keep)
+                    counts[qj, ti] = int(np.count_nonzero(keep))
+            else:
+                pr = np.asarray(part, np.int64)
+                counts[pr[:, 0], pr[:, 1]] = torch.from_numpy(self.matcher.knn_match_sets(handle, part, ratio, output="counts").astype(np.int64))
+        if self.world > 1:
+            c = counts.to(self.device)
+            dist.all_reduce(c)
+            counts = c.cpu()
+        return local, counts.numpy()

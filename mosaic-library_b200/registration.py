@@ -85,6 +85,16 @@ def upload_descriptors(desc, device=None) -> tuple[torch.Tensor, int]:
     return out, dim
 
 
+class DescriptorSets:
+    """Descriptor sets resident on the device (Matcher.upload_sets): one row matrix + the offsets of the sets in it."""
+
+    def __init__(self, desc, set_off, sizes, dtype, dim, total):
+        self.desc, self.set_off, self.sizes, self.dtype, self.dim, self.total = desc, set_off, sizes, dtype, dim, total
+
+    def __len__(self):
+        return len(self.sizes)
+
+
 class PendingMatch:
     """Handle of one queued Matcher.knn_match_arrays_async call."""
 
@@ -289,23 +299,40 @@ class Matcher:
         slot["owner"] = pending
         return pending
 
-    def knn_match_sets(self, sets: Sequence[np.ndarray], pairs: Sequence[tuple[int, int]], ratio: float = 0.7):
-        """Many (query set, train set) pairs in ONE launch: the consecutive-frame loop of
-        SequentialMosaic.match_features (mosaic.py:402-438: query = frame k+1, train = frame k) or all-pairs loop closure.
-        sets: descriptor arrays of equal width / dtype; pairs: (query index, train index) into `sets`.
-        -> list of (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) per pair (same values as knn_match_arrays)."""
+    def upload_sets(self, sets: Sequence[np.ndarray]) -> "DescriptorSets":
+        """Concatenate descriptor arrays of equal width / dtype into ONE device matrix (rows padded to 16 bytes) plus the
+        set-offset table mk_knn2_batched indexes it with.  Pass the handle to knn_match_sets as often as needed: all-pairs
+        matching uploads the keyframe set once and then only sends pair lists."""
         device = _cuda_device(self._device)
-        if not len(pairs):
-            return []
         arrs = [np.ascontiguousarray(a) for a in sets]
+        if not arrs:
+            raise _bad_input("no descriptor sets")
         dtype, dim = arrs[0].dtype, arrs[0].shape[1]
         if any(a.dtype != dtype or a.ndim != 2 or a.shape[1] != dim for a in arrs):
             raise _bad_input("all descriptor sets must share dtype and width")
-        code = _norm_code(self._norm, dtype, self._engine)
         sizes = np.array([a.shape[0] for a in arrs], np.int64)
         total = int(sizes.sum())
         desc, _ = upload_descriptors(np.concatenate(arrs) if total else np.zeros((0, dim), dtype), device)
         set_off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)).to(device)
+        return DescriptorSets(desc, set_off, sizes, dtype, dim, total)
+
+    def knn_match_sets(self, sets, pairs: Sequence[tuple[int, int]], ratio: float = 0.7, output: str = "host"):
+        """Many (query set, train set) pairs in ONE launch: the consecutive-frame loop of
+        SequentialMosaic.match_features (mosaic.py:402-438: query = frame k+1, train = frame k) or all-pairs loop closure.
+        sets: descriptor arrays of equal width / dtype, or the handle upload_sets returned; pairs: (query index, train
+        index) into `sets`.
+        output="host"   -> list of (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) per pair (= knn_match_arrays);
+        output="device" -> (idx, dist, keep, out_off): device tensors over all pairs' query rows, rows of pair p at
+                           out_off[p]:out_off[p+1] (host int32 array);
+        output="counts" -> int32 array, ratio-test survivors per pair (only 4 bytes per pair leave the device)."""
+        if output not in ("host", "device", "counts"):
+            raise ValueError("output must be 'host', 'device' or 'counts'")
+        device = _cuda_device(self._device)
+        if not len(pairs):
+            return [] if output == "host" else (np.zeros((0,), np.int32) if output == "counts" else None)
+        ds = sets if isinstance(sets, DescriptorSets) else self.upload_sets(sets)
+        desc, set_off, sizes, dtype, dim, total = ds.desc, ds.set_off, ds.sizes, ds.dtype, ds.dim, ds.total
+        code = _norm_code(self._norm, dtype, self._engine)
         pr = np.asarray(pairs, np.int32).reshape(-1, 2)
         nq_per = sizes[pr[:, 0]]
         out_off_h = np.concatenate([[0], np.cumsum(nq_per)]).astype(np.int32)
@@ -315,19 +342,24 @@ class Matcher:
         idx = torch.empty((rows, 2), dtype=torch.int32, device=device)
         dist = torch.empty((rows, 2), dtype=torch.float32, device=device)
         keep = torch.empty((rows,), dtype=torch.uint8, device=device)
+        n_keep = torch.empty((len(pr),), dtype=torch.int32, device=device) if output == "counts" else None
         L = self._matcher["lib"]
-        out = []
         CH = 65535                                   # grid.z limit per launch
         for lo in range(0, len(pr), CH):
             hi = min(len(pr), lo + CH)
             ws = self._workspace(L.mk_knn2_batched_workspace_bytes(code, hi - lo, max_nq, max_nt, dim, total), device)
             stride = desc.stride(0) * desc.element_size()
-            base = int(out_off_h[lo])
             _lib.check(L.mk_knn2_batched(code, desc.data_ptr(), total, dim, stride, set_off.data_ptr(),
                                          pairs_d.data_ptr() + lo * 8, hi - lo, out_off.data_ptr() + lo * 4, max_nq, max_nt,
-                                         idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), None,
+                                         idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(),
+                                         n_keep.data_ptr() + lo * 4 if n_keep is not None else None,
                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+        if output == "counts":
+            return n_keep.cpu().numpy()
+        if output == "device":
+            return idx, dist, keep, out_off_h
         idx_h, dist_h, keep_h = idx.cpu().numpy(), dist.cpu().numpy(), keep.cpu().numpy().astype(bool)
+        out = []
         for p in range(len(pr)):
             sl = slice(out_off_h[p], out_off_h[p + 1])
             out.append((idx_h[sl], dist_h[sl], keep_h[sl]))

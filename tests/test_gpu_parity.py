@@ -209,6 +209,14 @@ def test_knn_match_sets_vs_oracle(kind):
         assert np.array_equal(idx, oi), (kind, a, b)
         assert np.array_equal(dist, od), (kind, a, b)
         assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+    # resident sets + the other output forms give the same numbers
+    m = mb.Matcher(norm=norm, engine="popc" if kind.endswith("popc") else "auto")
+    handle = m.upload_sets(sets)
+    counts = m.knn_match_sets(handle, pairs, 0.7, output="counts")
+    assert counts.tolist() == [int(np.count_nonzero(k)) for _, _, k in res]
+    idx_d, dist_d, keep_d, off = m.knn_match_sets(handle, pairs, 0.7, output="device")
+    assert np.array_equal(idx_d.cpu().numpy(), np.concatenate([r[0] for r in res])) and off[-1] == idx_d.shape[0]
+    assert np.array_equal(keep_d.cpu().numpy().astype(bool), np.concatenate([r[2] for r in res]))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import mosaicking_b200 as mb
-from mosaicking_b200.distributed import ShardedMosaic, tiles_of_footprint
+from mosaicking_b200.distributed import ShardedMatcher, ShardedMosaic, all_pairs_schedule, tiles_of_footprint
 from oracle import oracle as orc
 
 TILE = (128, 96)
@@ -142,3 +142,81 @@ def test_tiles_of_footprint_equals_full_scan():
                 if mb.bbox_overlap(tc, crn):     # mosaic.py:612-614 over every tile
                     full.append((xi, yi))
         assert sorted(tiles_of_footprint(H, FRAME[1], FRAME[0], TILE, GRID)) == sorted(full)
+
+
+# ------------------------------------------------------------------------------------------------
+# all-pairs matching sharded over ranks (every (query image, train image) pair is independent)
+# ------------------------------------------------------------------------------------------------
+class OracleSetMatcher:
+    """CPU stand-in with Matcher.knn_match_sets' interface."""
+
+    def knn_match_sets(self, sets, pairs, ratio, output="host"):
+        out = []
+        for a, b in pairs:
+            idx, dist_ = orc.knn2(sets[a], sets[b], "hamming")
+            out.append((idx, dist_, orc.ratio_test(idx, dist_, ratio)))
+        if output == "counts":
+            return np.array([np.count_nonzero(k) for _, _, k in out], np.int32)
+        return out
+
+
+def _desc_sets():
+    rng = np.random.default_rng(21)
+    sets = [rng.integers(0, 256, (40 + 7 * k, 32), dtype=np.uint8) for k in range(9)]
+    sets[5][:20] = sets[2][:20]            # two images that really match
+    sets[7][3:30] = sets[2][10:37]
+    return sets
+
+
+def _match_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sets = _desc_sets()
+        sm = ShardedMatcher(OracleSetMatcher(), torch.device("cpu"))
+        local, counts = sm.match_all_pairs(sets, 0.7, chunk=5, keep_results=True)
+        owned, counts2 = sm.match_all_pairs(sets, 0.7, chunk=7)          # counts-only form: same matrix, same ownership
+        assert sorted(owned) == sorted(local) and np.array_equal(counts, counts2)
+        q.put((rank, sorted(local), counts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_all_pairs_matching_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_match_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    sets = _desc_sets()
+    n = len(sets)
+    want = np.zeros((n, n), np.int64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            idx, dist_ = orc.knn2(sets[j], sets[i], "hamming")
+            want[j, i] = np.count_nonzero(orc.ratio_test(idx, dist_, 0.7))
+    owned = [set(map(tuple, pairs)) for _, pairs, _ in sorted(got)]
+    assert not (owned[0] & owned[1]) and (owned[0] | owned[1]) == {(j, i) for i in range(n) for j in range(i + 1, n)}
+    assert min(len(o) for o in owned) > 0
+    for _, _, counts in got:                 # every rank ends up with the whole survivor-count matrix
+        assert np.array_equal(counts, want)
+    assert want[5, 2] >= 10 and want[7, 2] >= 10
+
+
+def test_all_pairs_schedule_is_a_balanced_partition():
+    for n, world in ((37, 8), (300, 8), (5, 2), (1, 2), (64, 3)):
+        seen, loads = set(), []
+        for r in range(world):
+            p = all_pairs_schedule(n, world, r)
+            assert not (seen & set(p))
+            seen |= set(p); loads.append(len(p))
+        assert seen == {(j, i) for i in range(n) for j in range(i + 1, n)}
+        if n >= 4 * world:
+            assert max(loads) - min(loads) <= 64
