@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
                 *reinterpret_cast<uint4 *>(s_src + r * T.rowbytes + c) = z;
             }
         }
-        mbar_wait(&s_bar, parity);
+        if (warp == 0) mbar_wait(&s_bar, parity);   // one polling warp; the others park at the hardware barrier (no issue slots)
         parity ^= 1u;
         canvas_loaded = true;
         __syncthreads();
@@ -515,15 +515,16 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
     }   // frames of this tile
 
     if (!canvas_loaded) return;   // no frame touched this tile
-    fence_proxy_async();   // make the generic-proxy writes to s_canvas visible to the bulk store engine
     __syncthreads();
 
-    // ---- write back the rows that changed: one bulk store per row ------------------------------
-    if (warp == 0) {
-        const int y = tileY + lane;
-        if (y < p.Hc && ((s_rowchg >> lane) & 1u))
-            bulk_s2g(p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, &s_canvas[lane][0], (uint32_t)nvec * 16u);
-        bulk_commit_wait_read();
+    // ---- write back the rows that changed.  Plain 16-byte stores: a bulk store would make the CTA wait ~1.5 us until the
+    //      copy engine has read the tile out of shared memory before it may exit; these retire with the issuing warp. --------
+    const unsigned chg = s_rowchg;
+    for (int v = tid; v < TH * ROWV; v += MTHREADS) {
+        const int r = v / ROWV, c = v - r * ROWV, y = tileY + r;
+        if (c < nvec && y < p.Hc && ((chg >> r) & 1u))
+            *reinterpret_cast<uint4 *>(p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3 + c * 16) =
+                *reinterpret_cast<const uint4 *>(&s_canvas[r][c * 16]);
     }
 }
 
