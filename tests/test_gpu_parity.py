@@ -95,7 +95,8 @@ def test_knn_f32_vs_oracle(nq, nt, dim, integer):
 
 
 @pytest.mark.parametrize("nq,nt,nbytes", [(5000, 5000, 32), (2000, 2000, 32), (700, 900, 16), (513, 4099, 24), (1000, 3, 32),
-                                           (300, 4000, 64)])
+                                           (300, 4000, 64), (600, 800, 31), (900, 700, 17), (150000, 2, 32), (20000, 20, 32),
+                                           (129, 2100, 1)])
 def test_knn_hamming_tensor_engine(nq, nt, nbytes):
     """Optional engine: Hamming = popc(q) + popc(t) - 2 q.t on bit-expanded e4m3 rows through the tcgen05 GEMM.
     Same indices, distances and keep flags as the XOR+POPC kernel / cv2.BFMatcher(NORM_HAMMING)."""
@@ -114,6 +115,23 @@ def test_knn_hamming_tensor_engine(nq, nt, nbytes):
     assert np.array_equal(idx, oi)
     assert np.array_equal(dist, od)
     assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+
+
+def test_knn_hamming_tensor_engine_extreme_counts():
+    """Keys at both ends of the 16-bit range: all-zero queries against all-one train rows (count 256 everywhere, so every
+    candidate ties and the two lowest train indices must win), identical rows (count 0), and a mix."""
+    nq, nt = 700, 900
+    q = np.zeros((nq, 32), np.uint8); t = np.full((nt, 32), 255, np.uint8)
+    q[100:200] = 255                       # these rows are at distance 0 from every train row
+    t[500] = 0; t[777] = 0                 # ... and these train rows at distance 0 from the zero queries
+    rng = np.random.default_rng(2)
+    q[300:400] = rng.integers(0, 256, (100, 32), dtype=np.uint8)
+    for engine in ("popc", "tensor"):
+        idx, dist, keep = mb.Matcher(norm="hamming", engine=engine).knn_match_arrays(q, t, 0.7)
+        oi, od = orc.knn2(q, t, "hamming")
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), engine
+        assert np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+    assert idx[0].tolist() == [500, 777] and idx[150].tolist() == [0, 1] and dist[150].tolist() == [0.0, 0.0]
 
 
 def test_knn_match_arrays_async_ring():
