@@ -80,9 +80,11 @@ uint64_t mk_launch_count(void);
  *   workspace scratch of at least mk_knn2_workspace_bytes(..) bytes, 256-byte aligned.
  * ------------------------------------------------------------------------------------- */
 size_t mk_knn2_workspace_bytes(int norm, int nq, int nt, int dim);
-/* 1 if mk_knn2 routes this problem through the tcgen05 / TMA descriptor GEMM (L2 norms, dim <= 128 and
- * enough pairs to amortise the extra launches; float rows must also turn out to be integer-valued in
- * [0,255] -- OpenCV SIFT is -- otherwise the bit-exact SIMT kernel runs, decided on the device). */
+/* 1 if mk_knn2 routes this problem through the tcgen05 / TMA descriptor GEMM: L2 norms with dim <= 128, or
+ * MK_NORM_HAMMING_TC with dim <= 32 bytes (bit-expanded fp8 rows, fp16 accumulators), and enough pairs to
+ * amortise the extra launch (>= 256 K).  Float rows must also turn out to be integer-valued in [0,255] --
+ * OpenCV SIFT is -- otherwise the bit-exact SIMT kernel runs, decided on the device.  MK_NORM_HAMMING always
+ * takes the XOR+POPC kernel; both Hamming codes return identical results. */
 int mk_knn2_uses_tensor_cores(int norm, int nq, int nt, int dim);
 
 int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t row_stride,
