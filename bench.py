@@ -370,10 +370,10 @@ def run_b200(args):
         if prev is not None and abs(cur_s - prev) < 0.05 * prev:
             break
         prev = cur_s
-    e2e_s = timed(lambda: e2e_loop(W, K))
+    e2e_s = float(np.median([timed(lambda: e2e_loop(W, K)) for _ in range(3)]))     # median of three passes of K frames
     for k in range(W):
         e2e_sync_step(k)
-    e2e_sync_s = timed(lambda: [e2e_sync_step(W + k) for k in range(K)])
+    e2e_sync_s = float(np.median([timed(lambda: [e2e_sync_step(W + k) for k in range(K)]) for _ in range(3)]))
     h2d = fh * fw * 3 + 2 * NDESC * 32
     d2h = NDESC * (2 * 4 + 2 * 4 + 1)
     # what the host link delivers for the same kind of copy (page-locked -> device, frame-sized), for the e2e number's context
@@ -389,7 +389,7 @@ def run_b200(args):
     link_gbs = 20 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
     e2e = {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
-                    "while frame k is in flight; wall clock incl. Python; untimed frames first until the PCIe path is warm"),
+                    "while frame k is in flight; wall clock incl. Python, median of 3 passes of K frames; untimed frames first until the PCIe path is warm"),
            "host_link": {"h2d_gbs_achieved": (world * K / e2e_s) * h2d / 1e9 / world, "h2d_gbs_plain_copy": link_gbs,
                          "note": "per GPU; plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
            "sync_value": world * K / e2e_sync_s,
