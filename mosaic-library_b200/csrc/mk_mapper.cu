@@ -179,11 +179,13 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
 {
     __shared__ __align__(16) uint8_t s_canvas[TH][ROWB];
     __shared__ __align__(16) uint32_t s_warp[TH][TW];
+    __shared__ __align__(16) uint8_t s_mask[TH][TW];      // canvas-mask tile, staged with the canvas rows
     __shared__ double s_row[3][EH][3];
     __shared__ unsigned long long s_m0[EH];
     __shared__ unsigned long long s_h[EH];
     __shared__ unsigned long long s_v[TH];
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar;     // source rectangle staged
+    __shared__ __align__(8) unsigned long long s_bar_c;   // canvas tile staged (needed from phase 2 on only)
     __shared__ uint8_t s_side[EH][4];
     __shared__ int s_corner[4][3];
     // ROI mode keeps the (non-binary) warped ROI values: erosion = 5x5 minimum
@@ -204,8 +206,9 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
         tileX = (p.tx0 + (int)blockIdx.x) * TW; tileY = (p.ty0 + (int)blockIdx.y) * TH;
     }
     const int nvec = min(ROWV, ((p.Wc - tileX) * 3 + 15) >> 4);  // 16-byte vectors holding canvas pixels
+    const int mbytes = min(TW, (p.Wc - tileX + 15) & ~15);       // mask bytes of a tile row (pitch is a multiple of 16, >= Wc)
     const FrameDesc &F = *(BATCH ? &s_frame : &p.f0);
-    if (tid == 160) { mbar_init(&s_bar, 1); s_rowchg = 0u; }
+    if (tid == 160) { mbar_init(&s_bar, 1); mbar_init(&s_bar_c, 1); s_rowchg = 0u; }
     bool canvas_loaded = false;
     uint32_t parity = 0;
 
@@ -296,20 +299,15 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
         const int c_lo = use_smem ? max(0, -T.bx0) : 0;
         const int c_hi = use_smem ? max(c_lo, min(T.rowbytes, row_end16 - T.bx0)) : 0;
         const int r_lo = use_smem ? max(0, -T.sy0) : 0, r_hi = use_smem ? min(T.R, F.h - T.sy0) : 0;   // rows inside the frame
+        // The source rectangle goes first and alone: phase 1 needs nothing else, and when a whole wave of CTAs starts at once
+        // the HBM burst they wait for is 40 % shorter.  The canvas rows are requested when phase 1 begins (below).
         if (warp == 0) {
             if (c_hi > c_lo)
                 for (int r = r_lo + lane; r < r_hi; r += 32)
                     bulk_g2s(s_src + r * T.rowbytes + c_lo, F.src + (size_t)(T.sy0 + r) * F.spitch + (T.bx0 + c_lo),
                              (uint32_t)(c_hi - c_lo), &s_bar);
-        } else if (warp == 1) {
-            const int y = tileY + lane;
-            if (!canvas_loaded && y < p.Hc)
-                bulk_g2s(&s_canvas[lane][0], p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, (uint32_t)nvec * 16u, &s_bar);
         } else if (tid == 64) {
-            const int nrows_c = canvas_loaded ? 0 : min(TH, p.Hc - tileY);
-            const uint32_t tx = (uint32_t)nrows_c * (uint32_t)nvec * 16u +
-                                ((c_hi > c_lo && r_hi > r_lo) ? (uint32_t)(r_hi - r_lo) * (uint32_t)(c_hi - c_lo) : 0u);
-            mbar_arrive_expect_tx(&s_bar, tx);
+            mbar_arrive_expect_tx(&s_bar, (c_hi > c_lo && r_hi > r_lo) ? (uint32_t)(r_hi - r_lo) * (uint32_t)(c_hi - c_lo) : 0u);
         }
         if (use_smem && (c_lo > 0 || c_hi < T.rowbytes || r_lo > 0 || r_hi < T.R)) {
             const int row_end = F.w * 3, nch = T.rowbytes >> 4;
@@ -330,7 +328,17 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
         }
         if (warp == 0) mbar_wait(&s_bar, parity);   // one polling warp; the others park at the hardware barrier (no issue slots)
         parity ^= 1u;
-        canvas_loaded = true;
+        if (!canvas_loaded) {                       // first frame of this tile: fetch the canvas rows under phase 1
+            if (warp == 1) {
+                const int y = tileY + lane;
+                if (y < p.Hc) {
+                    bulk_g2s(&s_canvas[lane][0], p.canvas + (size_t)y * p.cpitch + (size_t)tileX * 3, (uint32_t)nvec * 16u, &s_bar_c);
+                    bulk_g2s(&s_mask[lane][0], p.cmask + (size_t)y * p.mpitch + (size_t)tileX, (uint32_t)mbytes, &s_bar_c);
+                }
+            } else if (tid == 64) {
+                mbar_arrive_expect_tx(&s_bar_c, (uint32_t)min(TH, p.Hc - tileY) * ((uint32_t)nvec * 16u + (uint32_t)mbytes));
+            }
+        }
         __syncthreads();
     }
 
@@ -438,6 +446,10 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
             s_v[tid] = bits;
         }
     }
+    if (!canvas_loaded) {
+        if (warp == 0) mbar_wait(&s_bar_c, 0);      // used once per CTA: phase 0
+        canvas_loaded = true;
+    }
     __syncthreads();
 
     // ---- phase 2: blend; thread = 4 consecutive pixels = 3 aligned canvas words --------------
@@ -455,7 +467,8 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
         const uint32_t c0 = cw[0], c1 = cw[1], c2 = cw[2];
         uint32_t px[4] = { c0 & 0xFFFFFFu, (c0 >> 24) | ((c1 & 0xFFFFu) << 8), (c1 >> 16) | ((c2 & 0xFFu) << 16), c2 >> 8 };
         uint32_t *mp = reinterpret_cast<uint32_t *>(p.cmask + (size_t)y * p.mpitch + x);
-        uint32_t mk4 = *mp;
+        uint32_t *ms = reinterpret_cast<uint32_t *>(&s_mask[r][4 * g]);
+        uint32_t mk4 = *ms;
         const uint4 wv4 = *reinterpret_cast<const uint4 *>(&s_warp[r][4 * g]);
         const uint32_t wv[4] = { wv4.x, wv4.y, wv4.z, wv4.w };
         float4 wa;
@@ -508,6 +521,7 @@ __global__ void __launch_bounds__(MTHREADS, (INTERP == 1) ? 5 : 3) mapper_update
             cw[1] = (px[1] >> 8) | (px[2] << 16);
             cw[2] = (px[2] >> 16) | (px[3] << 8);
             *mp = mk4;
+            *ms = mk4;      // later frames of a batched launch read the tile's mask from here
             if constexpr (BLEND == MK_BLEND_FEATHER) *reinterpret_cast<float4 *>(wp) = wa;
         }
     }
