@@ -162,6 +162,16 @@ int mk_upload_2d(void *dst_dev, size_t dst_pitch, const void *src_host, size_t s
 int mk_download_2d(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch, size_t row_bytes,
                    size_t rows, void *stream);
 
+/* Stream ordering without a host round trip, for callers that run matching and compositing of a frame side by side
+ * (the reference's loop is single-threaded and serial, mosaic.py:402-438 / 678-686): mk_stream_follow records `event` on
+ * `src_stream` and makes `dst_stream` wait for it -- everything queued on dst afterwards runs after everything queued on
+ * src before.  With MK_STREAM_NONE as dst the event is only recorded, with MK_STREAM_NONE as src it is only waited for
+ * (record now, join later).  Events come from mk_event_create (timing disabled) and are reusable. */
+#define MK_STREAM_NONE ((void *)~(uintptr_t)0)
+void *mk_event_create(void);
+void mk_event_destroy(void *event);
+int mk_stream_follow(void *event, void *src_stream, void *dst_stream);
+
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */
 int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,

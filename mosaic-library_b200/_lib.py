@@ -16,6 +16,7 @@ CSRC = PKG_DIR / "csrc"
 
 MK_OK = 0
 NORM_HAMMING, NORM_L2_U8, NORM_L2_F32, NORM_HAMMING_TC = 0, 1, 2, 3
+STREAM_NONE = C.c_void_p(-1).value          # MK_STREAM_NONE
 INTER_LINEAR, INTER_CUBIC = 1, 2
 BLEND_ALPHA, BLEND_FEATHER = 0, 1
 
@@ -23,6 +24,7 @@ EXPORTS = (
     "mk_abi_version", "mk_version_string", "mk_last_error", "mk_launch_count",
     "mk_knn2_workspace_bytes", "mk_knn2_uses_tensor_cores", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
+    "mk_event_create", "mk_event_destroy", "mk_stream_follow",
 )
 
 
@@ -78,6 +80,11 @@ def lib() -> C.CDLL:
     L.mk_upload_2d.argtypes = [vp, sz, vp, sz, sz, sz, vp]
     L.mk_download_2d.restype = i32
     L.mk_download_2d.argtypes = [vp, sz, vp, sz, sz, sz, vp]
+    L.mk_event_create.restype = vp
+    L.mk_event_destroy.restype = None
+    L.mk_event_destroy.argtypes = [vp]
+    L.mk_stream_follow.restype = i32
+    L.mk_stream_follow.argtypes = [vp, vp, vp]
     L.mk_mapper_footprint.restype = i32
     L.mk_mapper_footprint.argtypes = [i32, i32, i32, i32, vp, i32, vp]
     if L.mk_abi_version() != 1:

@@ -46,3 +46,23 @@ extern "C" int mk_download_2d(void *dst_host, size_t dst_pitch, const void *src_
         MK_CUDA_TRY(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return MK_OK;
 }
+
+extern "C" void *mk_event_create(void)
+{
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { mk::set_error("cudaEventCreateWithFlags failed"); return nullptr; }
+    return e;
+}
+
+extern "C" void mk_event_destroy(void *event)
+{
+    if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+}
+
+extern "C" int mk_stream_follow(void *event, void *src_stream, void *dst_stream)
+{
+    if (!event) { mk::set_error("mk_stream_follow: null event"); return MK_ERR_ARG; }
+    if (src_stream != MK_STREAM_NONE) MK_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(src_stream)));
+    if (dst_stream != MK_STREAM_NONE) MK_CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(dst_stream), static_cast<cudaEvent_t>(event), 0));
+    return MK_OK;
+}

@@ -663,6 +663,13 @@ static EncodeTiledFn encode_fn()
 // esz = 2: bf16 rows, 64 elements per 128-byte atom; esz = 1: e4m3 bytes, 128 elements per atom
 static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int box_rows, int esz)
 {
+    // a frame loop asks for the same few maps over and over (the operand copies live in a persistent workspace): keep the
+    // last encodings per thread, cuTensorMapEncodeTiled costs more than a microsecond each
+    struct Entry { const void *base; int rows, kp, box_rows, esz; CUtensorMap map; };
+    static thread_local Entry cache[8];
+    static thread_local int next = 0;
+    for (const Entry &e : cache)
+        if (e.base == base && e.rows == rows && e.kp == kp && e.box_rows == box_rows && e.esz == esz && base) { *map = e.map; return MK_OK; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MK_ERR_CUDA; }
     const cuuint64_t dims[2] = { (cuuint64_t)kp, (cuuint64_t)rows };
@@ -673,6 +680,9 @@ static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int bo
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MK_ERR_CUDA; }
+    Entry &slot = cache[next];
+    next = (next + 1) % 8;
+    slot.base = base; slot.rows = rows; slot.kp = kp; slot.box_rows = box_rows; slot.esz = esz; slot.map = *map;
     return MK_OK;
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .registration import _cuda_device
+from .registration import _cuda_device, _raw_stream
 
 try:
     import cv2 as _cv2
@@ -128,7 +128,28 @@ class Mapper:
         """One fused update with a frame that already lives in HBM: uint8 [h, w, 3].  Rows are used in
         place when their stride is a multiple of 4 bytes (16 for the bulk-copy fast path).  `roi` is an
         optional uint8 [h, w] keypoint-hull mask on the device."""
+        # lean path: a dense uint8 [h, w, 3] device tensor whose rows can be used in place
+        if (roi is None and type(frame) is torch.Tensor and frame.is_cuda and frame.dtype == torch.uint8 and frame.dim() == 3
+                and frame.shape[2] == 3 and frame.is_contiguous() and (frame.shape[1] * 3) % 4 == 0 and frame.data_ptr() % 4 == 0):
+            self._launch_raw(frame.data_ptr(), int(frame.shape[0]), int(frame.shape[1]), int(frame.shape[1]) * 3, H, frame.device)
+            return
         self._update_any(frame, H, roi)
+
+    def _launch_raw(self, ptr: int, h: int, w: int, pitch: int, H, device) -> None:
+        Hm = H if (isinstance(H, np.ndarray) and H.dtype == np.float64 and H.shape == (3, 3) and H.flags.c_contiguous) else \
+            np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
+        ca = self._cargs
+        if ca is None:
+            ca = self._cargs = (self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
+                                self._wacc.data_ptr() if self._wacc is not None else None,
+                                self._wacc.stride(0) * 4 if self._wacc is not None else 0, self._height, self._width)
+        region = self._region_buf
+        ramp = self._ramp if self._ramp is not None else 0.1 * min(h, w)
+        rc = self._lib.mk_mapper_update(*ca, ptr, h, w, pitch, None, 0, Hm.__array_interface__["data"][0], self._alpha, self._interp,
+                                        self._blend, float(ramp), region, _raw_stream(device))
+        if rc:
+            _lib.check(rc)
+        self.last_region = (region[0], region[1], region[2], region[3])
 
     def _slot_buffer(self, slot: dict, key: str, h: int, row: int) -> torch.Tensor:
         pitch = _round_up(row, 128)

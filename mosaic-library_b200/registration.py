@@ -40,6 +40,14 @@ def _cuda_device(device=None) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
 
+def _raw_stream(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on `device` (the private fast accessor when this torch has it)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:                        # pragma: no cover - older / newer torch without the accessor
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 def _bad_input(msg: str):
     if _cv2 is not None:
         return _cv2.error(msg)
@@ -93,6 +101,31 @@ class DescriptorSets:
 
     def __len__(self):
         return len(self.sizes)
+
+
+class PendingDeviceMatch:
+    """Handle of one Matcher.knn_match_device_async call: the kernels run on the matcher's own stream."""
+
+    __slots__ = ("_outs", "_lib", "_event", "_own", "_device", "_keepalive")
+
+    def __init__(self, outs, lib, event, own_stream, device, keepalive):
+        self._outs, self._lib, self._event, self._own, self._device, self._keepalive = outs, lib, event, own_stream, device, keepalive
+
+    def result(self):
+        """-> (idx, dist, keep, n_keep) device tensors; the CURRENT stream is made to wait for the matching kernels (no host
+        synchronisation), so anything queued afterwards may read them."""
+        if self._event is not None:
+            self._lib.mk_stream_follow(self._event, _lib.STREAM_NONE, _raw_stream(self._device))   # join: current stream waits
+            self._event = self._keepalive = None
+        return self._outs
+
+    def __del__(self):
+        if self._event is not None and self._outs is not None:   # dropped without joining: keep the allocator from recycling early
+            try:
+                for t in self._outs:
+                    t.record_stream(self._own)
+            except Exception:
+                pass
 
 
 class PendingMatch:
@@ -166,8 +199,39 @@ class Matcher:
         return ws
 
     # -- device-side entry points --------------------------------------------------------------
-    def knn_match_device(self, query, train, ratio: float = 0.7):
+    def knn_match_device(self, query, train, ratio: float = 0.7, _stream: int | None = None):
         """-> (idx int32 [nq,2], dist float32 [nq,2], keep uint8 [nq], n_keep int32 [1]) on the device."""
+        # lean path for what a frame loop passes: two well-formed device tensors (about a third of the host time of the
+        # general path below, which matters once the kernels take ~20 us)
+        if (type(query) is torch.Tensor and type(train) is torch.Tensor and query.is_cuda and train.is_cuda
+                and query.dtype == train.dtype and query.dim() == 2 and train.dim() == 2 and query.is_contiguous()
+                and train.is_contiguous() and query.shape[1] == train.shape[1] and query.shape[0] > 0
+                and (query.shape[1] * query.element_size()) % 16 == 0 and query.dtype in (torch.uint8, torch.float32)
+                and query.device == train.device):
+            device = query.device
+            nq, dim = query.shape
+            nt = train.shape[0]
+            fp = self._matcher.setdefault("fast", {})
+            key = (query.dtype, dim, nq, nt, device)
+            ent = fp.get(key)
+            L = self._matcher["lib"]
+            if ent is None:
+                code = _norm_code(self._norm, np.uint8 if query.dtype == torch.uint8 else np.float32, self._engine)
+                ent = fp[key] = (code, int(L.mk_knn2_workspace_bytes(code, nq, nt, dim)), dim * query.element_size())
+                if len(fp) > 256:
+                    fp.clear(); fp[key] = ent
+            code, ws_bytes, stride = ent
+            ws = self._workspace(ws_bytes, device, "workspace" if _stream is None else "workspace_own_stream")
+            idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
+            dist = torch.empty((nq, 2), dtype=torch.float32, device=device)
+            keep = torch.empty((nq,), dtype=torch.uint8, device=device)
+            n_keep = torch.empty((1,), dtype=torch.int32, device=device)
+            rc = L.mk_knn2(code, query.data_ptr(), nq, train.data_ptr() if nt else None, nt, dim, stride, idx.data_ptr(), dist.data_ptr(),
+                           float(ratio), keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(), ws.numel(),
+                           _raw_stream(device) if _stream is None else _stream)
+            if rc:
+                _lib.check(rc)
+            return idx, dist, keep, n_keep
         device = _cuda_device(self._device)
         q, dim = upload_descriptors(query, device)
         t, dim_t = upload_descriptors(train, device)
@@ -184,13 +248,33 @@ class Matcher:
             return idx, dist, keep, torch.zeros((1,), dtype=torch.int32, device=device)
         n_keep = torch.empty((1,), dtype=torch.int32, device=device)   # the library zeroes it on the stream
         L = self._matcher["lib"]
-        ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device)
+        ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace" if _stream is None else "workspace_own_stream")
         stride = q.stride(0) * q.element_size()
         assert stride == t.stride(0) * t.element_size()
         _lib.check(L.mk_knn2(code, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, dim, stride,
                              idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), n_keep.data_ptr(),
-                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream if _stream is None else _stream))
         return idx, dist, keep, n_keep
+
+    def knn_match_device_async(self, query: torch.Tensor, train: torch.Tensor, ratio: float = 0.7) -> PendingDeviceMatch:
+        """knn_match_device on the matcher's OWN stream: the call orders that stream after the caller's current stream (so
+        the descriptors are ready), launches, and returns at once; handle.result() orders the caller's current stream after
+        the kernels and hands back the device tensors.  A frame loop writes
+            h = matcher.knn_match_device_async(desc_k1, desc_k); mapper.update_device(frame, H); idx, dist, keep, n = h.result()
+        and gets matching and compositing side by side without touching streams or events itself."""
+        device = query.device
+        L = self._matcher["lib"]
+        st = self._matcher.setdefault("dasync", {})
+        if st.get("device") != device:
+            st.clear()
+            st.update(device=device, stream=torch.cuda.Stream(device=device), ev=[L.mk_event_create() for _ in range(16)], pos=0)
+            st["sptr"] = st["stream"].cuda_stream
+        k = st["pos"] = (st["pos"] + 2) % 16
+        ev_in, ev_out = st["ev"][k], st["ev"][k + 1]
+        L.mk_stream_follow(ev_in, _raw_stream(device), st["sptr"])      # own stream after whatever produced the descriptors
+        outs = self.knn_match_device(query, train, ratio, _stream=st["sptr"])
+        L.mk_stream_follow(ev_out, st["sptr"], _lib.STREAM_NONE)        # completion of THIS call, joined in result()
+        return PendingDeviceMatch(outs, L, ev_out, st["stream"], device, (query, train))
 
     def knn_match_arrays(self, query, train, ratio: float = 0.7):
         """-> (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) as numpy arrays.

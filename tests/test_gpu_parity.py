@@ -151,6 +151,25 @@ def test_knn_match_arrays_async_ring():
     assert e[0].shape == (0, 2) and e[2].shape == (0,)
 
 
+def test_knn_match_device_async_own_stream():
+    """The matcher's own-stream form: same tensors as the blocking device call, usable from the caller's stream after
+    result(); several calls in flight, descriptors produced on the caller's stream right before the call."""
+    rng = np.random.default_rng(6)
+    m = mb.Matcher(norm="hamming")
+    dev = torch.device("cuda:0")
+    hs, want = [], []
+    for k in range(10):
+        qh = rng.integers(0, 256, (900 + 16 * k, 32), dtype=np.uint8); th = rng.integers(0, 256, (1100, 32), dtype=np.uint8)
+        q = torch.from_numpy(qh).to(dev, non_blocking=True); t = torch.from_numpy(th).to(dev, non_blocking=True)
+        q = q ^ 0                                   # a kernel on the caller's stream produces the final descriptors
+        hs.append(m.knn_match_device_async(q, t, 0.7)); want.append(orc.knn2(qh, th, "hamming"))
+    for h, (oi, od) in zip(hs, want):
+        idx, dist, keep, n_keep = h.result()
+        total = (idx.sum() + keep.sum()).item()     # consumer kernels on the caller's stream
+        assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+        assert int(n_keep.item()) == int(np.count_nonzero(orc.ratio_test(oi, od, 0.7))) and total == total
+
+
 def test_tensor_core_path_is_the_one_that_runs():
     """SIFT-sized L2 problems go through the tcgen05 GEMM: the call launches prep + the TC kernel (+ the guarded
     SIMT kernel for float rows) and the result is still bit-exact; small problems stay on the SIMT kernels."""
