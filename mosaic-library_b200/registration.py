@@ -191,6 +191,15 @@ class Matcher:
         self.__dict__.update(state)
         self._matcher = self._create_matcher()
 
+    def __del__(self):
+        try:                                  # events of knn_match_device_async belong to the library
+            st = self._matcher.get("dasync")
+            if st:
+                for e in st.pop("ev", ()):
+                    self._matcher["lib"].mk_event_destroy(e)
+        except Exception:
+            pass
+
     def _workspace(self, nbytes: int, device, key: str = "workspace") -> torch.Tensor:
         ws = self._matcher.get(key)
         if ws is None or ws.numel() < nbytes or ws.device != device:
