@@ -363,11 +363,11 @@ def run_b200(args):
             print(f"[e2e trace] {name}: {(time.perf_counter() - t0) / K * 1e6:.0f} us/frame", file=sys.stderr)
     # the host link needs its own warm-up: every freshly page-locked buffer (and fresh staging buffer) runs at about half speed
     # for its first few dozen copies on this box (tools/pin_probe2.py: 146 -> 132 -> 120 us per 6.2 MB frame) and nothing
-    # before this point has moved data over PCIe.  Warm up in chunks until two consecutive chunks agree within 5 %.
+    # before this point has moved data over PCIe.  Warm up in chunks of 32 frames: at least 7, then until two consecutive chunks agree within 2 %.
     chunk, prev = min(32, W + K), None
-    for _ in range(16):
+    for it in range(24):
         cur_s = timed(lambda: e2e_loop(0, chunk)) / chunk
-        if prev is not None and abs(cur_s - prev) < 0.05 * prev:
+        if it >= 6 and prev is not None and abs(cur_s - prev) < 0.02 * prev:
             break
         prev = cur_s
     e2e_s = float(np.median([timed(lambda: e2e_loop(W, K)) for _ in range(3)]))     # median of three passes of K frames
