@@ -172,6 +172,17 @@ void *mk_event_create(void);
 void mk_event_destroy(void *event);
 int mk_stream_follow(void *event, void *src_stream, void *dst_stream);
 
+/* Spatial partition of the GPU for the two halves of a frame step.  Matching (one CTA per SM, 180 KB of shared memory) and
+ * compositing (5 small CTAs per SM) cannot share an SM, so on two ordinary streams the later kernel mostly waits for the
+ * earlier one; with a green context each (CUDA driver API, sm_90+) they run side by side from the first microsecond.
+ * mk_sm_partition_create splits the SMs of the current device into a first group of at least `min_sms_first` SMs (rounded up
+ * by the driver, multiples of 8) and the rest, and returns one non-blocking stream in each; work launched on those streams
+ * stays inside its group.  mk_knn2 sizes its grid for the SM count of the stream it is given.  Returns MK_ERR_CUDA when the
+ * driver cannot provide green contexts (callers then just use ordinary streams). */
+int mk_sm_partition_create(int min_sms_first, void **partition, void **stream_first, void **stream_rest, int *sms_first,
+                           int *sms_rest);
+void mk_sm_partition_destroy(void *partition);
+
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */
 int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,

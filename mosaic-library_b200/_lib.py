@@ -24,7 +24,7 @@ EXPORTS = (
     "mk_abi_version", "mk_version_string", "mk_last_error", "mk_launch_count",
     "mk_knn2_workspace_bytes", "mk_knn2_uses_tensor_cores", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
-    "mk_event_create", "mk_event_destroy", "mk_stream_follow",
+    "mk_event_create", "mk_event_destroy", "mk_stream_follow", "mk_sm_partition_create", "mk_sm_partition_destroy",
 )
 
 
@@ -85,6 +85,10 @@ def lib() -> C.CDLL:
     L.mk_event_destroy.argtypes = [vp]
     L.mk_stream_follow.restype = i32
     L.mk_stream_follow.argtypes = [vp, vp, vp]
+    L.mk_sm_partition_create.restype = i32
+    L.mk_sm_partition_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
+    L.mk_sm_partition_destroy.restype = None
+    L.mk_sm_partition_destroy.argtypes = [vp]
     L.mk_mapper_footprint.restype = i32
     L.mk_mapper_footprint.argtypes = [i32, i32, i32, i32, vp, i32, vp]
     if L.mk_abi_version() != 1:

@@ -1,6 +1,8 @@
 // mk_api.cu -- version, error reporting and launch accounting of libmosaic_b200.
 #include "mk_common.cuh"
 
+#include <cuda.h>
+
 #include <stdarg.h>
 
 namespace mk {
@@ -66,3 +68,128 @@ extern "C" int mk_stream_follow(void *event, void *src_stream, void *dst_stream)
     if (dst_stream != MK_STREAM_NONE) MK_CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(dst_stream), static_cast<cudaEvent_t>(event), 0));
     return MK_OK;
 }
+
+// The driver API is reached through cudaGetDriverEntryPoint only: the library must load (and export its symbols) on
+// machines without libcuda.so.1, e.g. the CPU-only build check.
+namespace {
+template <class Fn>
+Fn driver_fn(const char *name)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<Fn>(p);
+}
+struct DriverApi {
+    CUresult (*CtxGetDevice)(CUdevice *) = nullptr;
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+    CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+    CUresult (*GreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+    CUresult (*GreenCtxGetDevResource)(CUgreenCtx, CUdevResource *, CUdevResourceType) = nullptr;
+    CUresult (*StreamGetGreenCtx)(CUstream, CUgreenCtx *) = nullptr;
+    CUresult (*StreamDestroy)(CUstream) = nullptr;
+    bool ok = false;
+};
+const DriverApi &driver()
+{
+    static const DriverApi api = [] {
+        DriverApi d;
+        d.CtxGetDevice = driver_fn<decltype(d.CtxGetDevice)>("cuCtxGetDevice");
+        d.DeviceGetDevResource = driver_fn<decltype(d.DeviceGetDevResource)>("cuDeviceGetDevResource");
+        d.DevSmResourceSplitByCount = driver_fn<decltype(d.DevSmResourceSplitByCount)>("cuDevSmResourceSplitByCount");
+        d.DevResourceGenerateDesc = driver_fn<decltype(d.DevResourceGenerateDesc)>("cuDevResourceGenerateDesc");
+        d.GreenCtxCreate = driver_fn<decltype(d.GreenCtxCreate)>("cuGreenCtxCreate");
+        d.GreenCtxDestroy = driver_fn<decltype(d.GreenCtxDestroy)>("cuGreenCtxDestroy");
+        d.GreenCtxStreamCreate = driver_fn<decltype(d.GreenCtxStreamCreate)>("cuGreenCtxStreamCreate");
+        d.GreenCtxGetDevResource = driver_fn<decltype(d.GreenCtxGetDevResource)>("cuGreenCtxGetDevResource");
+        d.StreamGetGreenCtx = driver_fn<decltype(d.StreamGetGreenCtx)>("cuStreamGetGreenCtx");
+        d.StreamDestroy = driver_fn<decltype(d.StreamDestroy)>("cuStreamDestroy");
+        d.ok = d.CtxGetDevice && d.DeviceGetDevResource && d.DevSmResourceSplitByCount && d.DevResourceGenerateDesc && d.GreenCtxCreate &&
+               d.GreenCtxDestroy && d.GreenCtxStreamCreate && d.GreenCtxGetDevResource && d.StreamGetGreenCtx && d.StreamDestroy;
+        return d;
+    }();
+    return api;
+}
+struct SmPartition {
+    CUgreenCtx ctx[2] = { nullptr, nullptr };
+    CUstream stream[2] = { nullptr, nullptr };
+};
+}  // namespace
+
+extern "C" int mk_sm_partition_create(int min_sms_first, void **partition, void **stream_first, void **stream_rest, int *sms_first,
+                                      int *sms_rest)
+{
+    if (!partition || !stream_first || !stream_rest || min_sms_first <= 0) { mk::set_error("mk_sm_partition_create: bad argument"); return MK_ERR_ARG; }
+    cudaFree(nullptr);                                   // make sure the primary context exists and is current
+    const DriverApi &D = driver();
+    if (!D.ok) { mk::set_error("mk_sm_partition_create: this driver has no green contexts"); return MK_ERR_CUDA; }
+    CUdevice dev;
+    CUdevResource all, first, rest;
+    unsigned int groups = 1;
+#define MK_CU_TRY(expr)                                                                                    \
+    do {                                                                                                   \
+        CUresult r_ = (expr);                                                                              \
+        if (r_ != CUDA_SUCCESS) {                                                                          \
+            mk::set_error("%s: driver error %d", #expr, (int)r_);                                          \
+            if (P) mk_sm_partition_destroy(P);                                                             \
+            return MK_ERR_CUDA;                                                                            \
+        }                                                                                                  \
+    } while (0)
+    SmPartition *P = nullptr;
+    MK_CU_TRY(D.CtxGetDevice(&dev));
+    MK_CU_TRY(D.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    MK_CU_TRY(D.DevSmResourceSplitByCount(&first, &groups, &all, &rest, 0, (unsigned int)min_sms_first));
+    if (groups < 1 || rest.sm.smCount == 0) { mk::set_error("mk_sm_partition_create: cannot split %u SMs at %d", all.sm.smCount, min_sms_first); return MK_ERR_ARG; }
+    P = new SmPartition();
+    CUdevResource parts[2] = { first, rest };
+    for (int i = 0; i < 2; ++i) {
+        CUdevResourceDesc desc;
+        MK_CU_TRY(D.DevResourceGenerateDesc(&desc, &parts[i], 1));
+        MK_CU_TRY(D.GreenCtxCreate(&P->ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+        MK_CU_TRY(D.GreenCtxStreamCreate(&P->stream[i], P->ctx[i], CU_STREAM_NON_BLOCKING, 0));
+    }
+#undef MK_CU_TRY
+    *partition = P;
+    *stream_first = P->stream[0];
+    *stream_rest = P->stream[1];
+    if (sms_first) *sms_first = (int)first.sm.smCount;
+    if (sms_rest) *sms_rest = (int)rest.sm.smCount;
+    return MK_OK;
+}
+
+extern "C" void mk_sm_partition_destroy(void *partition)
+{
+    SmPartition *P = static_cast<SmPartition *>(partition);
+    if (!P) return;
+    for (int i = 0; i < 2; ++i) {
+        if (P->stream[i]) driver().StreamDestroy(P->stream[i]);
+        if (P->ctx[i]) driver().GreenCtxDestroy(P->ctx[i]);
+    }
+    delete P;
+}
+
+namespace mk {
+// SMs available to work launched on `stream`: the size of its green-context partition, or the whole device.
+int stream_sm_count(cudaStream_t stream)
+{
+    static thread_local cudaStream_t last_stream = reinterpret_cast<cudaStream_t>(~(uintptr_t)0);
+    static thread_local int last_count = 0;
+    if (stream == last_stream && last_count > 0) return last_count;
+    int count = 0;
+    CUgreenCtx g = nullptr;
+    if (stream && driver().ok && driver().StreamGetGreenCtx(reinterpret_cast<CUstream>(stream), &g) == CUDA_SUCCESS && g) {
+        CUdevResource res;
+        if (driver().GreenCtxGetDevResource(g, &res, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS) count = (int)res.sm.smCount;
+    }
+    if (count <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    last_stream = stream; last_count = count;
+    return count;
+}
+}  // namespace mk

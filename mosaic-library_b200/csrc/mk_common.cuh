@@ -40,6 +40,9 @@ inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_
 // cv::warpPerspective inverts H unless WARP_INVERSE_MAP is set (mosaic.py:114 does not set it).
 bool invert3x3(const double *S, double *D);
 
+// SMs available to work launched on `stream` (its green-context partition, mk_sm_partition_create, or the whole device)
+int stream_sm_count(cudaStream_t stream);
+
 // Tensor-core kNN flags, written on the DEVICE (prep pass + TC kernel) and read by the guarded SIMT fallback:
 //   flags[0] != 0  some value is not an integer in [0,255]: bf16 operands would round it, the TC kernel does nothing;
 //   flags[3] != 0  some row's best-two squared distance reached 2^22: the TC path ranks by the integer d^2, which equals

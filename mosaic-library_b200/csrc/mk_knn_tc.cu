@@ -692,7 +692,7 @@ struct TcPlan {
 };
 
 // rows_q / rows_t: rows of the bf16 copies (batched: both = all rows of all sets and the copies are shared)
-static TcPlan tc_plan(int norm, int npairs, int max_nq, int max_nt, int dim, long rows_q, long rows_t, bool shared)
+static TcPlan tc_plan(int norm, int npairs, int max_nq, int max_nt, int dim, long rows_q, long rows_t, bool shared, int sms = 148)
 {
     TcPlan pl;
     if (norm == MK_NORM_HAMMING_TC) { pl.esz = 1; pl.kp = dim * 8 <= 128 ? 128 : 256; }   // one e4m3 byte per descriptor bit
@@ -707,7 +707,7 @@ static TcPlan tc_plan(int norm, int npairs, int max_nq, int max_nt, int dim, lon
         const int per = (ntiles + s - 1) / s;
         const int s_eff = (ntiles + per - 1) / per;
         const long ctas = (long)npairs * pl.nqb * s_eff;
-        const long waves = (ctas + 147) / 148;
+        const long waves = (ctas + sms - 1) / sms;
         const double cost = (double)waves * (per + 4.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = s_eff; }
     }
@@ -747,7 +747,10 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out)
 {
     const bool batched = pairs != nullptr;
-    const TcPlan pl = batched ? tc_plan(norm, npairs, nq, nt, dim, total_rows, total_rows, true) : tc_plan(norm, 1, nq, nt, dim, nq, nt, false);
+    const int sms = stream_sm_count(st);     // splits (hence the partial-result scratch) never exceed what 148 SMs ask for
+    TcPlan pl = batched ? tc_plan(norm, npairs, nq, nt, dim, total_rows, total_rows, true, sms) : tc_plan(norm, 1, nq, nt, dim, nq, nt, false, sms);
+    if (pl.total > workspace_bytes)          // the workspace was sized for the whole device: that plan always fits
+        pl = batched ? tc_plan(norm, npairs, nq, nt, dim, total_rows, total_rows, true) : tc_plan(norm, 1, nq, nt, dim, nq, nt, false);
     if (workspace_bytes < pl.total) { set_error("mk_knn2: workspace too small for the tensor-core path (%zu < %zu)", workspace_bytes, pl.total); return MK_ERR_WORKSPACE; }
     uint8_t *ws = static_cast<uint8_t *>(workspace);
     if (!aligned(ws, 256)) { set_error("mk_knn2: workspace must be 256-byte aligned for the tensor-core path"); return MK_ERR_ALIGN; }

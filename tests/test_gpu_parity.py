@@ -170,6 +170,30 @@ def test_knn_match_device_async_own_stream():
         assert int(n_keep.item()) == int(np.count_nonzero(orc.ratio_test(oi, od, 0.7))) and total == total
 
 
+def test_sm_partition_streams_give_the_same_results():
+    """Green-context partition (mk_sm_partition_create): matching in a 40-SM group (the kernel sizes its grid for the
+    group), compositing in the rest, results identical to the ordinary-stream path."""
+    rng = np.random.default_rng(8)
+    part = mb.SmPartition(40)
+    assert part.sms_first >= 40 and part.sms_rest > 0 and part.sms_first + part.sms_rest <= 148
+    q = rng.integers(0, 256, (3000, 32), dtype=np.uint8); t = rng.integers(0, 256, (3100, 32), dtype=np.uint8)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    img = torch.from_numpy(rng.integers(1, 256, (300, 400, 3), dtype=np.uint8)).cuda()
+    H = np.array([[0.98, -0.17, 210.3], [0.17, 0.98, 95.7], [0.0, 0.0, 1.0]])
+    m, mp_a, mp_b = mb.Matcher(norm="hamming"), mb.Mapper(1024, 768, interp="linear"), mb.Mapper(1024, 768, interp="linear")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(part.first):
+        idx, dist, keep, _ = m.knn_match_device(qd, td, 0.7)
+    with torch.cuda.stream(part.rest):
+        mp_a.update_device(img, H)
+    torch.cuda.synchronize()
+    mp_b.update_device(img, H)
+    oi, od = orc.knn2(q, t, "hamming")
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    assert np.array_equal(mp_a.output, mp_b.output) and np.array_equal(mp_a.mask, mp_b.mask)
+    part.close()
+
+
 def test_tensor_core_path_is_the_one_that_runs():
     """SIFT-sized L2 problems go through the tcgen05 GEMM: the call launches prep + the TC kernel (+ the guarded
     SIMT kernel for float rows) and the result is still bit-exact; small problems stay on the SIMT kernels."""
