@@ -203,6 +203,13 @@ def run_b200(args):
 
     s_match = torch.cuda.Stream(device=dev)     # matching and compositing of a frame are independent: two streams
     main = torch.cuda.current_stream(dev)
+    s_comp, partition = None, None
+    if args.sm_partition > 0 and not multi:      # optional: green-context SM groups for the two halves of the step
+        try:
+            partition = mb.SmPartition(args.sm_partition, dev)
+            s_match, s_comp = partition.first, partition.rest
+        except Exception as ex:                  # driver without green contexts: ordinary streams
+            print(f"[bench] SM partition unavailable ({ex}); using ordinary streams", file=sys.stderr)
 
     def one_step(k, mp, ev=None, last=False):
         """ev = [start, match done, compositing done, step done] recorded on the streams that run the work."""
@@ -213,6 +220,11 @@ def run_b200(args):
             if ev: ev[1].record(s_match)
         if multi:
             mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # frame exchange of step k+1 posted under step k
+        elif s_comp is not None:
+            s_comp.wait_stream(main)
+            with torch.cuda.stream(s_comp):
+                mp.update_device(frames[k], Hs[k])
+            main.wait_stream(s_comp)
         else:
             mp.update_device(frames[k], Hs[k])
         if ev: ev[2].record(main)
@@ -407,7 +419,8 @@ def run_b200(args):
             (f"BASELINE configs[1] per GPU, tile-sharded as in configs[3]: {grid[0]}x{grid[1]} tiles of 16384^2 over {world} GPUs, one 1920x1080 "
              "frame stream per rank, frames routed by warped footprint (NCCL send/recv), poses all-gathered once, 5000x32B Hamming kNN per frame"),
             "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events); inputs {nframes * fh * fw * 3 / 1e9:.2f} GB > L2",
-            "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching runs on its own stream next to compositing",
+            "timing": ("sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching runs on its own stream next to compositing"
+                       + (f"; SM groups {partition.sms_first} (matching) + {partition.sms_rest} (compositing), green contexts" if partition else "")),
             "blend": "alpha", "interp": "linear", "canvas": [grid[0] * CANVAS, grid[1] * CANVAS], "frame": [fw, fh],
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -696,6 +709,8 @@ def main():
     ap.add_argument("--black", type=float, default=0.0, help="fraction of pure-black world pixels (exercises any(!=0))")
     ap.add_argument("--hamming-engine", default="auto", choices=["auto", "popc", "tensor"],
                     help="auto/tensor: tcgen05 fp8 GEMM on bit-expanded rows when large enough (bit-identical); popc: XOR+POPC kernel")
+    ap.add_argument("--sm-partition", type=int, default=40,
+                    help="give matching its own group of at least this many SMs (green contexts) and compositing the rest; 0 = two ordinary streams")
     ap.add_argument("--no-feather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
