@@ -308,10 +308,14 @@ def run_b200(args):
         mapper = factory(CANVAS, CANVAS)
 
     # ---------------- end to end through the reference-facing API, host buffers ----------------
-    pin_frames = [torch.empty((fh, fw, 3), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    # page-locked host inputs out of a huge-page backed, CUDA-registered region (mosaicking_b200.pinned_empty): buffers from
+    # pin_memory() are made of 4 KB pages and cycled through the copy engine at 16-45 GB/s on some hosts (tools/pin_probe3.py)
+    pin_frames = [torch.from_numpy(mb.pinned_empty((fh, fw, 3))) for _ in range(4)]
     for i, pf in enumerate(pin_frames):
         pf.copy_(frames[i].cpu())
-    pin_desc = [torch.from_numpy(desc_h[k]).pin_memory() for k in range(min(nframes + 1, 8))]
+    pin_desc = [torch.from_numpy(mb.pinned_empty((NDESC, 32))) for _ in range(min(nframes + 1, 8))]
+    for k, pd in enumerate(pin_desc):
+        pd.copy_(torch.from_numpy(desc_h[k]))
     e2e_mapper = mapper if not multi else None
 
     def e2e_inputs(k):
@@ -381,20 +385,37 @@ def run_b200(args):
     # the host link needs its own warm-up: every freshly page-locked buffer (and fresh staging buffer) runs at about half speed
     # for its first few dozen copies on this box (tools/pin_probe2.py: 146 -> 132 -> 120 us per 6.2 MB frame) and nothing
     # before this point has moved data over PCIe.  Warm up in chunks of 32 frames: at least 7, then until two consecutive chunks agree within 2 %.
+    # (1) plain frame-sized copies until the link rate is stable: on some hosts the I/O path needs up to seconds of traffic
+    #     before it reaches its rate (observed: 2.4 k -> 3.3 k frames/s creeping up over 500 frames, other boxes 6.4 k at once)
+    link_windows = []
+    if not multi or True:
+        wd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
+        t_begin = time.perf_counter()
+        while time.perf_counter() - t_begin < 4.0:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for k in range(200):
+                wd.copy_(pin_frames[k % len(pin_frames)], non_blocking=True)
+            torch.cuda.synchronize()
+            link_windows.append(200 * wd.numel() / (time.perf_counter() - t0) / 1e9)
+            if len(link_windows) >= 3 and max(link_windows[-3:]) - min(link_windows[-3:]) < 0.015 * link_windows[-1]:
+                break
+        del wd
+    # (2) the loop itself, in chunks of 32 frames: at least 7, then until two consecutive chunks agree within 2 %
     chunk, prev = min(32, W + K), None
     for it in range(24):
         cur_s = timed(lambda: e2e_loop(0, chunk)) / chunk
         if it >= 6 and prev is not None and abs(cur_s - prev) < 0.02 * prev:
             break
         prev = cur_s
-    e2e_s = float(np.median([timed(lambda: e2e_loop(W, K)) for _ in range(3)]))     # median of three passes of K frames
+    e2e_passes = [timed(lambda: e2e_loop(W, K)) for _ in range(5)]     # five passes of K frames, the median counts
+    e2e_s = float(np.median(e2e_passes))
     for k in range(W):
         e2e_sync_step(k)
     e2e_sync_s = float(np.median([timed(lambda: [e2e_sync_step(W + k) for k in range(K)]) for _ in range(3)]))
     h2d = fh * fw * 3 + 2 * NDESC * 32
     d2h = NDESC * (2 * 4 + 2 * 4 + 1)
     # what the host link delivers for the same kind of copy (page-locked -> device, frame-sized), for the e2e number's context
-    probe_h = torch.empty(fh * fw * 3, dtype=torch.uint8).pin_memory()
+    probe_h = torch.from_numpy(mb.pinned_empty((fh * fw * 3,)))
     probe_d = torch.empty(fh * fw * 3, dtype=torch.uint8, device=dev)
     for _ in range(3):
         probe_d.copy_(probe_h, non_blocking=True)
@@ -406,9 +427,11 @@ def run_b200(args):
     link_gbs = 20 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
     e2e = {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
-                    "while frame k is in flight; wall clock incl. Python, median of 3 passes of K frames; untimed frames first until the PCIe path is warm"),
+                    "while frame k is in flight; wall clock incl. Python, median of 5 passes of K frames; untimed frames first until the PCIe path is warm"),
            "host_link": {"h2d_gbs_achieved": (world * K / e2e_s) * h2d / 1e9 / world, "h2d_gbs_plain_copy": link_gbs,
                          "note": "per GPU; plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
+           "passes_frames_per_s": [round(world * K / t) for t in e2e_passes],
+           "link_warmup_gbs": [round(x, 1) for x in link_windows],
            "sync_value": world * K / e2e_sync_s,
            "sync_note": "same calls with Matcher.knn_match_arrays (host waits for every frame's matches before the next frame)"}
 

@@ -29,8 +29,9 @@ from .mosaic import (Mapper, assign_frames_to_tiles, bbox_overlap, combine_tiles
                      get_corners, get_mosaic_dimensions, homogeneous_translation, warp_perspective)
 from .registration import CompositeMatcher, DMatch, Matcher, get_matches  # noqa: E402
 from .partition import SmPartition  # noqa: E402
+from .hostmem import pinned_empty  # noqa: E402
 
 __all__ = ["HAS_B200", "MosaicB200Error", "build", "launch_count", "Mapper", "Matcher", "CompositeMatcher", "DMatch",
            "get_matches", "get_corners", "get_mosaic_dimensions", "find_nice_homographies", "bbox_overlap",
            "assign_frames_to_tiles", "combine_tiles", "homogeneous_translation", "warp_perspective", "mosaic",
-           "registration", "SmPartition"]
+           "registration", "SmPartition", "pinned_empty"]

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .hostmem import pinned_empty
 
 try:  # cv2 is only used for the DMatch value type the reference API returns
     import cv2 as _cv2
@@ -333,7 +334,7 @@ class Matcher:
             qd = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
             td = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
             out = torch.empty(total_cap, dtype=torch.uint8, device=device)
-        ring = [{"host": torch.empty(total_cap, dtype=torch.uint8).pin_memory(), "event": torch.cuda.Event(), "owner": None}
+        ring = [{"host": torch.from_numpy(pinned_empty((total_cap,))), "event": torch.cuda.Event(), "owner": None}
                 for _ in range(PendingMatch.DEPTH)]
         for slot in ring:
             slot["host_ptr"] = slot["host"].data_ptr()
