@@ -170,6 +170,24 @@ def test_knn_match_device_async_own_stream():
         assert int(n_keep.item()) == int(np.count_nonzero(orc.ratio_test(oi, od, 0.7))) and total == total
 
 
+def test_pinned_empty_arrays_feed_the_host_paths():
+    """Huge-page backed, CUDA-registered host arrays (mosaicking_b200.pinned_empty) through Mapper.update and the matcher's
+    host path: same results as ordinary numpy arrays, and torch recognises the memory as page-locked."""
+    rng = np.random.default_rng(9)
+    img = mb.pinned_empty((180, 240, 3)); img[...] = rng.integers(0, 256, img.shape, dtype=np.uint8)
+    q = mb.pinned_empty((700, 32)); q[...] = rng.integers(0, 256, q.shape, dtype=np.uint8)
+    t = mb.pinned_empty((900, 32)); t[...] = rng.integers(0, 256, t.shape, dtype=np.uint8)
+    f32 = mb.pinned_empty((50, 128), np.float32); f32[...] = 1.5
+    assert torch.from_numpy(img).is_pinned() and f32.dtype == np.float32 and f32.flags.c_contiguous
+    H = np.array([[0.97, -0.2, 150.0], [0.2, 0.97, 90.0], [1e-5, 0.0, 1.0]])
+    a, b = mb.Mapper(640, 480, interp="linear"), mb.Mapper(640, 480, interp="linear")
+    a.update(img, H); b.update(img.copy(), H)
+    assert np.array_equal(a.output, b.output)
+    idx, dist, keep = mb.Matcher(norm="hamming").knn_match_arrays_async(q, t, 0.7).result()
+    oi, od = orc.knn2(np.array(q), np.array(t), "hamming")
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od) and np.array_equal(keep, orc.ratio_test(oi, od, 0.7))
+
+
 def test_sm_partition_streams_give_the_same_results():
     """Green-context partition (mk_sm_partition_create): matching in a 40-SM group (the kernel sizes its grid for the
     group), compositing in the rest, results identical to the ordinary-stream path."""
