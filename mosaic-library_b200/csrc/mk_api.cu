@@ -117,6 +117,7 @@ struct SmPartition {
     CUgreenCtx ctx[2] = { nullptr, nullptr };
     CUstream stream[2] = { nullptr, nullptr };
 };
+std::atomic<unsigned> g_partition_epoch{0};   // bumped whenever a partition dies: a recycled stream handle must not hit the cache
 }  // namespace
 
 extern "C" int mk_sm_partition_create(int min_sms_first, void **partition, void **stream_first, void **stream_rest, int *sms_first,
@@ -168,6 +169,7 @@ extern "C" void mk_sm_partition_destroy(void *partition)
         if (P->stream[i]) driver().StreamDestroy(P->stream[i]);
         if (P->ctx[i]) driver().GreenCtxDestroy(P->ctx[i]);
     }
+    g_partition_epoch.fetch_add(1, std::memory_order_release);
     delete P;
 }
 
@@ -175,21 +177,23 @@ namespace mk {
 // SMs available to work launched on `stream`: the size of its green-context partition, or the whole device.
 int stream_sm_count(cudaStream_t stream)
 {
+    // one-entry cache keyed by (stream handle, current device, partition epoch): a handle can be recycled after
+    // mk_sm_partition_destroy, and the NULL stream means a different device after cudaSetDevice
     static thread_local cudaStream_t last_stream = reinterpret_cast<cudaStream_t>(~(uintptr_t)0);
-    static thread_local int last_count = 0;
-    if (stream == last_stream && last_count > 0) return last_count;
+    static thread_local int last_count = 0, last_dev = -1;
+    static thread_local unsigned last_epoch = 0;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const unsigned epoch = g_partition_epoch.load(std::memory_order_acquire);
+    if (stream == last_stream && cur_dev == last_dev && epoch == last_epoch && last_count > 0) return last_count;
     int count = 0;
     CUgreenCtx g = nullptr;
     if (stream && driver().ok && driver().StreamGetGreenCtx(reinterpret_cast<CUstream>(stream), &g) == CUDA_SUCCESS && g) {
         CUdevResource res;
         if (driver().GreenCtxGetDevResource(g, &res, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS) count = (int)res.sm.smCount;
     }
-    if (count <= 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    last_stream = stream; last_count = count;
+    if (count <= 0) cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, cur_dev);
+    last_stream = stream; last_count = count; last_dev = cur_dev; last_epoch = epoch;
     return count;
 }
 }  // namespace mk

@@ -43,7 +43,18 @@ struct KnnParams {
     int32_t *n_keep;
     double ratio;
     const int *guard;   // if non-null the kernel only runs when the tensor-core path did not produce the result
+    const int32_t *tc_count;  // guarded runs: the tensor-core kernel's survivor counts, published to n_keep only if its result stands
 };
+
+// Guarded SIMT pass (float32 rows that went through the tensor-core kernel first).  The TC kernel counted its survivors
+// into a scratch counter, never into n_keep: if its result stands, one thread per pair publishes that count and the pass
+// is over; otherwise n_keep is still zero and this pass counts the survivors of the recomputed call itself.
+__device__ __forceinline__ bool knn_guard_skip(const KnnParams &p)
+{
+    if (!p.guard || !knn_tc_result_ok(p.guard)) return false;
+    if (p.tc_count && p.n_keep && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.n_keep[blockIdx.z] = p.tc_count[blockIdx.z];
+    return true;
+}
 
 // tensor-core path (mk_knn_tc.cu)
 size_t knn_tc_workspace_bytes(int norm, int nq, int nt, int dim);
@@ -51,7 +62,8 @@ size_t knn_tc_batched_workspace_bytes(int norm, int npairs, int max_nq, int max_
 bool knn_tc_supported(int norm, int nq, int nt, int dim);
 int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
                const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
-               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out);
+               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out,
+               const int32_t **tc_count_out);
 
 struct Problem {
     const uint8_t *q, *t;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_reg_kernel(const __grid_cons
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int z = blockIdx.z, qblk = blockIdx.x;
-    if (p.guard && knn_tc_result_ok(p.guard)) return;
+    if (knn_guard_skip(p)) return;
     const Problem pr = load_problem(p, z);
     if (qblk * QB >= pr.nq) return;
     const int qi = qblk * QB + lane;
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn2_f32_kernel(const __grid_cons
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int z = blockIdx.z, qblk = blockIdx.x;
-    if (p.guard && knn_tc_result_ok(p.guard)) return;
+    if (knn_guard_skip(p)) return;
     const Problem pr = load_problem(p, z);
     if (qblk * FT >= pr.nq) return;
     const int q0 = qblk * FT;
@@ -468,10 +480,14 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
     dim3 grid(pl.nqb, pl.splits, npairs);
     if (norm == MK_NORM_L2_F32) {
         const size_t smem = (size_t)2 * FT * P.dim * sizeof(float);
-        static std::atomic<size_t> configured{0};
-        if (smem > 48 * 1024 && configured.load() < smem) {
-            MK_CUDA_TRY(cudaFuncSetAttribute(knn2_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * FT * 256 * sizeof(float))));
-            configured.store(2 * FT * 256 * sizeof(float));
+        static std::atomic<int> configured{-1};   // device the attribute was last set on (cudaFuncSetAttribute is per device)
+        if (smem > 48 * 1024) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (configured.load(std::memory_order_acquire) != dev) {
+                MK_CUDA_TRY(cudaFuncSetAttribute(knn2_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * FT * 256 * sizeof(float))));
+                configured.store(dev, std::memory_order_release);
+            }
         }
         knn2_f32_kernel<<<grid, KNN_THREADS, smem, st>>>(P);
     } else {
@@ -553,11 +569,12 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
         const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
+        const int32_t *tc_count = nullptr;
         rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, nullptr, nullptr, 1, nullptr, 0, idx, dist, ratio, keep, n_keep,
-                        static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags);
+                        static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags, &tc_count);
         // uint8 rows: dim*255^2 < 2^22, bit counts <= 256: the TC result always stands
         if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
-        P.guard = flags;
+        P.guard = flags; P.tc_count = tc_count;
         return run_knn(bn, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
     }
     return run_knn(bn, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -587,11 +604,12 @@ extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int d
         const size_t simt_bytes = ((pl.ticket_bytes + pl.part_bytes) + 255) & ~(size_t)255;
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2_batched: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
+        const int32_t *tc_count = nullptr;
         rc = knn_tc_run(norm, desc, max_nq, nullptr, max_nt, dim, row_stride, set_off, pairs, npairs, out_off, total_rows, idx, dist,
                         ratio, keep, n_keep, static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes,
-                        (cudaStream_t)stream, &flags);
+                        (cudaStream_t)stream, &flags, &tc_count);
         if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
-        P.guard = flags;
+        P.guard = flags; P.tc_count = tc_count;
         return run_knn(bn, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
     }
     return run_knn(bn, P, npairs, max_nq, max_nt, workspace, workspace_bytes, (cudaStream_t)stream);

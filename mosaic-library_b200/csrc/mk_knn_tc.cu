@@ -688,7 +688,7 @@ static int make_map(CUtensorMap *map, const void *base, int rows, int kp, int bo
 
 struct TcPlan {
     int kp, esz, nqb, splits;
-    size_t off_qb, off_tb, off_qn, off_tn, off_flags, off_tickets, off_part, total;
+    size_t off_qb, off_tb, off_qn, off_tn, off_flags, off_tickets, off_cnt, off_part, total;
 };
 
 // rows_q / rows_t: rows of the bf16 copies (batched: both = all rows of all sets and the copies are shared)
@@ -721,6 +721,7 @@ static TcPlan tc_plan(int norm, int npairs, int max_nq, int max_nt, int dim, lon
     pl.off_flags = take(256);
     const size_t blocks = (size_t)(npairs > 0 ? npairs : 1) * (pl.nqb > 0 ? pl.nqb : 1);
     pl.off_tickets = take(blocks * 4);
+    pl.off_cnt = take((size_t)(npairs > 0 ? npairs : 1) * 4);   // float rows: survivor counts of the TC kernel (zeroed with the tickets)
     pl.off_part = take(pl.splits > 1 ? blocks * pl.splits * TC_M * 2 * 8 : 0);
     pl.total = o;
     return pl;
@@ -744,7 +745,8 @@ bool knn_tc_supported(int norm, int nq, int nt, int dim)
 // set_off / pairs / out_off are the device tables of mk_knn2_batched.  *flags_out lets the caller guard the SIMT fallback.
 int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
                const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
-               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out)
+               uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out,
+               const int32_t **tc_count_out)
 {
     const bool batched = pairs != nullptr;
     const int sms = stream_sm_count(st);     // splits (hence the partial-result scratch) never exceed what 148 SMs ask for
@@ -759,7 +761,9 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     int *flags = reinterpret_cast<int *>(ws + pl.off_flags), *tickets = reinterpret_cast<int *>(ws + pl.off_tickets);
     const int np = batched ? npairs : 1;
     // flags and tickets are adjacent in the workspace: one memset (the Hamming prep kernel, which sets no flag, zeroes them itself)
-    const size_t zero_bytes = (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4;
+    // float rows may be recomputed by the guarded SIMT kernel: the TC kernel then counts survivors into `cnt`, not n_keep
+    int32_t *cnt = (norm == MK_NORM_L2_F32 && n_keep) ? reinterpret_cast<int32_t *>(ws + pl.off_cnt) : nullptr;
+    const size_t zero_bytes = cnt ? (pl.off_cnt - pl.off_flags) + (size_t)np * 4 : (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4;
     if (norm != MK_NORM_HAMMING_TC) MK_CUDA_TRY(cudaMemsetAsync(flags, 0, zero_bytes, st));
     if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
     const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
@@ -787,7 +791,7 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     P.splits = pl.splits; P.nqb = pl.nqb;
     P.set_off = set_off; P.pairs = pairs; P.out_off = out_off;
     P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
-    P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = n_keep; P.ratio = ratio;
+    P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = cnt ? cnt : n_keep; P.ratio = ratio;
     static std::atomic<int> configured{-1};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -810,6 +814,7 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P));
     MK_LAUNCH_CHECK("knn2_tc_kernel");
     *flags_out = flags;
+    if (tc_count_out) *tc_count_out = cnt;
     return MK_OK;
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .registration import _cuda_device, _raw_stream
+from .registration import _cuda_device, _current_device, _raw_stream
 
 try:
     import cv2 as _cv2
@@ -58,10 +58,16 @@ class Mapper:
     keep the reference's signature.  Extra keyword-only knobs:
       interp   "cubic" (what the reference hard-codes, mosaic.py:114) or "linear" (north-star kernel)
       blend    "alpha" (reference semantics) or "feather" (SURVEY.md A.4b extension)
+      async_upload  False (default): update() returns once a HOST image has been consumed (its host-to-device copy is
+               complete), like the reference's synchronous update() -- the caller may overwrite the array at once.
+               True: the copy of a page-locked array stays in flight after update() returns (it overlaps the previous
+               frame's kernel).  The array is kept alive by the Mapper, `last_upload` is an event that completes when the
+               copy has read it, and the host never runs more than len(ring) = 3 uploads ahead: a page-locked buffer may
+               be refilled after `last_upload.synchronize()` or once update() has been called three more times.
     """
 
     def __init__(self, output_width: int, output_height: int, alpha_blend: float = 0.5, *, interp="cubic",
-                 blend: str = "alpha", feather_ramp: float | None = None, device=None):
+                 blend: str = "alpha", feather_ramp: float | None = None, device=None, async_upload: bool = False):
         assert 0.0 <= alpha_blend <= 1.0, "Alpha blend must in interval [0, 1]."
         self._alpha = float(alpha_blend)
         self._interp = INTERP[interp]
@@ -76,8 +82,10 @@ class Mapper:
         self._copy_stream = torch.cuda.Stream(device=self._device)
         self._copy_sptr = self._copy_stream.cuda_stream
         self._cargs = None          # cached canvas / mask / weight pointers and pitches (they only change on release)
-        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
+        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None, "host": None} for _ in range(3)]
         self._slot = 0
+        self._async_upload = bool(async_upload)
+        self.last_upload = None     # event: the most recent host image has been read by its host-to-device copy
         self._region_buf = (ctypes.c_int32 * 4)()
         self._flag = True
         self.last_region = (0, 0, 0, 0)
@@ -145,8 +153,9 @@ class Mapper:
                                 self._wacc.stride(0) * 4 if self._wacc is not None else 0, self._height, self._width)
         region = self._region_buf
         ramp = self._ramp if self._ramp is not None else 0.1 * min(h, w)
-        rc = self._lib.mk_mapper_update(*ca, ptr, h, w, pitch, None, 0, Hm.__array_interface__["data"][0], self._alpha, self._interp,
-                                        self._blend, float(ramp), region, _raw_stream(device))
+        with _current_device(self._device):
+            rc = self._lib.mk_mapper_update(*ca, ptr, h, w, pitch, None, 0, Hm.__array_interface__["data"][0], self._alpha, self._interp,
+                                            self._blend, float(ramp), region, _raw_stream(device))
         if rc:
             _lib.check(rc)
         self.last_region = (region[0], region[1], region[2], region[3])
@@ -183,6 +192,8 @@ class Mapper:
         if slot["free"] is None:
             slot["free"], slot["ready"] = torch.cuda.Event(), torch.cuda.Event()
         else:
+            if host_np and self._async_upload:
+                slot["ready"].synchronize()      # bounds the host's run-ahead to the ring depth (see async_upload)
             cs.wait_event(slot["free"])          # the kernel that last read this slot has finished
         rbuf = None
         if host_np:
@@ -204,6 +215,12 @@ class Mapper:
         cur.wait_event(slot["ready"])
         self._launch(buf, h, w, rbuf, H, cur)
         slot["free"].record(cur)
+        if host_np:
+            if self._async_upload:
+                slot["host"] = (image, roi)      # keep the source arrays alive while the DMA may still read them
+                self.last_upload = slot["ready"]
+            else:
+                slot["ready"].synchronize()      # the reference consumes the image before update() returns
 
     def _launch(self, buf, h, w, rbuf, H, cur=None) -> None:
         Hm = H if (isinstance(H, np.ndarray) and H.dtype == np.float64 and H.shape == (3, 3) and H.flags.c_contiguous) else \
@@ -217,10 +234,11 @@ class Mapper:
                                 self._wacc.stride(0) * 4 if self._wacc is not None else 0, self._height, self._width)
         if cur is None:
             cur = torch.cuda.current_stream(self._device)
-        rc = self._lib.mk_mapper_update(
-            *ca, buf.data_ptr(), h, w, buf.stride(0),
-            rbuf.data_ptr() if rbuf is not None else None, rbuf.stride(0) if rbuf is not None else 0,
-            Hm.__array_interface__["data"][0], self._alpha, self._interp, self._blend, float(ramp), region, cur.cuda_stream)
+        with _current_device(self._device):
+            rc = self._lib.mk_mapper_update(
+                *ca, buf.data_ptr(), h, w, buf.stride(0),
+                rbuf.data_ptr() if rbuf is not None else None, rbuf.stride(0) if rbuf is not None else 0,
+                Hm.__array_interface__["data"][0], self._alpha, self._interp, self._blend, float(ramp), region, cur.cuda_stream)
         if rc:
             _lib.check(rc)
         self.last_region = (region[0], region[1], region[2], region[3])
@@ -249,11 +267,12 @@ class Mapper:
             ptrs[k], hs[k], ws[k], pitches[k] = t2.data_ptr(), h, w, t2.stride(0)
         Hm = np.ascontiguousarray(np.stack([np.asarray(H, np.float64).reshape(3, 3) for H in Hs]))
         ramp = self._ramp if self._ramp is not None else 0.1 * min(int(hs[0]), int(ws[0]))
-        _lib.check(self._lib.mk_mapper_update_batch(
-            self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
-            self._wacc.data_ptr() if self._wacc is not None else None, self._wacc.stride(0) * 4 if self._wacc is not None else 0,
-            self._height, self._width, n, ptrs, hs, ws, pitches, Hm.ctypes.data, self._alpha, self._interp, self._blend, float(ramp),
-            torch.cuda.current_stream(self._device).cuda_stream))
+        with _current_device(self._device):
+            _lib.check(self._lib.mk_mapper_update_batch(
+                self._canvas.data_ptr(), self._canvas.stride(0), self._canvas_mask.data_ptr(), self._canvas_mask.stride(0),
+                self._wacc.data_ptr() if self._wacc is not None else None, self._wacc.stride(0) * 4 if self._wacc is not None else 0,
+                self._height, self._width, n, ptrs, hs, ws, pitches, Hm.ctypes.data, self._alpha, self._interp, self._blend, float(ramp),
+                torch.cuda.current_stream(self._device).cuda_stream))
         self._batch_keepalive = keep      # the launch is asynchronous: keep the staged frames alive until the next call
 
     def update(self, image, H: np.ndarray, stream=None, keypoints=None):
@@ -270,7 +289,8 @@ class Mapper:
     def release(self):
         self._canvas = self._canvas_mask = self._wacc = None
         self._cargs = None
-        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None} for _ in range(3)]
+        self._slots = [{"buf": None, "roi": None, "free": None, "ready": None, "host": None} for _ in range(3)]
+        self.last_upload = None
 
     @property
     def output(self) -> np.ndarray:
@@ -313,8 +333,9 @@ def warp_perspective(image, H: np.ndarray, dsize: tuple[int, int], interp="linea
     dpitch = _round_up(Wd * cn, 128)
     dst = torch.empty((Hd, dpitch), dtype=torch.uint8, device=device)
     Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
-    _lib.check(_lib.lib().mk_warp_perspective_u8(src.data_ptr(), h, w, cn, pitch, Hm.ctypes.data, dst.data_ptr(), Hd, Wd,
-                                                 dpitch, INTERP[interp], torch.cuda.current_stream(device).cuda_stream))
+    with _current_device(device):
+        _lib.check(_lib.lib().mk_warp_perspective_u8(src.data_ptr(), h, w, cn, pitch, Hm.ctypes.data, dst.data_ptr(), Hd, Wd,
+                                                     dpitch, INTERP[interp], torch.cuda.current_stream(device).cuda_stream))
     out = dst[:, : Wd * cn]
     return out.reshape(Hd, Wd) if cn == 1 else out.reshape(Hd, Wd, cn)
 

@@ -104,20 +104,59 @@ class DescriptorSets:
         return len(self.sizes)
 
 
+class _EventPool:
+    """The library events of Matcher.knn_match_device_async.  Pending handles hold a reference, so the events are destroyed
+    only after the matcher AND every unjoined handle are gone."""
+
+    def __init__(self, lib, n: int):
+        self.lib, self.ev = lib, [lib.mk_event_create() for _ in range(n)]
+
+    def __del__(self):
+        try:
+            for e in self.ev:
+                self.lib.mk_event_destroy(e)
+        except Exception:
+            pass
+
+
+class _current_device:
+    """`with _current_device(dev):` -- make `dev` the current CUDA device for the C-ABI calls inside (the library allocates
+    its tables and sets kernel attributes on the current device); free when it already is."""
+
+    __slots__ = ("_idx", "_prev")
+
+    def __init__(self, device):
+        self._idx = device.index if isinstance(device, torch.device) else int(device)
+
+    def __enter__(self):
+        self._prev = None
+        if self._idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self._idx:
+                self._prev = cur
+                torch.cuda.set_device(self._idx)
+
+    def __exit__(self, *exc):
+        if self._prev is not None:
+            torch.cuda.set_device(self._prev)
+        return False
+
+
 class PendingDeviceMatch:
     """Handle of one Matcher.knn_match_device_async call: the kernels run on the matcher's own stream."""
 
-    __slots__ = ("_outs", "_lib", "_event", "_own", "_device", "_keepalive")
+    __slots__ = ("_outs", "_lib", "_event", "_own", "_device", "_keepalive", "_pool")
 
-    def __init__(self, outs, lib, event, own_stream, device, keepalive):
+    def __init__(self, outs, lib, event, own_stream, device, keepalive, pool=None):
         self._outs, self._lib, self._event, self._own, self._device, self._keepalive = outs, lib, event, own_stream, device, keepalive
+        self._pool = pool            # keeps the library events alive while this handle may still join on one
 
     def result(self):
         """-> (idx, dist, keep, n_keep) device tensors; the CURRENT stream is made to wait for the matching kernels (no host
         synchronisation), so anything queued afterwards may read them."""
         if self._event is not None:
             self._lib.mk_stream_follow(self._event, _lib.STREAM_NONE, _raw_stream(self._device))   # join: current stream waits
-            self._event = self._keepalive = None
+            self._event = self._keepalive = self._pool = None
         return self._outs
 
     def __del__(self):
@@ -192,24 +231,22 @@ class Matcher:
         self.__dict__.update(state)
         self._matcher = self._create_matcher()
 
-    def __del__(self):
-        try:                                  # events of knn_match_device_async belong to the library
-            st = self._matcher.get("dasync")
-            if st:
-                for e in st.pop("ev", ()):
-                    self._matcher["lib"].mk_event_destroy(e)
-        except Exception:
-            pass
-
-    def _workspace(self, nbytes: int, device, key: str = "workspace") -> torch.Tensor:
+    def _workspace(self, nbytes: int, device, key: str = "workspace", stream=None) -> torch.Tensor:
+        """Growable scratch.  `stream`: the torch stream the scratch is USED on when that is not the current one -- the block
+        is then allocated from that stream's pool, so that replacing it cannot hand memory a kernel on the private stream
+        still uses to a later allocation of the caller's stream."""
         ws = self._matcher.get(key)
         if ws is None or ws.numel() < nbytes or ws.device != device:
-            ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+            if stream is not None:
+                with torch.cuda.stream(stream):
+                    ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+            else:
+                ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
             self._matcher[key] = ws
         return ws
 
     # -- device-side entry points --------------------------------------------------------------
-    def knn_match_device(self, query, train, ratio: float = 0.7, _stream: int | None = None):
+    def knn_match_device(self, query, train, ratio: float = 0.7, _stream: int | None = None, _tstream=None):
         """-> (idx int32 [nq,2], dist float32 [nq,2], keep uint8 [nq], n_keep int32 [1]) on the device."""
         # lean path for what a frame loop passes: two well-formed device tensors (about a third of the host time of the
         # general path below, which matters once the kernels take ~20 us)
@@ -231,14 +268,15 @@ class Matcher:
                 if len(fp) > 256:
                     fp.clear(); fp[key] = ent
             code, ws_bytes, stride = ent
-            ws = self._workspace(ws_bytes, device, "workspace" if _stream is None else "workspace_own_stream")
+            ws = self._workspace(ws_bytes, device, "workspace" if _stream is None else "workspace_own_stream", _tstream)
             idx = torch.empty((nq, 2), dtype=torch.int32, device=device)
             dist = torch.empty((nq, 2), dtype=torch.float32, device=device)
             keep = torch.empty((nq,), dtype=torch.uint8, device=device)
             n_keep = torch.empty((1,), dtype=torch.int32, device=device)
-            rc = L.mk_knn2(code, query.data_ptr(), nq, train.data_ptr() if nt else None, nt, dim, stride, idx.data_ptr(), dist.data_ptr(),
-                           float(ratio), keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(), ws.numel(),
-                           _raw_stream(device) if _stream is None else _stream)
+            with _current_device(device):
+                rc = L.mk_knn2(code, query.data_ptr(), nq, train.data_ptr() if nt else None, nt, dim, stride, idx.data_ptr(), dist.data_ptr(),
+                               float(ratio), keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(), ws.numel(),
+                               _raw_stream(device) if _stream is None else _stream)
             if rc:
                 _lib.check(rc)
             return idx, dist, keep, n_keep
@@ -258,12 +296,13 @@ class Matcher:
             return idx, dist, keep, torch.zeros((1,), dtype=torch.int32, device=device)
         n_keep = torch.empty((1,), dtype=torch.int32, device=device)   # the library zeroes it on the stream
         L = self._matcher["lib"]
-        ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace" if _stream is None else "workspace_own_stream")
+        ws = self._workspace(L.mk_knn2_workspace_bytes(code, nq, nt, dim), device, "workspace" if _stream is None else "workspace_own_stream", _tstream)
         stride = q.stride(0) * q.element_size()
         assert stride == t.stride(0) * t.element_size()
-        _lib.check(L.mk_knn2(code, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, dim, stride,
-                             idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), n_keep.data_ptr(),
-                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream if _stream is None else _stream))
+        with _current_device(device):
+            _lib.check(L.mk_knn2(code, q.data_ptr(), nq, t.data_ptr() if nt else None, nt, dim, stride,
+                                 idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(), n_keep.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream if _stream is None else _stream))
         return idx, dist, keep, n_keep
 
     def knn_match_device_async(self, query: torch.Tensor, train: torch.Tensor, ratio: float = 0.7) -> PendingDeviceMatch:
@@ -277,14 +316,16 @@ class Matcher:
         st = self._matcher.setdefault("dasync", {})
         if st.get("device") != device:
             st.clear()
-            st.update(device=device, stream=torch.cuda.Stream(device=device), ev=[L.mk_event_create() for _ in range(16)], pos=0)
+            with _current_device(device):
+                st.update(device=device, stream=torch.cuda.Stream(device=device), pool=_EventPool(L, 16), pos=0)
             st["sptr"] = st["stream"].cuda_stream
         k = st["pos"] = (st["pos"] + 2) % 16
-        ev_in, ev_out = st["ev"][k], st["ev"][k + 1]
+        pool = st["pool"]
+        ev_in, ev_out = pool.ev[k], pool.ev[k + 1]
         L.mk_stream_follow(ev_in, _raw_stream(device), st["sptr"])      # own stream after whatever produced the descriptors
-        outs = self.knn_match_device(query, train, ratio, _stream=st["sptr"])
+        outs = self.knn_match_device(query, train, ratio, _stream=st["sptr"], _tstream=st["stream"])
         L.mk_stream_follow(ev_out, st["sptr"], _lib.STREAM_NONE)        # completion of THIS call, joined in result()
-        return PendingDeviceMatch(outs, L, ev_out, st["stream"], device, (query, train))
+        return PendingDeviceMatch(outs, L, ev_out, st["stream"], device, (query, train), pool)
 
     def knn_match_arrays(self, query, train, ratio: float = 0.7):
         """-> (idx [nq,2] int32, dist [nq,2] float32, keep [nq] bool) as numpy arrays.
@@ -382,12 +423,13 @@ class Matcher:
         if slot["owner"] is not None:
             slot["owner"]._resolve()             # an uncollected older call still points at this slot
         base = hp["out_ptr"]
-        _lib.check(L.mk_upload_2d(hp["q_ptr"], stride, q.__array_interface__["data"][0], row, row, nq, sptr))
-        if nt:
-            _lib.check(L.mk_upload_2d(hp["t_ptr"], stride, t.__array_interface__["data"][0], row, row, nt, sptr))
-        _lib.check(L.mk_knn2(code, hp["q_ptr"], nq, hp["t_ptr"] if nt else None, nt, dim, stride, base, base + nq * 8,
-                             float(ratio), base + off_keep, base + off_n, ws[0], ws[1], sptr))
-        _lib.check(L.mk_download_2d(slot["host_ptr"], total, base, total, total, 1, sptr))
+        with _current_device(hp["device"]):
+            _lib.check(L.mk_upload_2d(hp["q_ptr"], stride, q.__array_interface__["data"][0], row, row, nq, sptr))
+            if nt:
+                _lib.check(L.mk_upload_2d(hp["t_ptr"], stride, t.__array_interface__["data"][0], row, row, nt, sptr))
+            _lib.check(L.mk_knn2(code, hp["q_ptr"], nq, hp["t_ptr"] if nt else None, nt, dim, stride, base, base + nq * 8,
+                                 float(ratio), base + off_keep, base + off_n, ws[0], ws[1], sptr))
+            _lib.check(L.mk_download_2d(slot["host_ptr"], total, base, total, total, 1, sptr))
         slot["event"].record(hp["stream"])
         pending = PendingMatch(slot, nq, off_keep, (q, t))
         slot["owner"] = pending
@@ -443,11 +485,12 @@ class Matcher:
             hi = min(len(pr), lo + CH)
             ws = self._workspace(L.mk_knn2_batched_workspace_bytes(code, hi - lo, max_nq, max_nt, dim, total), device)
             stride = desc.stride(0) * desc.element_size()
-            _lib.check(L.mk_knn2_batched(code, desc.data_ptr(), total, dim, stride, set_off.data_ptr(),
-                                         pairs_d.data_ptr() + lo * 8, hi - lo, out_off.data_ptr() + lo * 4, max_nq, max_nt,
-                                         idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(),
-                                         n_keep.data_ptr() + lo * 4 if n_keep is not None else None,
-                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
+            with _current_device(device):
+                _lib.check(L.mk_knn2_batched(code, desc.data_ptr(), total, dim, stride, set_off.data_ptr(),
+                                             pairs_d.data_ptr() + lo * 8, hi - lo, out_off.data_ptr() + lo * 4, max_nq, max_nt,
+                                             idx.data_ptr(), dist.data_ptr(), float(ratio), keep.data_ptr(),
+                                             n_keep.data_ptr() + lo * 4 if n_keep is not None else None,
+                                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream(device).cuda_stream))
         if output == "counts":
             return n_keep.cpu().numpy()
         if output == "device":
