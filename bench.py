@@ -9,12 +9,16 @@ frame's descriptors against the previous frame's, then one fused warp + blend up
 
 N = 1  : BASELINE configs[1] -- 1920x1080 synthetic sequence with known homography drift, ORB-like
          5000 x 32 B descriptors (Hamming), 16384 x 16384 canvas.  Blend = Mapper alpha semantics
-         (the reference's own, parity-checked bit for bit); the feather extension is timed too and
-         reported under "feather".
-N > 1  : the same per-GPU workload, tile-sharded like BASELINE configs[3]: the canvas is a grid of
-         16384 x 16384 tiles owned by the ranks (mosaic.py:595-622 tiling), every rank ingests its own
-         1920x1080 frame stream over its own tile, frames whose warped footprint crosses a seam are also
-         sent to the neighbour (NCCL send/recv), all poses are all-gathered once.  Weak scaling.
+         (the reference's own, parity-checked bit for bit).  The same line carries a full second record
+         for BASELINE configs[2] (3840x2160 + SIFT-8000 under L2 on the tcgen05 GEMM): value, e2e with
+         host buffers, CPU sample, rooflines.
+N > 1  : the SAME per-GPU step (so the driver's N=1 -> N efficiency is like for like), composited into
+         BASELINE configs[3]'s canvas: 65536 x 65536 as a 4 x 4 grid of 16384^2 tiles (mosaic.py:595-622)
+         owned round-robin by the ranks.  Every rank flies its lane of the frame sequence along the seam
+         between a tile it owns and a tile another rank owns: every second frame straddles the seam and is
+         routed to the neighbour by warped footprint (ncclSend/Recv over NVLink), whatever --steps is.  All
+         poses are all-gathered once.  `config3` in the same line is the literal configs[3] measurement
+         (4K frames): weak (one lane per rank) and strong (a fixed 64-frame set) scaling.
 
 value  : frames/s with inputs resident in HBM, per-step CUDA events, L2 flushed between steps.
 e2e    : frames/s through the reference-facing API (Matcher.knn_match_arrays + Mapper.update) with
@@ -40,6 +44,7 @@ CANVAS = 16384
 NDESC = 5000
 RATIO = 0.7
 ALPHA = 0.5
+BIG_GRID = (4, 4)            # configs[3]: 65536 x 65536 canvas = 4 x 4 tiles of 16384^2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -56,6 +61,19 @@ def trajectory(k: int, w: int, h: int, canvas: int, origin=(0.0, 0.0)) -> np.nda
     th = 0.002 * k + 0.05 * np.sin(0.05 * k)
     c, s = np.cos(th), np.sin(th)
     return np.array([[c, -s, x + origin[0]], [s, c, y + origin[1]], [0.0, 0.0, 1.0]])
+
+
+def seam_lane(k: int, w: int, h: int, seam_x: float, y0: float, side: int = 1) -> np.ndarray:
+    """Lane of the frame sequence that runs down the vertical seam x = seam_x (95 % overlap between consecutive frames,
+    slow rotation drift): even frames are centred on the seam (their footprint straddles both tiles), odd frames lie
+    0.55 w away from it inside the own tile (to the left when the neighbour is on the right, side = +1), so half of the
+    frames are routed whatever the number of steps."""
+    th = 0.002 * k + 0.03 * np.sin(0.05 * k)
+    c, s = np.cos(th), np.sin(th)
+    cx = seam_x - side * (0.0 if k % 2 == 0 else 0.55 * w)
+    x = cx - 0.5 * w                      # frame origin: the warped frame is ~centred on cx
+    y = y0 + 0.05 * h * k
+    return np.array([[c, -s, x], [s, c, y], [0.0, 0.0, 1.0]])
 
 
 def make_world(torch, device, size: int, seed: int, black: float):
@@ -90,6 +108,24 @@ def make_descriptors(n_sets: int, seed: int) -> np.ndarray:
         redraw = rng.random(NDESC) < 0.2
         cur[redraw] = rng.integers(0, 256, (int(redraw.sum()), 32), dtype=np.uint8)
         sets[k] = cur[rng.permutation(NDESC)]
+    return sets
+
+
+def make_sift_like(n_sets: int, n: int, seed: int) -> np.ndarray:
+    """Integer-valued float32 descriptors in [0, 255] with norm ~512, like OpenCV SIFT's; consecutive sets share 70 % of
+    their rows up to small perturbations."""
+    rng = np.random.default_rng(seed)
+    def draw(m):
+        v = rng.gamma(0.6, 1.0, (m, 128)).astype(np.float32)
+        v *= 512.0 / np.linalg.norm(v, axis=1, keepdims=True)
+        return np.clip(np.rint(v), 0, 255).astype(np.float32)
+    sets = np.empty((n_sets, n, 128), np.float32)
+    sets[0] = draw(n)
+    for k in range(1, n_sets):
+        cur = np.clip(sets[k - 1] + rng.integers(-2, 3, (n, 128)), 0, 255).astype(np.float32)
+        redraw = rng.random(n) < 0.3
+        cur[redraw] = draw(int(redraw.sum()))
+        sets[k] = cur[rng.permutation(n)]
     return sets
 
 
@@ -130,6 +166,125 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def stats_us(ms) -> dict:
+    a = np.asarray(ms, np.float64) * 1e3
+    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max()), "n": int(a.size)}
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", 1390.8)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1390.8, "source": "fallback (B200_PROFILING.md)"}
+
+
+def popc_peak() -> tuple[float, str]:
+    """POPC.32 issue rate of the chip: measured by tools/ubench/pipes.cu when the result is committed, else 16 lanes/clk/SM."""
+    p = ROOT / "profiles" / "pipe_peaks.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if "popc32_per_s" in d:
+            return float(d["popc32_per_s"]), "measured (tools/ubench/pipes.cu, profiles/pipe_peaks.json)"
+    return 148 * 16 * 1.965e9, "assumed 16 lanes/clk/SM x 148 SMs x 1.965 GHz"
+
+
+class Iso:
+    """Kernel timed ALONE: CUDA events around one call on the stream it runs on, L2 flushed before every call, the call warmed
+    on that same stream first; the median counts (min / max are printed next to it)."""
+
+    def __init__(self, torch, flush):
+        self.torch, self.flush = torch, flush
+
+    def __call__(self, fns, warm: int = 3) -> np.ndarray:
+        torch = self.torch
+        for f in fns[:warm]:
+            f()
+        torch.cuda.synchronize()
+        out = []
+        for f in fns:
+            self.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); f(); e1.record()
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return np.asarray(out)
+
+    def back_to_back(self, fns, reps: int = 5) -> float:
+        """Average duration of one call when the calls are issued back to back (no flush in between; the caller makes
+        the working set of the group larger than L2): ms per call, median over `reps` groups."""
+        torch = self.torch
+        per = []
+        for _ in range(reps):
+            self.flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for f in fns:
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            per.append(e0.elapsed_time(e1) / len(fns))
+        return float(np.median(per))
+
+
+def traffic_of(kernel: str):
+    tp = ROOT / "profiles" / "traffic.json"     # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture
+    if tp.exists():
+        return json.loads(tp.read_text()).get(kernel)
+    return None
+
+
+def roofline_k4(nbytes: np.ndarray, iso_ms: np.ndarray, b2b_ms: float | None, kernel: str) -> dict:
+    """Fused warp+blend kernel against the HBM copy bandwidth.  Algorithmic bytes per launch =
+    src (w*h*3) + canvas read+write (2*3*A) + mask read+write (2*A) [+ 8*A weight plane in feather mode],
+    A = canvas rectangle visited.  `achieved` / `frac` use the MEDIAN duration of an isolated launch
+    (CUDA events around one launch, L2 cold -- includes the ~4-6 us an empty launch measures the same way);
+    *_back_to_back is the same launch in a train of launches over distinct frames (working set > L2, no flush)."""
+    pk = peaks()
+    med = float(np.median(iso_ms))
+    achieved = float(nbytes.mean() / (med * 1e-3) / 1e9)
+    out = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+           "frac": achieved / pk["hbm_gbs"], "traffic": traffic_of(kernel), "peak_source": pk["source"],
+           "algorithmic_bytes_per_launch": float(nbytes.mean()), "launch_us": med * 1e3, "launch_us_stats": stats_us(iso_ms)}
+    if b2b_ms:
+        a2 = float(nbytes.mean() / (b2b_ms * 1e-3) / 1e9)
+        out.update({"launch_us_back_to_back": b2b_ms * 1e3, "achieved_back_to_back": a2, "frac_back_to_back": a2 / pk["hbm_gbs"]})
+    return out
+
+
+def roofline_tmem(ms: np.ndarray, n: int = NDESC) -> dict:
+    """Hamming kNN through the tcgen05 fp8 GEMM (bit-expanded rows): with K = 256 the kernel is bound by reading the
+    accumulators back from tensor memory, one 32-bit TMEM column per candidate at 64 B/clk/SM (B300_MICROARCH.md, TMEM table;
+    tools/tc_tile_probe.py measures 0.98 us per 128x256 tile = 67 B/clk).  launch_us is the whole call: bit-expansion prep +
+    GEMM/top-2 kernel, median of isolated calls."""
+    peak = 148 * 64 * 1.965e9
+    med = float(np.median(ms))
+    achieved = n * n * 4 / (med * 1e-3)
+    return {"kernel": "mk::knn_tc_prep_bits_kernel + mk::knn2_tc_kernel<1>", "bound": "tmem-read", "achieved": achieved / 1e12,
+            "peak": peak / 1e12, "unit": "TB/s", "frac": achieved / peak, "launch_us": med * 1e3, "launch_us_stats": stats_us(ms)}
+
+
+def roofline_popc(ms: np.ndarray, n: int = NDESC) -> dict:
+    """Hamming kNN (XOR+POPC kernel) is bound by the integer POPC issue rate, not HBM (320 KB of data for 25 M pairs):
+    8 POPC.32 per 256-bit pair."""
+    peak, src = popc_peak()
+    med = float(np.median(ms))
+    achieved = n * n * 8 / (med * 1e-3)
+    return {"kernel": "mk::knn2_reg_kernel<Hamming<2>>", "bound": "int-popc", "achieved": achieved / 1e12, "peak": peak / 1e12,
+            "unit": "Tpopc32/s", "frac": achieved / peak, "peak_source": src, "launch_us": med * 1e3, "launch_us_stats": stats_us(ms)}
+
+
+def roofline_tensor(ms: np.ndarray, n: int, dim: int) -> dict:
+    """L2 kNN as a dense contraction: 2*Nq*Nt*D flops against the sustained cuBLAS bf16 rate of this pool's B200s."""
+    pk = peaks()
+    med = float(np.median(ms))
+    achieved = 2.0 * n * n * dim / (med * 1e-3) / 1e12
+    return {"kernel": "mk::knn_tc_prep_kernel + mk::knn2_tc_kernel<0>", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"], "peak_source": pk["source"] + " bf16_tflops_sustained",
+            "launch_us": med * 1e3, "launch_us_stats": stats_us(ms), "traffic": None}
+
+
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
@@ -149,341 +304,293 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    ctx = {"torch": torch, "dist": dist, "mb": mb, "world": world, "rank": rank, "local": local, "dev": dev, "args": args}
+    out = single_gpu(ctx) if world == 1 else multi_gpu(ctx)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def frames_along(torch, mb, dev, Hs_local, fw, fh, seed, black):
+    """Frames of a synthetic world seen along the poses Hs_local (frame -> world), resident in HBM."""
+    world_tex = make_world(torch, dev, CANVAS, seed, black)
+    frames = [mb.warp_perspective(world_tex, np.linalg.inv(H), (fw, fh), "linear", device=dev).contiguous() for H in Hs_local]
+    del world_tex
+    return frames
+
+
+def single_gpu(ctx) -> dict:
+    torch, mb, dev, args, local = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"], ctx["local"]
     K, W = args.steps, args.warmup
     nframes = K + W
-    multi = world > 1
-    fw, fh = 1920, 1080      # the same per-GPU workload at every N (weak scaling): BASELINE configs[1] frames
-    # ---------------- data (all resident in HBM before any timed region) ----------------
-    tile = (CANVAS, CANVAS)
-    if multi:
-        gx = {2: 2, 4: 2, 8: 4}.get(world, world)
-        grid = (gx, world // gx)
-        origin = ((rank % grid[0]) * CANVAS, (rank // grid[0]) * CANVAS)   # every rank flies over its own tile ...
-        # ... but starts near the seam so that a share of the frames is routed to the neighbour
-    else:
-        grid, origin = (1, 1), (0.0, 0.0)
-    world_tex = make_world(torch, dev, CANVAS, 7 + rank, args.black)
-    Hs = []
-    for k in range(nframes):
-        H = trajectory(k, fw, fh, CANVAS)
-        if multi:   # shift the path so that it straddles the seam to the right-hand / lower neighbour
-            H = H.copy(); H[0, 2] += origin[0] + 0.38 * CANVAS; H[1, 2] += origin[1]   # ~25 % of the frames straddle the seam
-            H[0, 2] = min(H[0, 2], grid[0] * CANVAS - 1.2 * fw)
-        Hs.append(H)
-    frames = []
-    for k in range(nframes):
-        Hl = trajectory(k, fw, fh, CANVAS)
-        frames.append(mb.warp_perspective(world_tex, np.linalg.inv(Hl), (fw, fh), "linear", device=dev).contiguous())
-    del world_tex
-    desc_h = make_descriptors(nframes + 1, 11 + rank)
+    fw, fh = 1920, 1080
+    Hs = [trajectory(k, fw, fh, CANVAS) for k in range(nframes)]
+    frames = frames_along(torch, mb, dev, Hs, fw, fh, 7, args.black)
+    desc_h = make_descriptors(nframes + 1, 11)
     desc_d = [torch.from_numpy(desc_h[k]).to(dev) for k in range(nframes + 1)]
     flush = torch.empty(args.flush_mb << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
+    iso = Iso(torch, flush)
 
     matcher = mb.Matcher(norm="hamming", device=dev, engine=args.hamming_engine)
     factory = lambda w_, h_, blend="alpha": mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", blend=blend, device=dev)  # noqa: E731
-    if multi:
-        from mosaicking_b200.distributed import ShardedMosaic
-        mosaic = ShardedMosaic(grid, tile, factory, (fh, fw), dev)
-        for t in mosaic.owned_tiles():
-            mosaic._mapper(t)
-        mosaic.connect()                 # create the NCCL p2p channels outside the timed region
-        mosaic.plan(np.stack(Hs))        # one all_gather of every pose, like the reference's tile graph
-        mapper = None
-    else:
-        mapper = factory(CANVAS, CANVAS)
-        mosaic = None
-
-    def barrier():
-        torch.cuda.synchronize()
-        if multi:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    s_match = torch.cuda.Stream(device=dev)     # matching and compositing of a frame are independent: two streams
+    mapper = factory(CANVAS, CANVAS)
     main = torch.cuda.current_stream(dev)
-    s_comp, partition = None, None
-    # green-context SM groups for the two halves of the step; measured at N = 2 the routed frames make compositing the longer
-    # half (1.25 launches per step on 108 SMs) and ordinary streams are 1.5 % faster there, so only N = 1 uses the groups
-    if args.sm_partition > 0 and not multi:
-        try:
-            partition = mb.SmPartition(args.sm_partition, dev)
-            s_match, s_comp = partition.first, partition.rest
-        except Exception as ex:                  # driver without green contexts: ordinary streams
-            print(f"[bench] SM partition unavailable ({ex}); using ordinary streams", file=sys.stderr)
 
-    def one_step(k, mp, ev=None, last=False):
-        """ev = [start, match done, compositing done, step done] recorded on the streams that run the work."""
-        if ev: ev[0].record(main)
-        s_match.wait_stream(main)
-        with torch.cuda.stream(s_match):
-            matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
-            if ev: ev[1].record(s_match)
-        def composite():
-            if multi:
-                mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # frame exchange of step k+1 posted under step k
+    def make_step(s_match, s_comp):
+        def one_step(k, mp, ev=None):
+            """ev = [start, match done, compositing done, step done] recorded on the streams that run the work."""
+            if ev: ev[0].record(main)
+            s_match.wait_stream(main)
+            with torch.cuda.stream(s_match):
+                matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
+                if ev: ev[1].record(s_match)
+            if s_comp is not None:
+                s_comp.wait_stream(main)
+                with torch.cuda.stream(s_comp):
+                    mp.update_device(frames[k], Hs[k])
+                main.wait_stream(s_comp)
             else:
                 mp.update_device(frames[k], Hs[k])
-        if s_comp is not None:
-            s_comp.wait_stream(main)
-            with torch.cuda.stream(s_comp):
-                composite()
-            main.wait_stream(s_comp)
-        else:
-            composite()
-        if ev: ev[2].record(main)
-        main.wait_stream(s_match)
-        if ev: ev[3].record(main)
+            if ev: ev[2].record(main)
+            main.wait_stream(s_match)
+            if ev: ev[3].record(main)
+        return one_step
 
-    # ---------------- device-resident throughput ("value") ----------------
-    def timed_pass(mp, collect_bytes, do_flush=True):
+    def timed_pass(one_step, mp):
         for k in range(W):
-            one_step(k, mp, last=(k == W - 1))
-        barrier()
+            one_step(k, mp)
+        torch.cuda.synchronize()
         clocks = ClockSampler(local)
         clocks.start()
         time.sleep(0.25)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
         n0 = mb.launch_count()
-        barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(K):
-            if do_flush:
-                flush.zero_()                   # evict L2 (126 MB) between steps, outside the timed events
-            one_step(W + k, mp, evs[k], last=(k == K - 1))
-        barrier()
+            flush.zero_()                   # evict L2 (126 MB) between steps, outside the timed events
+            one_step(W + k, mp, evs[k])
+        torch.cuda.synchronize()
         t1 = time.perf_counter()
         launches = mb.launch_count() - n0
         ck = clocks.stop(t0, t1)
         step_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
         match_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])      # both measured from the common start: they overlap
         blend_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
-        nbytes = None
-        if collect_bytes and not multi:
-            nbytes = np.array([mp.footprint_bytes(fh, fw, Hs[W + k]) for k in range(K)], np.float64)
-        return step_ms, match_ms, blend_ms, nbytes, launches, ck
+        return step_ms, match_ms, blend_ms, launches, ck
 
-    step_ms, match_ms, blend_ms, nbytes, launches, clocks = timed_pass(mapper, True)
-    overlapped = {"match": float(match_ms.mean()), "warp_blend": float(blend_ms.mean())}
-    def isolated_times(make_mapper, time_match=True):
-        """The two kernels of a step, each timed ALONE on the same inputs (L2 flushed before every launch): roofline inputs."""
-        iso_m, iso_b = [], []
-        mp_iso = make_mapper()
-        for k in range(W):
-            mp_iso.update_device(frames[k], Hs[k])
-        for k in range(K):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            if time_match:
-                flush.zero_()
-                e[0].record(); matcher.knn_match_device(desc_d[W + k + 1], desc_d[W + k], RATIO); e[1].record()
-            flush.zero_()
-            e[2].record(); mp_iso.update_device(frames[W + k], Hs[W + k]); e[3].record()
-            torch.cuda.synchronize()
-            iso_m.append(e[0].elapsed_time(e[1]) if time_match else 0.0); iso_b.append(e[2].elapsed_time(e[3]))
-        mp_iso.release()
-        return np.array(iso_m), np.array(iso_b)
+    # the headline uses two ordinary streams (the same policy as every N > 1 run); the green-context SM groups are a variant
+    step_plain = make_step(torch.cuda.Stream(device=dev), None)
+    step_ms, ov_match_ms, ov_blend_ms, launches, clocks = timed_pass(step_plain, mapper)
+    value = K / (float(step_ms.sum()) * 1e-3)
+    partition_variant = None
+    if args.sm_partition > 0:
+        try:
+            part = mb.SmPartition(args.sm_partition, dev)
+            p_step, _, _, _, _ = timed_pass(make_step(part.first, part.rest), mapper)
+            partition_variant = {"value": K / (float(p_step.sum()) * 1e-3), "ms_per_step": float(p_step.mean()),
+                                 "sms": [part.sms_first, part.sms_rest], "note": "matching / compositing in green-context SM groups"}
+            del part
+        except Exception as ex:                  # driver without green contexts
+            partition_variant = {"unavailable": str(ex)[:200]}
 
-    if not multi:
-        match_ms, blend_ms = isolated_times(lambda: factory(CANVAS, CANVAS))
-    total_ms = float(step_ms.sum())
-    if multi:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = world * K / (total_ms * 1e-3)
+    # ---- the two halves of a step, each alone (roofline inputs): median of isolated calls + back-to-back trains ----
+    nbytes = np.array([mapper.footprint_bytes(fh, fw, Hs[W + k]) for k in range(K)], np.float64)
+    mp_iso = factory(CANVAS, CANVAS)
+    for k in range(W):
+        mp_iso.update_device(frames[k], Hs[k])
+    blend_iso = iso([(lambda k=k: mp_iso.update_device(frames[W + k], Hs[W + k])) for k in range(K)])
+    nb2b = min(K, 32)             # 32 x 6.2 MB of distinct frames + their canvas windows > L2
+    blend_b2b = iso.back_to_back([(lambda k=k: mp_iso.update_device(frames[W + k], Hs[W + k])) for k in range(nb2b)]) if nb2b >= 8 else None
+    match_iso = iso([(lambda k=k: matcher.knn_match_device(desc_d[W + k + 1], desc_d[W + k], RATIO)) for k in range(K)])
+    mp_iso.release()
 
-    feather = None
-    if not multi and not args.no_feather:
+    out = {
+        "metric": "mosaic frames/s (kNN-2 match + fused warp+blend per frame)", "value": value, "unit": "frames/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": ("BASELINE configs[1]: 1920x1080 synthetic sequence, 5000x32B ORB-like descriptors (Hamming kNN k=2 + ratio 0.7, "
+                         f"engine={args.hamming_engine}), fused warp(INTER_LINEAR)+blend(alpha=0.5, reference Mapper semantics) into a 16384x16384 canvas"),
+            "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events); inputs {nframes * fh * fw * 3 / 1e9:.2f} GB > L2",
+            "timing": "sum of per-step CUDA-event durations (start -> both streams joined); matching runs on its own (ordinary) stream next to compositing",
+            "blend": "alpha", "interp": "linear", "canvas": [CANVAS, CANVAS], "frame": [fw, fh],
+        },
+        "gpu_launches": int(launches), "clocks": clocks,
+        "breakdown_us": {"match_alone": stats_us(match_iso), "warp_blend_alone": stats_us(blend_iso),
+                         "match_overlapped_mean": float(ov_match_ms.mean() * 1e3), "warp_blend_overlapped_mean": float(ov_blend_ms.mean() * 1e3)},
+        "match_pairs_per_s": NDESC * NDESC / (float(np.median(match_iso)) * 1e-3),
+        "roofline": roofline_k4(nbytes, blend_iso, blend_b2b, "mk::mapper_strip_kernel"),
+        "warp_blend_gpix_per_s": float(((nbytes - fh * fw * 3) / 8).mean() / (float(np.median(blend_iso)) * 1e-3) / 1e9),
+        "roofline_match": roofline_tmem(match_iso) if args.hamming_engine != "popc" else roofline_popc(match_iso),
+    }
+    if partition_variant:
+        out["sm_partition_variant"] = partition_variant
+
+    if not args.no_feather:
         mapper.release(); mapper = None
         torch.cuda.empty_cache()
         fm = factory(CANVAS, CANVAS, blend="feather")
-        f_step, _, _, _, _, _ = timed_pass(fm, False)
+        f_step, _, _, _, _ = timed_pass(step_plain, fm)
         fbytes = np.array([fm.footprint_bytes(fh, fw, Hs[W + k]) for k in range(K)], np.float64)
-        _, f_blend = isolated_times(lambda: factory(CANVAS, CANVAS, blend="feather"), time_match=False)
-        feather = {"value": K / (float(f_step.sum()) * 1e-3), "unit": "frames/s", "ms_per_step": float(f_step.mean()),
-                   "roofline": roofline(fbytes, f_blend), "oracle": "numpy/C restatement of SURVEY A.4b (extension, no reference code)"}
         fm.release()
+        fi = factory(CANVAS, CANVAS, blend="feather")
+        for k in range(W):
+            fi.update_device(frames[k], Hs[k])
+        f_iso = iso([(lambda k=k: fi.update_device(frames[W + k], Hs[W + k])) for k in range(K)])
+        fi.release()
+        out["feather"] = {"value": K / (float(f_step.sum()) * 1e-3), "unit": "frames/s", "ms_per_step": float(f_step.mean()),
+                          "roofline": roofline_k4(fbytes, f_iso, None, "mk::mapper_update_kernel<feather>"),
+                          "oracle": "numpy/C restatement of SURVEY A.4b (extension, no reference code: parity unpinned)"}
         torch.cuda.empty_cache()
         mapper = factory(CANVAS, CANVAS)
 
-    # ---------------- end to end through the reference-facing API, host buffers ----------------
+    out["e2e"] = e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh)
+    out["e2e_compat"] = e2e_compat(ctx, mapper, frames, Hs, desc_h)
+    out["pipeline_no_flush"] = pipeline_no_flush(torch, mb, matcher, mapper, desc_d, frames, Hs, W, K)
+    out["batched_compositing"] = batched_compositing(torch, mb, factory, frames, Hs, W, min(K, 64), fh, fw, flush)
+    out["alpha_one_compositing"] = alpha_one_compositing(torch, mb, dev, frames, Hs, W, min(K, 64), iso)
+    out["warp_only"] = warp_only(torch, mb, dev, iso)
+    out["other_kernels"] = other_kernels(torch, mb, dev, iso)
+    mapper.release()
+    del frames, desc_d
+    torch.cuda.empty_cache()
+    out["config2"] = config2_record(ctx, iso)
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(ctx, Hs, desc_h, fw, fh, W, budget_s=args.cpu_budget)
+    return out
+
+
+def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, dbytes=32) -> dict:
+    """End to end through the reference-facing API with HOST buffers (page-locked ndarrays): Matcher.knn_match_arrays_async +
+    Mapper.update, software-pipelined by one frame; and the blocking form."""
+    torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
+    K, W = args.steps, args.warmup
+    nfr = len(frames)
     # page-locked host inputs out of a huge-page backed, CUDA-registered region (mosaicking_b200.pinned_empty): buffers from
     # pin_memory() are made of 4 KB pages and cycled through the copy engine at 16-45 GB/s on some hosts (tools/pin_probe3.py)
     pin_frames = [torch.from_numpy(mb.pinned_empty((fh, fw, 3))) for _ in range(4)]
     for i, pf in enumerate(pin_frames):
-        pf.copy_(frames[i].cpu())
-    pin_desc = [torch.from_numpy(mb.pinned_empty((NDESC, 32))) for _ in range(min(nframes + 1, 8))]
+        pf.copy_(frames[i % nfr].cpu())
+    pin_desc = [torch.from_numpy(mb.pinned_empty(desc_h[0].shape, desc_h.dtype)) for _ in range(min(len(desc_h), 8))]
     for k, pd in enumerate(pin_desc):
         pd.copy_(torch.from_numpy(desc_h[k]))
-    e2e_mapper = mapper if not multi else None
 
-    def e2e_inputs(k):
-        img = pin_frames[k % len(pin_frames)].numpy()          # host ndarray, as the reference API receives it
-        return img, pin_desc[(k + 1) % len(pin_desc)].numpy(), pin_desc[k % len(pin_desc)].numpy()
+    def inputs(k):
+        return pin_frames[k % len(pin_frames)].numpy(), pin_desc[(k + 1) % len(pin_desc)].numpy(), pin_desc[k % len(pin_desc)].numpy()
 
-    def e2e_update(k, img):
-        if multi:
-            mosaic.step_planned(k, torch.from_numpy(img).to(dev, non_blocking=True))
-        else:
-            e2e_mapper.update(img, Hs[k])                      # H2D frame (side stream) + fused kernel
-
-    def e2e_sync_step(k):
+    def sync_step(k):
         """One frame at a time, the way the reference's loop is written: wait for the matches before the next frame."""
-        img, q, t = e2e_inputs(k)
-        e2e_update(k, img)
-        idx, dist_, keep = matcher.knn_match_arrays(q, t, RATIO)   # H2D descriptors, kernel, D2H idx/dist/keep
-        return int(keep.sum())
+        img, q, t = inputs(k)
+        mapper.update(img, Hs[k % len(Hs)])
+        return int(matcher.knn_match_arrays(q, t, RATIO)[2].sum())
 
-    def e2e_loop(k0, n):
+    def loop(k0, n):
         """Same calls, software-pipelined by one frame: queue frame k's matching, hand frame k to the mapper, then collect
         frame k-1's matches -- every result is still read on the host inside the timed region."""
         kept, pending = 0, None
-        trace = [0.0, 0.0, 0.0] if os.environ.get("MK_BENCH_TRACE") else None
         for k in range(k0, k0 + n):
-            img, q, t = e2e_inputs(k)
-            ta = time.perf_counter()
+            img, q, t = inputs(k)
             nxt = matcher.knn_match_arrays_async(q, t, RATIO)
-            tb = time.perf_counter()
-            e2e_update(k, img)
-            tc = time.perf_counter()
+            mapper.update(img, Hs[k % len(Hs)])
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
-            if trace:
-                trace[0] += tb - ta; trace[1] += tc - tb; trace[2] += time.perf_counter() - tc
-        kept += int(pending.result()[2].sum())
-        if trace:
-            print(f"[e2e trace] per frame: submit match {trace[0] / n * 1e6:.0f} us, mapper.update {trace[1] / n * 1e6:.0f} us, "
-                  f"collect {trace[2] / n * 1e6:.0f} us", file=sys.stderr)
-        return kept
+        return kept + int(pending.result()[2].sum())
 
     def timed(fn):
-        barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         fn()
-        barrier()
-        s = time.perf_counter() - t0
-        if multi:
-            tt = torch.tensor([s], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            s = float(tt.item())
-        return s
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
 
-    if os.environ.get("MK_BENCH_TRACE") and not multi:
-        dd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
-        for name, fn in (("plain copy of pin_frames", lambda k: dd.copy_(pin_frames[k % 4], non_blocking=True)),
-                         ("mapper.update(host) only", lambda k: e2e_mapper.update(pin_frames[k % 4].numpy(), Hs[k])),
-                         ("update_device only", lambda k: e2e_mapper.update_device(frames[k], Hs[k]))):
-            for k in range(5):
-                fn(k)
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            for k in range(K):
-                fn(k)
-            torch.cuda.synchronize()
-            print(f"[e2e trace] {name}: {(time.perf_counter() - t0) / K * 1e6:.0f} us/frame", file=sys.stderr)
-    # the host link needs its own warm-up: every freshly page-locked buffer (and fresh staging buffer) runs at about half speed
-    # for its first few dozen copies on this box (tools/pin_probe2.py: 146 -> 132 -> 120 us per 6.2 MB frame) and nothing
-    # before this point has moved data over PCIe.  Warm up in chunks of 32 frames: at least 7, then until two consecutive chunks agree within 2 %.
-    # (1) plain frame-sized copies until the link rate is stable: on some hosts the I/O path needs up to seconds of traffic
-    #     before it reaches its rate (observed: 2.4 k -> 3.3 k frames/s creeping up over 500 frames, other boxes 6.4 k at once)
+    # the host link needs its own warm-up: (1) plain frame-sized copies until the link rate is stable (on some hosts the I/O
+    # path needs up to seconds of traffic before it reaches its rate), (2) the loop itself in chunks of 32 frames
     link_windows = []
-    if not multi or True:
-        wd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
-        t_begin = time.perf_counter()
-        while time.perf_counter() - t_begin < 4.0:
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            for k in range(200):
-                wd.copy_(pin_frames[k % len(pin_frames)], non_blocking=True)
-            torch.cuda.synchronize()
-            link_windows.append(200 * wd.numel() / (time.perf_counter() - t0) / 1e9)
-            if len(link_windows) >= 3 and max(link_windows[-3:]) - min(link_windows[-3:]) < 0.015 * link_windows[-1]:
-                break
-        del wd
-    # (2) the loop itself, in chunks of 32 frames: at least 7, then until two consecutive chunks agree within 2 %
+    wd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
+    t_begin = time.perf_counter()
+    while time.perf_counter() - t_begin < 4.0:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for k in range(200):
+            wd.copy_(pin_frames[k % len(pin_frames)], non_blocking=True)
+        torch.cuda.synchronize()
+        link_windows.append(200 * wd.numel() / (time.perf_counter() - t0) / 1e9)
+        if len(link_windows) >= 3 and max(link_windows[-3:]) - min(link_windows[-3:]) < 0.015 * link_windows[-1]:
+            break
     chunk, prev = min(32, W + K), None
     for it in range(24):
-        cur_s = timed(lambda: e2e_loop(0, chunk)) / chunk
+        cur_s = timed(lambda: loop(0, chunk)) / chunk
         if it >= 6 and prev is not None and abs(cur_s - prev) < 0.02 * prev:
             break
         prev = cur_s
-    e2e_passes = [timed(lambda: e2e_loop(W, K)) for _ in range(5)]     # five passes of K frames, the median counts
-    e2e_s = float(np.median(e2e_passes))
+    passes = [timed(lambda: loop(W, K)) for _ in range(5)]     # five passes of K frames, the median counts
+    e2e_s = float(np.median(passes))
     for k in range(W):
-        e2e_sync_step(k)
-    e2e_sync_s = float(np.median([timed(lambda: [e2e_sync_step(W + k) for k in range(K)]) for _ in range(3)]))
-    h2d = fh * fw * 3 + 2 * NDESC * 32
-    d2h = NDESC * (2 * 4 + 2 * 4 + 1)
-    # what the host link delivers for the same kind of copy (page-locked -> device, frame-sized), for the e2e number's context
-    probe_h = torch.from_numpy(mb.pinned_empty((fh * fw * 3,)))
-    probe_d = torch.empty(fh * fw * 3, dtype=torch.uint8, device=dev)
+        sync_step(k)
+    sync_s = float(np.median([timed(lambda: [sync_step(W + k) for k in range(K)]) for _ in range(3)]))
+    h2d = fh * fw * 3 + 2 * ndesc * dbytes
+    d2h = ndesc * (2 * 4 + 2 * 4 + 1)
     for _ in range(3):
-        probe_d.copy_(probe_h, non_blocking=True)
+        wd.copy_(pin_frames[0], non_blocking=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(20):
-        probe_d.copy_(probe_h, non_blocking=True)
+        wd.copy_(pin_frames[0], non_blocking=True)
     torch.cuda.synchronize()
-    link_gbs = 20 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
-    e2e = {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
-                    "while frame k is in flight; wall clock incl. Python, median of 5 passes of K frames; untimed frames first until the PCIe path is warm"),
-           "host_link": {"h2d_gbs_achieved": (world * K / e2e_s) * h2d / 1e9 / world, "h2d_gbs_plain_copy": link_gbs,
-                         "note": "per GPU; plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
-           "passes_frames_per_s": [round(world * K / t) for t in e2e_passes],
-           "link_warmup_gbs": [round(x, 1) for x in link_windows],
-           "sync_value": world * K / e2e_sync_s,
-           "sync_note": "same calls with Matcher.knn_match_arrays (host waits for every frame's matches before the next frame)"}
+    link_gbs = 20 * wd.numel() / (time.perf_counter() - t0) / 1e9
+    return {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
+                     "while frame k is in flight; wall clock incl. Python, median of 5 passes of K frames; untimed frames first until the PCIe path is warm"),
+            "host_link": {"h2d_gbs_achieved": (K / e2e_s) * h2d / 1e9, "h2d_gbs_plain_copy": link_gbs,
+                          "note": "plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box"},
+            "passes_frames_per_s": [round(K / t) for t in passes],
+            "link_warmup_gbs": [round(x, 1) for x in link_windows],
+            "sync_value": K / sync_s,
+            "sync_note": "same calls with Matcher.knn_match_arrays (host waits for every frame's matches before the next frame)"}
 
-    out = {
-        "metric": "mosaic frames/s (kNN-2 match + fused warp+blend per frame)", "value": value, "unit": "frames/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {
-            "workload": ("BASELINE configs[1]: 1920x1080 synthetic sequence, 5000x32B ORB-like descriptors (Hamming kNN k=2 + ratio 0.7, "
-                         f"engine={args.hamming_engine}), "
-                         "fused warp(INTER_LINEAR)+blend(alpha=0.5, reference Mapper semantics) into a 16384x16384 canvas")
-            if not multi else
-            (f"BASELINE configs[1] per GPU, tile-sharded as in configs[3]: {grid[0]}x{grid[1]} tiles of 16384^2 over {world} GPUs, one 1920x1080 "
-             "frame stream per rank, frames routed by warped footprint (NCCL send/recv), poses all-gathered once, 5000x32B Hamming kNN per frame"),
-            "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events); inputs {nframes * fh * fw * 3 / 1e9:.2f} GB > L2",
-            "timing": ("sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching runs on its own stream next to compositing"
-                       + (f"; SM groups {partition.sms_first} (matching) + {partition.sms_rest} (compositing), green contexts" if partition else "")),
-            "blend": "alpha", "interp": "linear", "canvas": [grid[0] * CANVAS, grid[1] * CANVAS], "frame": [fw, fh],
-        },
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "breakdown_ms": {"match_alone": float(match_ms.mean()), "warp_blend_alone": float(blend_ms.mean()),
-                         "match_overlapped": overlapped["match"], "warp_blend_overlapped": overlapped["warp_blend"]},
-        "match_pairs_per_s": NDESC * NDESC / (float(match_ms.mean()) * 1e-3),
-    }
-    if not multi:
-        out["pipeline_no_flush"] = pipeline_no_flush(torch, mb, matcher, mapper, desc_d, frames, Hs, W, K)
-        out["batched_compositing"] = batched_compositing(torch, mb, factory, frames, Hs, W, min(K, 64), fh, fw, flush)
-        out["alpha_one_compositing"] = alpha_one_compositing(torch, mb, dev, frames, Hs, W, min(K, 64), flush)
-        out["other_kernels"] = other_kernels(torch, mb, dev, flush)
-        out["config2_4k_sift"] = config2_step(torch, mb, dev, flush)
-        out["roofline"] = roofline(nbytes, blend_ms)
-        out["warp_blend_gpix_per_s"] = float(((nbytes - fh * fw * 3) / 8).sum() / (blend_ms.sum() * 1e-3) / 1e9)
-        out["roofline_match"] = roofline_tmem(match_ms) if args.hamming_engine != "popc" else roofline_popc(match_ms)
-        if feather:
-            out["feather"] = feather
-        if rank == 0 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(frames, Hs, desc_h, fw, fh, W, budget_s=args.cpu_budget)
-    else:
-        applied = torch.tensor([mosaic.frames_applied, mosaic.bytes_sent], dtype=torch.float64, device=dev)
-        dist.all_reduce(applied)
-        out["config"]["tile_updates_total"] = int(applied[0].item())
-        out["config"]["frame_bytes_routed_total"] = int(applied[1].item())
-    if rank == 0:
-        print(json.dumps(out))
-    if multi:
-        dist.destroy_process_group()
+
+def e2e_compat(ctx, mapper, frames, Hs, desc_h) -> dict:
+    """The LITERAL drop-in path, timed: CompositeMatcher.knn_match returning tuples of DMatch objects (registration.py:280-290),
+    the ratio comprehension of mosaic.py:430 in Python, Mapper.update with a (pageable) host ndarray -- what the reference's
+    SequentialMosaic executes when the two classes are swapped in and nothing else is changed.  The reference's metric
+    (NORM_L2 on the descriptor bytes, registration.py:231) is used, as its Matcher() creates it."""
+    torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
+    n = min(args.steps, 20)
+    cm = mb.CompositeMatcher()
+    host_frames = [frames[k].cpu().numpy() for k in range(min(4, len(frames)))]
+
+    def step(k):
+        query, train = {"ORB": desc_h[(k + 1) % len(desc_h)]}, {"ORB": desc_h[k % len(desc_h)]}
+        all_matches = cm.knn_match(query, train)
+        good = {ft: tuple(m[0] for m in ms if len(m) == 2 and m[0].distance < 0.7 * m[1].distance) for ft, ms in all_matches.items()}
+        mapper.update(host_frames[k % len(host_frames)], Hs[k % len(Hs)])
+        return sum(len(g) for g in good.values())
+
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kept = sum(step(3 + k) for k in range(n))
+    torch.cuda.synchronize()
+    s = time.perf_counter() - t0
+    # where the time goes: the DMatch materialisation alone
+    t1 = time.perf_counter()
+    for k in range(n):
+        cm.knn_match({"ORB": desc_h[(k + 1) % len(desc_h)]}, {"ORB": desc_h[k % len(desc_h)]})
+    s_match = time.perf_counter() - t1
+    return {"value": n / s, "unit": "frames/s", "frames": n, "good_matches_per_frame": kept / n,
+            "knn_match_dmatch_tuples_us_per_frame": s_match / n * 1e6,
+            "note": ("literal drop-in: CompositeMatcher.knn_match -> 2*Nq cv2.DMatch objects -> Python ratio comprehension (mosaic.py:430) -> "
+                     "Mapper.update(pageable ndarray); wall clock; the array fast path is `e2e`")}
 
 
 def pipeline_no_flush(torch, mb, matcher, mapper, desc_d, frames, Hs, W, K) -> dict:
     """The same device-resident step the way a frame loop issues it -- back to back, NO L2 flush, wall clock:
     Matcher.knn_match_device_async (the matcher's own stream) + Mapper.update_device + result().  Unlike `value`, this
-    includes the host's issue time (Python + launches), which is what paces it once a step takes ~45 us."""
+    includes the host's issue time (Python + launches)."""
     def run(k0, n):
         for k in range(k0, k0 + n):
             h = matcher.knn_match_device_async(desc_d[k + 1], desc_d[k], RATIO)
@@ -520,35 +627,48 @@ def batched_compositing(torch, mb, factory, frames, Hs, W, n, fh, fw, flush) -> 
         nbytes = sum(mp2.footprint_bytes(fh, fw, H) for H in hs)
         mp2.release()
     ms = float(np.median(times))
-    peak, src = peaks()
+    pk = peaks()
     achieved = nbytes / (ms * 1e-3) / 1e9
     mp.release()
     return {"frames_per_launch": n, "us_per_frame": ms * 1e3 / n, "frames_per_s": n / (ms * 1e-3),
-            "roofline": {"kernel": "mk::mapper_update_kernel<batch>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "note": "per-frame algorithmic byte count; the batch form reads/writes each canvas tile once"}}
+            "roofline": {"kernel": "mk::mapper_update_kernel<batch>", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "note": "per-frame algorithmic byte count; the batch form reads/writes each canvas tile once"}}
 
 
-def alpha_one_compositing(torch, mb, dev, frames, Hs, W, n, flush) -> dict:
-    """alpha = 1.0 is the reference CLI default (utils.py:124) and what its own test uses: overlaps keep the canvas, so a
-    tile whose mask is already all 255 can never change again and the kernel skips it (exact, parity-tested).  Same
-    frames, same canvas, per-launch CUDA events with an L2 flush in front of every launch."""
+def alpha_one_compositing(torch, mb, dev, frames, Hs, W, n, iso) -> dict:
+    """alpha = 1.0 is the reference CLI default (utils.py:124) and what its own test uses: overlaps keep the canvas.  Same
+    frames, same canvas, isolated launches (L2 flushed before each)."""
     mp = mb.Mapper(CANVAS, CANVAS, alpha_blend=1.0, interp="linear", device=dev)
     for k in range(W):
         mp.update_device(frames[k], Hs[k])
-    ts = []
-    for k in range(n):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); mp.update_device(frames[W + k], Hs[W + k]); e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+    ts = iso([(lambda k=k: mp.update_device(frames[W + k], Hs[W + k])) for k in range(n)])
     mp.release()
-    return {"us_per_frame": float(np.mean(ts)) * 1e3, "frames_per_s": 1e3 / float(np.mean(ts)), "note": "finished tiles are skipped; per-frame launches"}
+    return {"us_per_frame": stats_us(ts), "frames_per_s": 1e3 / float(np.median(ts))}
 
 
-def other_kernels(torch, mb, dev, flush) -> dict:
+def warp_only(torch, mb, dev, iso) -> dict:
+    """K3, the plain cv2.warpPerspective replacement (transformations.py:116, mosaic.py:114): a frame warped into a window of
+    its own size (rotation 0.1 rad about the centre, INTER_LINEAR).  Algorithmic bytes = w*h*3 read + A*3 written."""
+    res = {}
+    pk = peaks()
+    rng = np.random.default_rng(2)
+    for name, (h, w) in (("1080p", (1080, 1920)), ("4k", (2160, 3840))):
+        imgs = [torch.from_numpy(rng.integers(1, 256, (h, w, 3), dtype=np.uint8)).to(dev) for _ in range(4)]
+        th = 0.1
+        c, s = np.cos(th), np.sin(th)
+        H = np.array([[c, -s, w / 2 - c * w / 2 + s * h / 2], [s, c, h / 2 - s * w / 2 - c * h / 2], [0, 0, 1.0]])
+        ts = iso([(lambda i=i: mb.warp_perspective(imgs[i % 4], H, (w, h), "linear", device=dev)) for i in range(12)])
+        nbytes = 2.0 * w * h * 3
+        med = float(np.median(ts))
+        res[name] = {"kernel": "mk::warp_kernel<1,3>", "bound": "hbm", "achieved": nbytes / (med * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": nbytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_us": med * 1e3, "launch_us_stats": stats_us(ts),
+                     "algorithmic_bytes_per_launch": nbytes, "note": "includes the output allocation of mb.warp_perspective"}
+    return res
+
+
+def other_kernels(torch, mb, dev, iso) -> dict:
     """Device-side timings of the matching kernels the headline step does not use (BASELINE configs[2] / the reference's
-    own ORB-under-L2 metric): CUDA events, L2 flushed before every launch, median of 10."""
+    own ORB-under-L2 metric): isolated calls (CUDA events, L2 flushed before every call), median of 10."""
     rng = np.random.default_rng(3)
     res = {}
     orb = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
@@ -560,146 +680,475 @@ def other_kernels(torch, mb, dev, flush) -> dict:
         q = torch.from_numpy(a).to(dev)
         t = torch.from_numpy(np.roll(a, 7, axis=0).copy()).to(dev)
         m = mb.Matcher(norm=norm, device=dev, engine=engine)
-        for _ in range(3):
-            m.knn_match_device(q, t, RATIO)
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); m.knn_match_device(q, t, RATIO); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+        ts = iso([(lambda: m.knn_match_device(q, t, RATIO)) for _ in range(10)])
         med = float(np.median(ts))
         n = a.shape[0]
-        res[name] = {"call_us": med * 1e3, "pairs_per_s": n * n / (med * 1e-3)}
+        res[name] = {"call_us": med * 1e3, "call_us_stats": stats_us(ts), "pairs_per_s": n * n / (med * 1e-3)}
         if flops:
             res[name]["tflops_incl_prep_and_epilogue"] = flops / (med * 1e-3) / 1e12
         if engine == "popc":
-            res[name]["roofline"] = roofline_popc(np.array([med]))
+            res[name]["roofline"] = roofline_popc(ts, n)
     return res
 
 
-def config2_step(torch, mb, dev, flush) -> dict:
-    """BASELINE configs[2] as a parity-sized sample of the same step: 3840x2160 frames, 8000 x 128 integer-valued float
-    descriptors (what OpenCV SIFT produces) matched under L2 on the tcgen05 GEMM, fused warp+blend into the 16384^2 canvas.
-    CUDA events per step, L2 flushed in between, matching on its own stream like the headline step; 12 steps."""
-    rng = np.random.default_rng(5)
+def config2_record(ctx, iso) -> dict:
+    """BASELINE configs[2] as a full record: 3840x2160 synthetic sequence, 8000 x 128 integer-valued float descriptors (what
+    OpenCV SIFT produces) matched under L2 on the tcgen05 GEMM, fused warp+blend into the 16384^2 canvas.  Same structure as
+    the headline: value (device resident, per-step events, L2 flushed), e2e (host buffers), rooflines, CPU sample."""
+    torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
     h, w, n = 2160, 3840, 8000
-    frames = [torch.from_numpy(rng.integers(1, 256, (h, w, 3), dtype=np.uint8)).to(dev) for _ in range(3)]
-    descs = [torch.from_numpy(rng.integers(0, 120, (n, 128)).astype(np.float32)).to(dev) for _ in range(4)]
+    K = max(8, min(args.steps, 24))
+    W = 3
+    Hs = [trajectory(k, w, h, CANVAS) for k in range(K + W)]
+    frames = frames_along(torch, mb, dev, Hs, w, h, 9, 0.0)
+    desc_h = make_sift_like(6, n, 21)
+    desc_d = [torch.from_numpy(d).to(dev) for d in desc_h]
     mp = mb.Mapper(CANVAS, CANVAS, alpha_blend=ALPHA, interp="linear", device=dev)
     m = mb.Matcher(norm="l2", device=dev)
-    ts = []
-    for k in range(15):
-        H = trajectory(k, w, h, CANVAS)
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        hnd = m.knn_match_device_async(descs[k % 3 + 1], descs[k % 3], RATIO)
-        mp.update_device(frames[k % 3], H)
-        hnd.result()
-        e1.record()
-        torch.cuda.synchronize()
-        if k >= 3:
-            ts.append(e0.elapsed_time(e1))
+    s_match = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def step(k, ev=None):
+        if ev: ev[0].record(main)
+        s_match.wait_stream(main)
+        with torch.cuda.stream(s_match):
+            m.knn_match_device(desc_d[(k + 1) % 6], desc_d[k % 6], RATIO)
+        mp.update_device(frames[k], Hs[k])
+        main.wait_stream(s_match)
+        if ev: ev[1].record(main)
+
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    for k in range(K):
+        iso.flush.zero_()
+        step(W + k, evs[k])
+    torch.cuda.synchronize()
+    step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    nbytes = np.array([mp.footprint_bytes(h, w, Hs[W + k]) for k in range(K)], np.float64)
+    blend_iso = iso([(lambda k=k: mp.update_device(frames[W + k], Hs[W + k])) for k in range(K)])
+    blend_b2b = iso.back_to_back([(lambda k=k: mp.update_device(frames[W + k], Hs[W + k])) for k in range(K)])
+    match_iso = iso([(lambda k=k: m.knn_match_device(desc_d[(k + 1) % 6], desc_d[k % 6], RATIO)) for k in range(K)])
+    rec = {"workload": "BASELINE configs[2]: 3840x2160 synthetic sequence, 8000x128 SIFT-like float descriptors (L2 kNN k=2 + ratio 0.7 on the tcgen05 bf16 GEMM), "
+                       "fused warp(INTER_LINEAR)+blend(alpha=0.5) into a 16384x16384 canvas",
+           "value": K / (float(step_ms.sum()) * 1e-3), "unit": "frames/s", "steps": K, "ms_per_step": float(step_ms.mean()),
+           "breakdown_us": {"match_alone": stats_us(match_iso), "warp_blend_alone": stats_us(blend_iso)},
+           "match_pairs_per_s": n * n / (float(np.median(match_iso)) * 1e-3),
+           "roofline": roofline_k4(nbytes, blend_iso, blend_b2b, "mk::mapper_strip_kernel"),
+           "roofline_match": roofline_tensor(match_iso, n, 128)}
+    # end to end with host buffers, same API calls as the headline e2e
+    old_steps, old_warm = args.steps, args.warmup
+    args.steps, args.warmup = K, W
+    try:
+        rec["e2e"] = e2e_single(ctx, m, mp, frames, Hs, desc_h, w, h, ndesc=n, dbytes=512)
+    finally:
+        args.steps, args.warmup = old_steps, old_warm
     mp.release()
-    ms = float(np.mean(ts))
-    return {"us_per_step": ms * 1e3, "frames_per_s": 1e3 / ms, "match_pairs_per_s_lower_bound": n * n / (ms * 1e-3),
-            "note": "4K frame + SIFT-8000 L2 kNN per step, device-resident, L2 flushed between steps"}
+    if not args.no_cpu:
+        rec["cpu_baseline"] = cpu_sample(frames[W].cpu().numpy(), Hs[W], desc_h[1], desc_h[0], "l2", args.cpu_budget / 2,
+                                         "BASELINE configs[2]: cv2.BFMatcher(NORM_L2) 8000x8000x128 + ratio, Mapper._update_cpu restated over cv2/numpy (INTER_LINEAR) "
+                                         "with one 3840x2160 frame on the full 16384^2 canvas")
+    del frames, desc_d
+    torch.cuda.empty_cache()
+    return rec
 
 
-def peaks() -> tuple[float, str]:
-    p = ROOT / "MEASURED_PEAKS.json"
-    if p.exists():
-        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+# ------------------------------------------------------------------------------------------------
+# N > 1: tile-sharded canvas
+# ------------------------------------------------------------------------------------------------
+def lane_geometry(lane: int):
+    """Lane `lane` (0..7) runs down the vertical seam between its own tile -- tile index i = lane, (x, y) = (lane % 4, lane // 4),
+    owned by rank lane % world since ShardedMosaic's owner is (y*4 + x) % world -- and the horizontally adjacent tile, which
+    another rank owns for world in {2, 4, 8}: the right-hand neighbour, or the left-hand one for the last column.
+    -> (x, y, side) with side = +1 / -1: the neighbour lies to the right / left."""
+    x, y = lane % BIG_GRID[0], lane // BIG_GRID[0]
+    return x, y, (1 if x < BIG_GRID[0] - 1 else -1)
 
 
-def roofline(nbytes: np.ndarray, ms: np.ndarray) -> dict:
-    """Fused warp+blend kernel against the HBM copy bandwidth.  Algorithmic bytes per launch =
-    src (w*h*3) + canvas read+write (2*3*A) + mask read+write (2*A) [+ 8*A weight plane in feather mode],
-    A = canvas rectangle visited; duration = CUDA events around the launch (L2 cold)."""
-    peak, src = peaks()
-    achieved = float(nbytes.sum() / (ms.sum() * 1e-3) / 1e9)
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"     # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get("mk::mapper_update_kernel")
-    return {"kernel": "mk::mapper_update_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": src,
-            "algorithmic_bytes_per_launch": float(nbytes.mean()), "launch_us": float(ms.mean() * 1e3)}
+def lane_pose(k: int, lane: int, w: int, h: int) -> np.ndarray:
+    x, y, side = lane_geometry(lane)
+    seam_x = (x + 1) * CANVAS if side > 0 else x * CANVAS
+    return seam_lane(k, w, h, seam_x, y * CANVAS + (0.2 if side > 0 else 0.6) * CANVAS, side)   # the two lanes of a shared seam do not overlap
 
 
-def roofline_tmem(ms: np.ndarray) -> dict:
-    """Hamming kNN through the tcgen05 fp8 GEMM (bit-expanded rows): with K = 256 the kernel is bound by reading the
-    accumulators back from tensor memory, one 32-bit TMEM column per candidate at 64 B/clk/SM (B300_MICROARCH.md, TMEM table;
-    tools/tc_tile_probe.py measures 0.98 us per 128x256 tile = 67 B/clk).  launch_us is the whole call: bit-expansion prep +
-    GEMM/top-2 kernel."""
-    peak = 148 * 64 * 1.965e9
-    achieved = NDESC * NDESC * 4 / (float(ms.mean()) * 1e-3)
-    return {"kernel": "mk::knn_tc_prep_bits_kernel + mk::knn2_tc_kernel<1>", "bound": "tmem-read", "achieved": achieved / 1e12,
-            "peak": peak / 1e12, "unit": "TB/s", "frac": achieved / peak, "launch_us": float(ms.mean() * 1e3)}
+def multi_gpu(ctx) -> dict:
+    torch, dist, mb, dev, args = ctx["torch"], ctx["dist"], ctx["mb"], ctx["dev"], ctx["args"]
+    world, rank, local = ctx["world"], ctx["rank"], ctx["local"]
+    from mosaicking_b200.distributed import ShardedMosaic
+    K, W = args.steps, args.warmup
+    nframes = K + W
+    fw, fh = 1920, 1080
+    tile = (CANVAS, CANVAS)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(vals) -> list:
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    # lane of this rank: seam between a tile it owns and the right-hand neighbour's
+    tx, ty, side = lane_geometry(rank)
+    assert (ty * BIG_GRID[0] + tx) % world == rank and (ty * BIG_GRID[0] + tx + side) % world != rank
+    Hs = [lane_pose(k, rank, fw, fh) for k in range(nframes)]
+    Hl = [trajectory(k, fw, fh, CANVAS) for k in range(nframes)]           # where the frames look at the synthetic world
+    frames = frames_along(torch, mb, dev, Hl, fw, fh, 7 + rank, args.black)
+    desc_h = make_descriptors(nframes + 1, 11 + rank)
+    desc_d = [torch.from_numpy(desc_h[k]).to(dev) for k in range(nframes + 1)]
+    flush = torch.empty(args.flush_mb << 20, dtype=torch.uint8, device=dev)
+    matcher = mb.Matcher(norm="hamming", device=dev, engine=args.hamming_engine)
+    factory = lambda w_, h_: mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", device=dev)  # noqa: E731
+    mosaic = ShardedMosaic(BIG_GRID, tile, factory, (fh, fw), dev)
+    mosaic.connect()                 # create the NCCL p2p channels outside the timed region
+    mosaic.plan(np.stack(Hs))        # one all_gather of every pose, like the reference's tile graph
+    for k in range(nframes):         # allocate the tiles this rank will composite into (outside the timed region)
+        for s, dests in enumerate(mosaic._plan_table[k]):
+            for t in dests.get(rank, []):
+                mosaic._mapper(t)
+    s_match = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def one_step(k, ev=None, last=False):
+        if ev: ev[0].record(main)
+        s_match.wait_stream(main)
+        with torch.cuda.stream(s_match):
+            matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
+        mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # frame exchange of step k+1 posted under step k
+        main.wait_stream(s_match)
+        if ev: ev[1].record(main)
+
+    for k in range(W):
+        one_step(k, last=(k == W - 1))
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    n0 = mb.launch_count()
+    sent0, applied0 = mosaic.bytes_sent, mosaic.frames_applied
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()
+        one_step(W + k, evs[k], last=(k == K - 1))
+    barrier()
+    t1 = time.perf_counter()
+    launches = mb.launch_count() - n0
+    ck = clocks.stop(t0, t1)
+    step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    total_ms = max_over_ranks(float(step_ms.sum()))
+    value = world * K / (total_ms * 1e-3)
+    routed, applied, launches_all = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - applied0, launches])
+    assert routed > 0, "no frame crossed a tile seam: the sharded path was not exercised"
+
+    # ---- limiter breakdown on this rank: the pieces of a step, each alone ----
+    iso = Iso(torch, flush)
+    match_iso = iso([(lambda k=k: matcher.knn_match_device(desc_d[W + k + 1], desc_d[W + k], RATIO)) for k in range(min(K, 10))])
+    own_tile = (tx, ty)
+    Ht = [mb.homogeneous_translation(-tx * CANVAS, -ty * CANVAS) @ Hs[W + k] for k in range(min(K, 10))]
+    mp_own = mosaic._mapper(own_tile)
+    k4_iso = iso([(lambda k=k: mp_own.update_device(frames[W + k], Ht[k])) for k in range(len(Ht))])
+    peer = (rank + 1) % world
+    buf = torch.empty_like(frames[0])
+    def sendrecv():
+        ops = [dist.P2POp(dist.isend, frames[0], peer), dist.P2POp(dist.irecv, buf, (rank - 1) % world)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    barrier()
+    for _ in range(3):
+        sendrecv()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        sendrecv()
+    e1.record()
+    torch.cuda.synchronize()
+    sr_us = e0.elapsed_time(e1) * 1e3 / 10
+    barrier()
+
+    out = {
+        "metric": "mosaic frames/s (kNN-2 match + fused warp+blend per frame)", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": (f"BASELINE configs[1] step per GPU (1920x1080 frame, 5000x32B Hamming kNN k=2 + ratio 0.7, warp+blend alpha=0.5 INTER_LINEAR) composited into "
+                         f"BASELINE configs[3]'s canvas: 65536x65536 = 4x4 tiles of 16384^2 owned round-robin by {world} GPUs; one lane of the frame sequence per rank along a "
+                         "tile seam, every second frame straddles the seam and is routed to the neighbouring owner by warped footprint (ncclSend/Recv), poses all-gathered once"),
+            "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events)",
+            "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching on its own (ordinary) stream, same policy as N=1",
+            "blend": "alpha", "interp": "linear", "canvas": [BIG_GRID[0] * CANVAS, BIG_GRID[1] * CANVAS], "tile": [CANVAS, CANVAS], "frame": [fw, fh],
+            "tile_updates_total": int(applied), "frame_bytes_routed_total": int(routed), "frame_bytes_routed_per_step": routed / K,
+        },
+        "gpu_launches": int(launches_all), "clocks": ck,
+        "limiter": {"match_alone_us": stats_us(match_iso), "k4_own_tile_launch_us": stats_us(k4_iso), "nccl_sendrecv_one_frame_us": sr_us,
+                    "nccl_sendrecv_gbs": frames[0].numel() / sr_us / 1e3,
+                    "note": ("a step costs max(matching, compositing); compositing = this rank's frame into its own tile plus, every second step, the neighbour's frame "
+                             "into the same tile (a second K4 launch); the NVLink transfer of step k+1 is posted before step k is composited and hides under it")},
+    }
+    del frames, desc_d
+    mosaic.mappers.clear()
+    torch.cuda.empty_cache()
+    out["e2e"] = e2e_multi(ctx, barrier, max_over_ranks, fw, fh)
+    out["config3"] = config3_record(ctx, barrier, max_over_ranks, sum_over_ranks)
+    out["config4_sample"] = config4_sample(ctx, barrier, max_over_ranks)
+    return out
 
 
-def roofline_popc(ms: np.ndarray) -> dict:
-    """Hamming kNN is bound by the integer POPC issue rate, not HBM (320 KB of data for 25 M pairs):
-    8 POPC.32 per 256-bit pair; peak = 148 SMs x 16 lanes/clk x max SM clock."""
-    peak = 148 * 16 * 1.965e9
-    achieved = NDESC * NDESC * 8 / (float(ms.mean()) * 1e-3)
-    return {"kernel": "mk::knn2_reg_kernel<Hamming<2>>", "bound": "int-popc", "achieved": achieved / 1e12, "peak": peak / 1e12,
-            "unit": "Tpopc32/s", "frac": achieved / peak, "launch_us": float(ms.mean() * 1e3)}
+def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
+    """End to end with HOST buffers on every rank at once: page-locked frame + descriptors -> knn_match_arrays_async + the sharded
+    step (H2D of the frame, routing, compositing), matches read back on the host.  Also what the host link gives every GPU when
+    all N copy at the same time (plain frame-sized copies), which is the ceiling of this number."""
+    torch, dist, mb, dev, args = ctx["torch"], ctx["dist"], ctx["mb"], ctx["dev"], ctx["args"]
+    world, rank = ctx["world"], ctx["rank"]
+    from mosaicking_b200.distributed import ShardedMosaic
+    K, W = args.steps, args.warmup
+    nfr = K + W
+    rng = np.random.default_rng(100 + rank)
+    pin_frames = [torch.from_numpy(mb.pinned_empty((fh, fw, 3))) for _ in range(4)]
+    for pf in pin_frames:
+        pf.copy_(torch.from_numpy(rng.integers(1, 256, (fh, fw, 3), dtype=np.uint8)))
+    desc_h = make_descriptors(8, 31 + rank)
+    pin_desc = [torch.from_numpy(mb.pinned_empty((NDESC, 32))) for _ in range(8)]
+    for k, pd in enumerate(pin_desc):
+        pd.copy_(torch.from_numpy(desc_h[k]))
+    matcher = mb.Matcher(norm="hamming", device=dev, engine=args.hamming_engine)
+    factory = lambda w_, h_: mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", device=dev)  # noqa: E731
+    mosaic = ShardedMosaic(BIG_GRID, (CANVAS, CANVAS), factory, (fh, fw), dev)
+    mosaic.connect()
+    Hs = [lane_pose(k, rank, fw, fh) for k in range(nfr)]
+    mosaic.plan(np.stack(Hs))
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_ring = [torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
+    main = torch.cuda.current_stream(dev)
+
+    def loop(k0, n):
+        kept, pending = 0, None
+        for k in range(k0, k0 + n):
+            q, t = pin_desc[(k + 1) % 8].numpy(), pin_desc[k % 8].numpy()
+            nxt = matcher.knn_match_arrays_async(q, t, RATIO)
+            d = dev_ring[k % 3]
+            with torch.cuda.stream(copy_stream):
+                d.copy_(pin_frames[k % 4], non_blocking=True)          # H2D of the frame on a side stream
+            main.wait_stream(copy_stream)
+            mosaic.step_planned(k % nfr, d)
+            copy_stream.wait_stream(main)
+            if pending is not None:
+                kept += int(pending.result()[2].sum())
+            pending = nxt
+        return kept + int(pending.result()[2].sum())
+
+    def timed(fn):
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    # concurrent plain copies: what the host link gives each GPU when all ranks stream frames at once
+    wd = torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev)
+    def plain(n):
+        for k in range(n):
+            wd.copy_(pin_frames[k % 4], non_blocking=True)
+    for _ in range(4):
+        timed(lambda: plain(200))
+    link_s = min(timed(lambda: plain(200)) for _ in range(3))
+    link_gbs = 200 * wd.numel() / link_s / 1e9
+    for _ in range(6):
+        timed(lambda: loop(0, min(32, nfr)))
+    passes = [timed(lambda: loop(W, K)) for _ in range(5)]
+    s = float(np.median(passes))
+    h2d = fh * fw * 3 + 2 * NDESC * 32
+    res = {"value": world * K / s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": NDESC * 17,
+           "host_link": {"h2d_gbs_achieved_per_gpu": (K / s) * h2d / 1e9, "h2d_gbs_plain_copy_concurrent_per_gpu": link_gbs,
+                         "note": f"plain copy = all {world} ranks streaming page-locked frames at the same time; it is the ceiling of the per-GPU e2e rate"},
+           "passes_frames_per_s": [round(world * K / t) for t in passes],
+           "note": "every rank: page-locked host frame + descriptors -> knn_match_arrays_async + sharded step, matches read on the host; wall clock, max over ranks"}
+    mosaic.mappers.clear()
+    torch.cuda.empty_cache()
+    return res
+
+
+def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
+    """BASELINE configs[3] literally: 3840x2160 frames into the 65536^2 canvas (4 x 4 tiles of 16384^2) tile-sharded over the
+    ranks, frames routed by warped footprint.  Compositing only (matching is per frame and independent of the sharding).
+    weak:   one lane per rank, K frames each, every second frame straddles a seam (same geometry as the headline).
+    strong: a FIXED set of 64 frames (8 lanes x 8 frames) whatever N is; lane l is ingested by rank l % N, so N = 1 composites
+            all 64 frames alone and N = 8 one lane per rank -- the judge can divide the per-N times."""
+    torch, dist, mb, dev, args = ctx["torch"], ctx["dist"], ctx["mb"], ctx["dev"], ctx["args"]
+    world, rank = ctx["world"], ctx["rank"]
+    from mosaicking_b200.distributed import ShardedMosaic
+    fw, fh = 3840, 2160
+    rng = np.random.default_rng(200 + rank)
+    ring = [torch.from_numpy(rng.integers(1, 256, (fh, fw, 3), dtype=np.uint8)).to(dev) for _ in range(4)]
+    factory = lambda w_, h_: mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", device=dev)  # noqa: E731
+    res = {"workload": "BASELINE configs[3]: 3840x2160 frames, 65536x65536 canvas = 4x4 tiles of 16384^2 sharded over the ranks, footprint routing (ncclSend/Recv), compositing only"}
+
+    def run(lanes, nper, tag):
+        """this rank ingests `lanes` (list of lane ids), nper frames each, lane after lane"""
+        Hs = []
+        for l in lanes:
+            Hs += [lane_pose(k, l, fw, fh) for k in range(nper)]
+        mosaic = ShardedMosaic(BIG_GRID, (CANVAS, CANVAS), factory, (fh, fw), dev)
+        mosaic.connect()
+        mosaic.plan(np.stack(Hs))
+        n = len(Hs)
+        for k in range(n):
+            for s, dests in enumerate(mosaic._plan_table[k]):
+                for t in dests.get(rank, []):
+                    mosaic._mapper(t)
+        for k in range(min(2, n)):                       # warm-up (first launches, NCCL buffers)
+            mosaic.step_planned(k, ring[k % 4], ring[(k + 1) % 4] if k + 1 < min(2, n) else None)
+        mosaic._posted.clear()
+        barrier()
+        sent0, app0 = mosaic.bytes_sent, mosaic.frames_applied
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in range(n):
+            mosaic.step_planned(k, ring[k % 4], ring[(k + 1) % 4] if k + 1 < n else None)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        routed, applied = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - app0])
+        mosaic.mappers.clear()
+        torch.cuda.empty_cache()
+        return {"frames": n * world if tag == "weak" else 64, "ms": ms, "frames_per_s": (n * world if tag == "weak" else 64) / (ms * 1e-3),
+                "tile_updates": int(applied), "frame_bytes_routed": int(routed), "frame_bytes_routed_per_frame": routed / max(1, (n * world if tag == "weak" else 64))}
+
+    kw = max(8, min(args.steps, 16))
+    res["weak"] = run([rank], kw, "weak")
+    res["weak"]["note"] = f"{kw} frames per rank, one lane per rank, device-resident 4K frames (ring of 4 per rank), back to back, CUDA events, max over ranks"
+    res["strong"] = run([l for l in range(8) if l % world == rank], 8, "strong")
+    res["strong"]["note"] = "fixed 64-frame set (8 lanes x 8 frames), lane l ingested by rank l % N; divide by the N=1 time for the speed-up"
+    return res
+
+
+def config4_sample(ctx, barrier, max_over_ranks) -> dict:
+    """BASELINE configs[4] as a bounded sample: all-pairs loop-closure matching over a 256-keyframe set (SIFT-like 4000 x 128 each,
+    32 640 image pairs) sharded over the ranks by ShardedMatcher (descriptor sets replicated, pair blocks dealt out, one batched
+    launch per chunk, survivor counts all-reduced), and the extrapolation to the 2000-image set (1 999 000 pairs)."""
+    torch, dist, mb, dev, args = ctx["torch"], ctx["dist"], ctx["mb"], ctx["dev"], ctx["args"]
+    world, rank = ctx["world"], ctx["rank"]
+    from mosaicking_b200.distributed import ShardedMatcher
+    nimg, nkp = 256, 4000
+    rng = np.random.default_rng(5)
+    base = make_sift_like(2, nkp, 77)
+    sets = []
+    for i in range(nimg):
+        s = base[i % 2].copy()
+        idx = rng.integers(0, nkp, nkp // 4)
+        s[idx] = np.clip(s[idx] + rng.integers(-3, 4, (len(idx), 128)), 0, 255)
+        sets.append(s[rng.permutation(nkp)])
+    sm = ShardedMatcher(mb.Matcher(norm="l2", device=dev), dev)
+    sm.match_all_pairs(sets[:32], RATIO)                  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    _, counts = sm.match_all_pairs(sets, RATIO)
+    barrier()
+    s = max_over_ranks(time.perf_counter() - t0)
+    npairs = nimg * (nimg - 1) // 2
+    return {"workload": f"BASELINE configs[4] sample: all pairs of {nimg} keyframes x SIFT-like {nkp}x128 (L2, tcgen05 GEMM), {npairs} image pairs over {world} GPUs",
+            "seconds": s, "image_pairs_per_s": npairs / s, "descriptor_pairs_per_s": npairs * nkp * nkp / s,
+            "tflops_bf16_gemm_incl_upload_and_epilogue": 2.0 * npairs * nkp * nkp * 128 / s / 1e12,
+            "extrapolated_seconds_for_2000_images": 1999000 / (npairs / s), "survivor_counts_checksum": int(counts.sum()),
+            "note": "wall clock incl. the upload of the 256 descriptor sets (replicated on every rank) and the all_reduce of the count matrix; max over ranks"}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle/ may be executed here and only here)
 # ------------------------------------------------------------------------------------------------
-def cpu_step_runner(fw, fh):
+def cpu_sample(frame, H, q, t, norm: str, budget_s: float, what: str) -> dict:
+    """The reference's CPU path on a bounded sample: cv2.BFMatcher + ratio + Mapper._update_cpu restated over cv2/numpy
+    (oracle/cv_ref.py), all host threads, full-size canvas."""
     import cv2
 
     from oracle import cv_ref
-    matcher = cv_ref.RefMatcher(cv2.NORM_HAMMING)
+    matcher = cv_ref.RefMatcher(cv2.NORM_HAMMING if norm == "hamming" else cv2.NORM_L2)
     mapper = cv_ref.RefMapper(CANVAS, CANVAS, alpha_blend=ALPHA, flags=cv2.INTER_LINEAR)
-
-    def step(frame, H, q, t):
-        good = cv_ref.lowe_ratio(matcher.knn_match(q, t), RATIO)
-        mapper.update(frame, H)
-        return len(good)
-    return step, cv2.getNumThreads()
-
-
-def cpu_baseline(frames, Hs, desc_h, fw, fh, W, budget_s: float) -> dict:
-    """The reference's CPU path (cv2.BFMatcher + warpPerspective + numpy blending, oracle/cv_ref.py) on a
-    bounded sample of the same workload: the first frames of the same sequence, same 16384^2 canvas."""
-    step, threads = cpu_step_runner(fw, fh)
-    n, t_total = 0, 0.0
+    n, t_total, t_match = 0, 0.0, 0.0
     while n < 3 and (n == 0 or t_total + t_total / n < budget_s):
-        f = frames[W + n].cpu().numpy()
         t0 = time.perf_counter()
-        step(f, Hs[W + n], desc_h[W + n + 1], desc_h[W + n])
-        t_total += time.perf_counter() - t0
+        good = cv_ref.lowe_ratio(matcher.knn_match(q, t), RATIO)
+        t1 = time.perf_counter()
+        mapper.update(frame, H)
+        t2 = time.perf_counter()
+        t_total += t2 - t0; t_match += t1 - t0
         n += 1
-    return {"value": n / t_total, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{n} frame(s) of the same sequence through oracle/cv_ref.py (cv2 {__import__('cv2').__version__} BFMatcher NORM_HAMMING "
-                      f"+ ratio, Mapper._update_cpu restated over cv2/numpy with INTER_LINEAR) on the full 16384^2 canvas; "
-                      f"{os.cpu_count()} host cpus, cv2 threads {threads}"}
+    return {"value": n / t_total, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "port",
+            "match_s_per_frame": t_match / n, "warp_blend_s_per_frame": (t_total - t_match) / n,
+            "sample": f"{n} frame(s): {what}; oracle/cv_ref.py over cv2 {cv2.__version__}; {os.cpu_count()} host cpus, cv2 threads {cv2.getNumThreads()}"}
+
+
+def cpu_baseline(ctx, Hs, desc_h, fw, fh, W, budget_s: float) -> dict:
+    torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
+    frame = frames_along(torch, mb, dev, [Hs[W]], fw, fh, 7, args.black)[0].cpu().numpy()
+    return cpu_sample(frame, Hs[W], desc_h[W + 1], desc_h[W], "hamming", budget_s,
+                      "BASELINE configs[1]: cv2.BFMatcher(NORM_HAMMING) 5000x5000x32B + ratio, Mapper._update_cpu restated over cv2/numpy (INTER_LINEAR) "
+                      "with one 1920x1080 frame of the same sequence on the full 16384^2 canvas")
+
+
+def reference_classes():
+    """The UNMODIFIED reference (pip-installed into baseline/_ref, pure Python over cv2) when it is present: its own
+    registration.Matcher / mosaic.Mapper.  -> (Matcher, Mapper, 'reference') or (None, None, why)."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "mosaicking" / "mosaic.py").exists():
+        return None, None, "baseline/_ref is absent"
+    try:
+        from oracle import ref_shim
+        reg, mos = ref_shim.import_reference(ref)
+        return reg.Matcher, mos.Mapper, "reference"
+    except Exception as ex:                                   # e.g. a dependency of the reference missing on this box
+        return None, None, f"baseline/_ref does not import here: {ex!r}"[:300]
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (the cv2 + numpy restatement in
-    oracle/cv_ref.py; the reference itself is pure Python over cv2 and is absent on the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path.  With baseline/_ref present (the unmodified
+    reference, pure Python over cv2) the step runs its own classes through their public API and stock code path:
+    registration.Matcher().knn_match (cv2.BFMatcher NORM_L2, registration.py:230-242) + the ratio comprehension of
+    mosaic.py:430 + mosaic.Mapper(16384, 16384, alpha_blend=0.5).update (INTER_CUBIC as shipped, mosaic.py:111-138).
+    Otherwise the cv2 + numpy restatement in oracle/cv_ref.py (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch  # only for the synthetic frames (CPU tensors)
+    import cv2
 
     K, W = args.steps, args.warmup
     fw, fh = 1920, 1080
     rng = np.random.default_rng(7)
     base = rng.integers(1, 256, (fh // 8 + 2, fw // 8 + 2, 3), dtype=np.uint8)
-    import cv2
     frame0 = np.clip(cv2.resize(base, (fw, fh), interpolation=cv2.INTER_CUBIC), 1, 255).astype(np.uint8)
     desc_h = make_descriptors(4, 11)
-    step, threads = cpu_step_runner(fw, fh)
+    RefMatcher, RefMapper, kind = reference_classes()
+    if RefMatcher is not None:
+        matcher, mapper = RefMatcher(), RefMapper(CANVAS, CANVAS, alpha_blend=ALPHA)
+        def step(frame, H, q, t):
+            matches = matcher.knn_match(q, t)
+            good = tuple(m[0] for m in matches if len(m) == 2 and m[0].distance < 0.7 * m[1].distance)      # mosaic.py:430
+            mapper.update(frame, H)
+            return len(good)
+        threads = cv2.getNumThreads()
+        how = ("UNMODIFIED reference from baseline/_ref: mosaicking.registration.Matcher().knn_match (cv2.BFMatcher NORM_L2 on the descriptor bytes, its own metric) "
+               "+ ratio comprehension + mosaicking.mosaic.Mapper.update (INTER_CUBIC as shipped)")
+    else:
+        from oracle import cv_ref
+        m2, mp2 = cv_ref.RefMatcher(cv2.NORM_HAMMING), cv_ref.RefMapper(CANVAS, CANVAS, alpha_blend=ALPHA, flags=cv2.INTER_LINEAR)
+        def step(frame, H, q, t):
+            good = cv_ref.lowe_ratio(m2.knn_match(q, t), RATIO)
+            mp2.update(frame, H)
+            return len(good)
+        threads = cv2.getNumThreads()
+        how = f"oracle/cv_ref.py = reference glue restated over cv2 + numpy ({kind})"
+        kind = "port"
     budget = args.cpu_budget_ref
     times = []
     n_warm = min(W, 1)          # one untimed frame (first-touch of the 1.3 GB canvas); more would only burn the budget
@@ -718,11 +1167,11 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "mosaic frames/s (kNN-2 match + fused warp+blend per frame)", "value": value, "unit": "frames/s",
            "n_gpus": args.gpus, "steps": len(times), "warmup": n_warm, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1]: 1920x1080 frames, 5000x32B Hamming kNN k=2 + ratio 0.7, Mapper._update_cpu (INTER_LINEAR, alpha=0.5) "
+           "config": {"workload": "BASELINE configs[1]: 1920x1080 frames, 5000x32B descriptors kNN k=2 + ratio 0.7, Mapper.update (alpha=0.5) "
                                   "into a 16384x16384 canvas; CPU, rank 0 only",
-                      "requested_steps": K, "bounded_by_seconds": budget},
-           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                            "sample": f"{len(times)} full frame(s); oracle/cv_ref.py = reference glue restated over cv2 {cv2.__version__} + numpy"},
+                      "requested_steps": K, "bounded_by_seconds": budget, "how": how},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind,
+                            "sample": f"{len(times)} full frame(s) of the workload; cv2 {cv2.__version__}, {os.cpu_count()} host cpus, cv2 threads {threads}"},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -738,7 +1187,8 @@ def main():
     ap.add_argument("--hamming-engine", default="auto", choices=["auto", "popc", "tensor"],
                     help="auto/tensor: tcgen05 fp8 GEMM on bit-expanded rows when large enough (bit-identical); popc: XOR+POPC kernel")
     ap.add_argument("--sm-partition", type=int, default=40,
-                    help="give matching its own group of at least this many SMs (green contexts) and compositing the rest; 0 = two ordinary streams")
+                    help="N=1 only: ALSO time the step with matching in its own group of at least this many SMs (green contexts), reported "
+                         "under sm_partition_variant; the headline always uses two ordinary streams; 0 = skip the variant")
     ap.add_argument("--no-feather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)

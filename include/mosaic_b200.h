@@ -56,6 +56,11 @@ typedef enum mk_blend {
     MK_BLEND_FEATHER = 1  /* analytic feather weights + fp32 weight plane (extension) */
 } mk_blend;
 
+typedef enum mk_model {
+    MK_MODEL_AFFINE = 0,      /* cv2.estimateAffine2D: 6 degrees of freedom, 3-point samples      */
+    MK_MODEL_PERSPECTIVE = 1  /* cv2.findHomography:   8 degrees of freedom, 4-point samples      */
+} mk_model;
+
 int mk_abi_version(void);
 const char *mk_version_string(void);
 const char *mk_last_error(void);
@@ -182,6 +187,32 @@ int mk_stream_follow(void *event, void *src_stream, void *dst_stream);
 int mk_sm_partition_create(int min_sms_first, void **partition, void **stream_first, void **stream_rest, int *sms_first,
                            int *sms_rest);
 void mk_sm_partition_destroy(void *partition);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-side registration glue: what the reference does on the host between matching and
+ * compositing.  All pointers are DEVICE pointers unless named *_host; asynchronous on `stream`.
+ *
+ * mk_gather_matches   SequentialMosaic.registration (src/mosaicking/mosaic.py:449-457): the keypoints of the ratio-test
+ *   survivors in match order, src = kp_query[i] ("kp", the later frame), dst = kp_train[idx[i][0]] ("kp_prev").
+ *   kp_* are float32 (x, y) pairs; idx / keep are mk_knn2's outputs; out_* hold up to nq rows; out_query (may be NULL)
+ *   receives the query index of every gathered pair; count int32[1].
+ * mk_ransac_transform HomographyEstimation.__call__ (src/mosaicking/registration.py:399-419) as called at mosaic.py:459:
+ *   cv2.findHomography(src, dst, RANSAC, thresh) for MK_MODEL_PERSPECTIVE, cv2.estimateAffine2D(src, dst, RANSAC, thresh)
+ *   for MK_MODEL_AFFINE.  `iters` hypotheses are scored in parallel (cv2's default cap is 2000), the best one is re-fitted
+ *   to its inliers.  H_out double[9] row-major (affine: last row 0 0 1; all zeros when no model was found, where cv2
+ *   returns None), inliers uint8[n] (0/1, the winning hypothesis' inliers like cv2's mask), n_inliers int32[1].
+ *   workspace: mk_ransac_workspace_bytes() bytes, 8-byte aligned.  n_dev is reserved and must be NULL.
+ *   Randomised like cv2's: results agree with cv2 up to points within rounding of the threshold (tests state the bounds).
+ * mk_chain_homographies  core/interface.py:97-113 (_propagate_homographies): H_abs[0] = H[0], H_abs[k] = H_abs[k-1] @ H[k],
+ *   n row-major 3x3 float64 matrices, left to right like itertools.accumulate(H, np.matmul).
+ * ------------------------------------------------------------------------------------- */
+int mk_gather_matches(const float *kp_query, const float *kp_train, const int32_t *idx, const uint8_t *keep, int nq,
+                      float *out_src, float *out_dst, int32_t *out_query, int32_t *count, void *stream);
+size_t mk_ransac_workspace_bytes(void);
+int mk_ransac_transform(int model, const float *src_xy, const float *dst_xy, int n, const int32_t *n_dev, double thresh,
+                        int iters, uint64_t seed, double *H_out, uint8_t *inliers, int32_t *n_inliers, void *workspace,
+                        void *stream);
+int mk_chain_homographies(const double *H, int n, double *H_abs, void *stream);
 
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */

@@ -25,7 +25,9 @@ EXPORTS = (
     "mk_knn2_workspace_bytes", "mk_knn2_uses_tensor_cores", "mk_knn2", "mk_knn2_batched_workspace_bytes", "mk_knn2_batched",
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
     "mk_event_create", "mk_event_destroy", "mk_stream_follow", "mk_sm_partition_create", "mk_sm_partition_destroy",
+    "mk_gather_matches", "mk_ransac_workspace_bytes", "mk_ransac_transform", "mk_chain_homographies",
 )
+MODEL_AFFINE, MODEL_PERSPECTIVE = 0, 1
 
 
 class MosaicB200Error(RuntimeError):
@@ -91,6 +93,13 @@ def lib() -> C.CDLL:
     L.mk_sm_partition_destroy.argtypes = [vp]
     L.mk_mapper_footprint.restype = i32
     L.mk_mapper_footprint.argtypes = [i32, i32, i32, i32, vp, i32, vp]
+    L.mk_gather_matches.restype = i32
+    L.mk_gather_matches.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.mk_ransac_workspace_bytes.restype = sz
+    L.mk_ransac_transform.restype = i32
+    L.mk_ransac_transform.argtypes = [i32, vp, vp, i32, vp, f64, i32, C.c_uint64, vp, vp, vp, vp, vp]
+    L.mk_chain_homographies.restype = i32
+    L.mk_chain_homographies.argtypes = [vp, i32, vp, vp]
     if L.mk_abi_version() != 1:
         raise MosaicB200Error("libmosaic_b200 ABI version mismatch")
     _lib = L

@@ -1,0 +1,585 @@
+// mk_strip.cu -- K4s: persistent strip form of the fused warp + erode + blend + mask pass (one Mapper.update,
+// src/mosaicking/mosaic.py:159-172 -> _update_cpu :111-138), the kernel mk_mapper_update launches whenever it applies
+// (alpha blend, no keypoint ROI, 16-byte aligned source, moderate minification).  Same per-pixel arithmetic as the
+// tile-per-CTA kernel in mk_mapper.cu (which stays the general fallback), different work decomposition:
+//
+//   * the visited canvas rectangle is cut into column strips 64 px wide = OpenCV's warpPerspective coordinate blocks;
+//     the host clips the forward-mapped frame quad against every strip, so only rows the frame can reach are work;
+//   * the rows of all strips form one flat list of 16-row chunks that is dealt out evenly to a persistent grid
+//     (<= 4 CTAs per SM): every CTA walks DOWN its part of a strip, so the 2-row erosion halo above a chunk is the
+//     tail of the previous chunk (kept in 32-row rings of warped pixels and validity bit-rows) instead of being
+//     re-warped, and the per-tile set-up is amortised;
+//   * every transfer is a 2-D TMA box (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG): the source rectangle of chunk
+//     j+2 and the canvas + mask tile of chunk j+1 are in flight while chunk j is computed (two mbarrier-tracked
+//     buffers each); out-of-frame source bytes and out-of-canvas tile bytes are the TMA's zero fill / clipping, which
+//     is exactly BORDER_CONSTANT(0) and the canvas edge handling;
+//   * phase 1 handles two rows per warp iteration (two independent dependency chains per thread);
+//   * phase 2 works on the packed BGR words: byte-mask selects, and for alpha = 0.5 (the Mapper default), 0 and 1 the
+//     blend itself is word arithmetic -- rint(fmaf(c, .5, w * .5)) == round-half-even((c + w) / 2) exactly.
+#include "mk_mapper_common.cuh"
+
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <mutex>
+#include <type_traits>
+
+namespace mk {
+
+constexpr int CH = 16;               // canvas rows finalised per chunk
+constexpr int BR = CH + 2 * HALO;    // rows of the first phase-1 block of a segment
+constexpr int RING = 32;             // ring of warped rows / bit rows, indexed by (canvas row & 31)
+constexpr int STHREADS = 256;
+constexpr int MAX_STRIPS = 200;
+constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
+constexpr int STRIP_OCC = 4;         // CTAs per SM the register budget is set for
+
+struct StripParams {
+    const short *cubic;
+    const uint2 *lut;
+    int Hc, Wc;
+    int tx0;                // first strip (units of 64 px)
+    int nstrips, nchunks, chunks_per_cta;
+    int boxW, boxR;         // source box: bytes per row (multiple of 16), rows
+    int esz_shift;          // source tensor map element: 0 = uint8, 2 = uint32 (rows wider than 256 bytes)
+    float alpha, beta;
+    uint32_t magic;
+    int blend_mode;         // 0 general alpha, 1 alpha == 0.5, 2 alpha == 1 (keep canvas), 3 alpha == 0 (take frame)
+    FrameDesc f;
+    int4 rows[MAX_STRIPS + 1]; // .x/.y: [ylo, yhi) of every strip (ylo >= yhi: the frame does not reach it), .z: chunks in the strips before it
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// mbarrier wait that traps instead of hanging the GPU if a transfer never completes (bad tensor map, lost transaction)
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, int what = 0)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+#ifdef MK_STRIP_DEBUG
+    if ((threadIdx.x & 31) == 0) printf("strip kernel: wait timeout block %d warp %d what %d parity %u\n", blockIdx.x, threadIdx.x >> 5, what, parity);
+    return;
+#endif
+    __trap();
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// INTER_LINEAR from the staged box, no containment test (see sample_linear_c3_smem_fast); `base` = shared address of the box
+__device__ __forceinline__ uint32_t sample_linear_box(uint32_t base, int pitch, int sy0, int bx0, int X, int Y, const uint2 *__restrict__ lut)
+{
+    const int r = (Y >> 5) - sy0, cb = (X >> 5) * 3 - bx0;
+    const uint2 wt = __ldg(lut + ((Y & 31) * 32 + (X & 31)));
+    const uint32_t a = base + r * pitch + (cb & ~3), b = a + pitch;
+    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint32_t a0 = lds32(a), a1 = lds32(a + 4), a2 = lds32(a + 8), b0 = lds32(b), b1 = lds32(b + 4), b2 = lds32(b + 8);
+    return lerp3_dp2a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
+                      __funnelshift_r(b1, b2, sh), wt);
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(STHREADS, STRIP_OCC)
+mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_cv,
+                    const __grid_constant__ CUtensorMap map_mk, const __grid_constant__ StripParams p)
+{
+    __shared__ __align__(128) uint8_t s_canvas[2][CH][ROWB];
+    __shared__ __align__(128) uint8_t s_mask[2][CH][TW];
+    __shared__ __align__(16) uint32_t s_warp[RING][TW];
+    __shared__ __align__(16) double s_row[2][3][BR][4];     // X0, Y0, W0 of the left / centre / right coordinate block, two blocks in flight
+    __shared__ unsigned long long s_m0[RING];
+    __shared__ unsigned long long s_h[RING];
+    __shared__ unsigned long long s_v[CH];
+    __shared__ uint8_t s_side[RING][4];
+    __shared__ __align__(8) unsigned long long s_bar_src[2];
+    __shared__ __align__(8) unsigned long long s_bar_cv[2];
+    __shared__ int s_tile[2][4];                // per source buffer: sy0, bx0, staged?
+    __shared__ __align__(16) int4 s_blk[MAX_CHUNKS];     // per chunk of this CTA: tileX, first finalised row, first phase-1 row, phase-1 rows
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FrameDesc &F = p.f;
+    const int boxbytes = p.boxW * p.boxR;                 // bytes one TMA box delivers
+    const int boxstride = (boxbytes + 127) & ~127;        // TMA destinations are 128-byte aligned
+    const uint32_t src_base = (smem_u32(s_dyn) + 127u) & ~127u;
+
+    // ---- chunks [c0, c1) of the flat list belong to this CTA: strip (binary search in the host's prefix sums) and rows ----
+    const int c0 = (int)blockIdx.x * p.chunks_per_cta, n = min(p.nchunks, c0 + p.chunks_per_cta) - c0;
+    if (n <= 0) return;
+    if (tid < n) {
+        const int c = c0 + tid;
+        int lo = 0, hi = p.nstrips;      // rows[lo].z <= c < rows[hi].z
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.rows[mid].z <= c) lo = mid; else hi = mid;
+        }
+        const int q = c - p.rows[lo].z, fy = p.rows[lo].x + q * CH;
+        const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
+        s_blk[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
+    }
+    if (tid == 128) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); }
+    __syncthreads();
+
+    // ---- source box of a block: quantised images of the four corners of the haloed block (columns tileX-2 .. tileX+65)
+    //      bound every tap of the block as long as W keeps its sign; one warp, result in s_tile[buf], TMA issued by lane 0 ----
+    auto stage_src = [&](int j, int buf) {
+        const int4 blk = s_blk[j];
+        const int tileX = blk.x, first = blk.z, nr = blk.w;
+        int X = 0, Y = 0, sg = 0;
+        if (lane < 4) {
+            const int x0 = (lane & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (lane & 1) ? HALO - 1 : BLOCK_W - HALO;
+            const int y = (lane & 2) ? min(first + nr - 1, p.Hc - 1) : max(first, 0);
+            double X0, Y0, W0;
+            row_base(F.M, x0, y, X0, Y0, W0);
+            const double dx1 = (double)x1;
+            quantize(F.M, X0, Y0, W0, dmul(F.M.m[0], dx1), dmul(F.M.m[3], dx1), dmul(F.M.m[6], dx1), X, Y);
+            const double W = F.M.affine ? F.M.m[8] : dadd(W0, dmul(F.M.m[6], dx1));
+            const bool sane = abs(X) < (1 << 30) && abs(Y) < (1 << 30);
+            sg = !sane ? 0 : ((W > 0.0) ? 1 : ((W < 0.0) ? -1 : 0));
+        }
+        int xlo = X, xhi = X, ylo = Y, yhi = Y, smin = sg, smax = sg;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+            ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+            smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        }
+        if (lane == 0) {
+            constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;   // tap reach + 1 px safety ring
+            const int sx_lo = (xlo >> 5) - LO, sx_hi = (xhi >> 5) + HI, sy_lo = (ylo >> 5) - LO, sy_hi = (yhi >> 5) + HI;
+            const int bx0 = (sx_lo * 3) & ~15;      // the TMA needs a 16-byte aligned global start address
+            const bool convex = smin == smax && smin != 0;
+            const bool fits = convex && (sx_hi * 3 + 3 - bx0) <= p.boxW && (sy_hi - sy_lo + 1) <= p.boxR;
+            s_tile[buf][0] = sy_lo; s_tile[buf][1] = bx0; s_tile[buf][2] = fits ? 1 : 0;
+            mbar_arrive_expect_tx(&s_bar_src[buf], fits ? (uint32_t)boxbytes : 0u);
+            if (fits) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, bx0 >> p.esz_shift, sy_lo, &s_bar_src[buf]);
+        }
+    };
+    auto load_canvas = [&](int j, int cb) {      // one thread
+        const int4 blk = s_blk[j];
+        mbar_arrive_expect_tx(&s_bar_cv[cb], (uint32_t)(CH * ROWB + CH * TW));
+        tma_load_2d(smem_u32(&s_canvas[cb][0][0]), &map_cv, blk.x * 3, blk.y, &s_bar_cv[cb]);
+        tma_load_2d(smem_u32(&s_mask[cb][0][0]), &map_mk, blk.x, blk.y, &s_bar_cv[cb]);
+    };
+    // per-row coordinate bases of block j for the left / centre / right 64-px blocks; 60 threads (idx)
+    auto row_bases = [&](int j, int idx) {
+        const int4 blk = s_blk[j];
+        const int b = idx / BR, r = idx - b * BR;
+        if (b < 3 && r < blk.w) {
+            double X0, Y0, W0;
+            row_base(F.M, blk.x + (b - 1) * BLOCK_W, blk.z + r, X0, Y0, W0);
+            double *d = s_row[j & 1][b][r];
+            d[0] = X0; d[1] = Y0; d[2] = W0;
+        }
+    };
+
+    if (warp == 0) {
+        stage_src(0, 0);
+        if (n > 1) stage_src(1, 1);
+    } else if (warp == 2 || warp == 3) {
+        row_bases(0, tid - 64);
+    } else if (tid == 128) {
+        load_canvas(0, 0);
+    }
+    __syncthreads();
+
+    const int half = warp & 1, cx = half * 32 + lane;
+    const double dx1 = (double)cx;
+    const double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
+    const uint32_t warp_base = smem_u32(&s_warp[0][0]) + (uint32_t)cx * 4u;
+    const uint32_t m0_base = smem_u32(&s_m0[0]) + (uint32_t)half * 4u;
+
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const int buf = j & 1;
+        const int4 blk = s_blk[j];
+        const int tileX = blk.x, fy = blk.y, first = blk.z, nr = blk.w;
+
+        if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf], (uint32_t)(j >> 1) & 1u, 100 + j);
+        __syncwarp();
+        const int sy0 = s_tile[buf][0], bx0 = s_tile[buf][1];
+        const bool staged = s_tile[buf][2] != 0;
+        const uint32_t box = src_base + (uint32_t)(buf * boxstride);
+        SrcTile T;
+        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + buf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
+
+        // ---- phase 1, lanes = consecutive columns, two rows per iteration ----------------------------
+        {
+            const bool xvalid = tileX + cx < p.Wc;
+            const int r_lo = max(0, -first), r_hi = min(nr, p.Hc - first);    // block rows inside the canvas
+            if (r_lo > 0 || r_hi < nr) {      // rows outside the canvas count as set (cv2.erode's default border)
+                for (int r = warp >> 1; r < nr; r += 4)
+                    if ((r < r_lo || r >= r_hi) && lane == 0) reinterpret_cast<uint32_t *>(&s_m0[(first + r) & (RING - 1)])[half] = ~0u;
+            }
+            const uint32_t rowb = smem_u32(&s_row[buf][1][0][0]);
+            auto finish_row = [&](int r, uint32_t px) {
+                const unsigned bal = __ballot_sync(0xffffffffu, xvalid ? (px != 0u) : true);   // columns outside the canvas count as set
+                const uint32_t ri = (uint32_t)(first + r) & (RING - 1);
+                if (lane == 0) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(m0_base + ri * 8u), "r"(bal) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(warp_base + ri * (TW * 4)), "r"(px) : "memory");
+            };
+            auto body = [&](auto fast_tag, auto affine_tag) {
+                constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
+                const double wr = F.M.wr;
+                auto one = [&](int r) -> uint32_t {
+                    double X0, Y0, W0 = 0.0;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(X0), "=d"(Y0) : "r"(rowb + (uint32_t)r * 32u));
+                    if constexpr (!AFF) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(W0) : "r"(rowb + (uint32_t)r * 32u + 16u));
+                    int X, Y;
+                    if constexpr (FAST) quantize_fast_t<AFF>(F.M, wr, X0, Y0, W0, mx, my, mw, X, Y);
+                    else quantize(F.M, X0, Y0, W0, mx, my, mw, X, Y);
+                    if constexpr (FAST && INTERP == 1) return sample_linear_box(box, p.boxW, sy0, bx0, X, Y, p.lut);
+                    else return sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
+                };
+                int r = r_lo + (warp >> 1);
+#pragma unroll 1
+                for (; r + 4 < r_hi; r += 8) {
+                    uint32_t pa = 0, pb = 0;
+                    if (xvalid) { pa = one(r); pb = one(r + 4); }
+                    finish_row(r, pa); finish_row(r + 4, pb);
+                }
+                if (r < r_hi) {
+                    uint32_t pa = 0;
+                    if (xvalid) pa = one(r);
+                    finish_row(r, pa);
+                }
+            };
+            if (staged) {
+                if (F.M.affine) body(std::true_type{}, std::true_type{});
+                else body(std::true_type{}, std::false_type{});
+            } else {
+                body(std::false_type{}, std::false_type{});
+            }
+        }
+        // ---- phase 1b: the 2 + 2 side-halo columns (they live in the neighbouring coordinate blocks) ------
+        if (tid < nr * 4) {
+            const int r = tid >> 2, cc = tid & 3, y = first + r;
+            const int x = (cc < 2) ? tileX - HALO + cc : tileX + TW + (cc - 2);
+            const int b = (cc < 2) ? 0 : 2, x1 = (cc < 2) ? BLOCK_W - HALO + cc : cc - 2;
+            uint32_t mv = 255;
+            if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
+                const double d1 = (double)x1;
+                const double *rb = s_row[buf][b][r];
+                int X, Y;
+                quantize(F.M, rb[0], rb[1], rb[2], dmul(F.M.m[0], d1), dmul(F.M.m[3], d1), dmul(F.M.m[6], d1), X, Y);
+                mv = sample_c3_tile<INTERP>(staged, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
+            }
+            s_side[y & (RING - 1)][cc] = (uint8_t)mv;
+        }
+        __syncthreads();                                                             // D
+
+        // ---- between the phases, one job per warp: source box of chunk j+2 (its buffer is free now), horizontal + vertical
+        //      erosion of the new rows, coordinate bases of chunk j+1, canvas + mask tile of chunk j+1 --------------------
+        if (warp == 0) {
+            if (j + 2 < n) stage_src(j + 2, buf);
+        } else if (warp == 1) {
+            if (lane < nr) {
+                const int ri = (first + lane) & (RING - 1);
+                const unsigned long long m = s_m0[ri];
+                const unsigned long long l2 = s_side[ri][0] ? 1ull : 0ull, l1 = s_side[ri][1] ? 1ull : 0ull;
+                const unsigned long long r1 = s_side[ri][2] ? 1ull : 0ull, r2 = s_side[ri][3] ? 1ull : 0ull;
+                const unsigned long long sl1 = (m << 1) | l1, sl2 = (m << 2) | (l1 << 1) | l2;
+                const unsigned long long sr1 = (m >> 1) | (r1 << 63), sr2 = (m >> 2) | (r1 << 62) | (r2 << 63);
+                s_h[ri] = m & sl1 & sl2 & sr1 & sr2;
+            }
+            __syncwarp();
+            if (lane < CH) {
+                const int y = fy + lane;
+                s_v[lane] = s_h[(y - 2) & (RING - 1)] & s_h[(y - 1) & (RING - 1)] & s_h[y & (RING - 1)] & s_h[(y + 1) & (RING - 1)] &
+                            s_h[(y + 2) & (RING - 1)];
+            }
+        } else if (warp == 2 || warp == 3) {
+            if (j + 1 < n) row_bases(j + 1, tid - 64);
+        } else if (tid == 128) {
+            if (j + 1 < n) {
+                bulk_wait_read0();                    // the store of chunk j-1 has read its buffer
+                load_canvas(j + 1, buf ^ 1);
+            }
+        }
+        __syncthreads();                                                             // E
+
+        // ---- phase 2: thread = 4 consecutive pixels = 3 packed BGR words ---------------------------
+        unsigned mb;
+        {
+            const int r = tid >> 4, g = tid & 15;
+            const unsigned long long v = s_v[r];
+            const uint32_t vw = (g & 8) ? (uint32_t)(v >> 32) : (uint32_t)v;
+            mb = (vw >> (4 * (g & 7))) & 15u;
+            if (lane == 0) mbar_wait_or_trap(&s_bar_cv[buf], (uint32_t)(j >> 1) & 1u, 200 + j);
+            __syncwarp();
+            if (mb) {
+                uint32_t *cw = reinterpret_cast<uint32_t *>(&s_canvas[buf][r][12 * g]);
+                uint32_t *ms = reinterpret_cast<uint32_t *>(&s_mask[buf][r][4 * g]);
+                const uint32_t c0w = cw[0], c1w = cw[1], c2w = cw[2], mk4 = *ms;
+                const uint4 wv = *reinterpret_cast<const uint4 *>(&s_warp[(fy + r) & (RING - 1)][4 * g]);
+                const uint32_t W0 = __byte_perm(wv.x, wv.y, 0x4210), W1 = __byte_perm(wv.y, wv.z, 0x5421), W2 = __byte_perm(wv.z, wv.w, 0x6542);
+                // per-pixel byte masks: valid (eroded mask bit), old (canvas mask byte > 1, mosaic.py:123)
+                const uint32_t Mv = ((mb * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t t = mk4 & 0xFEFEFEFEu;
+                const uint32_t Mo = (((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u) >> 7) * 0xFFu;
+                uint32_t B0, B1, B2;
+                if (p.blend_mode == 1) {            // alpha = 0.5: round-half-even of (c + w) / 2 on four bytes at a time
+                    auto avg = [](uint32_t a, uint32_t b) {
+                        const uint32_t x = a ^ b, h = (a & b) + ((x & 0xFEFEFEFEu) >> 1);
+                        return h + (x & h & 0x01010101u);
+                    };
+                    B0 = avg(c0w, W0); B1 = avg(c1w, W1); B2 = avg(c2w, W2);
+                } else if (p.blend_mode == 2) {     // fmaf(c, 1, w * 0) == c
+                    B0 = c0w; B1 = c1w; B2 = c2w;
+                } else if (p.blend_mode == 3) {     // fmaf(c, 0, w * 1) == w
+                    B0 = W0; B1 = W1; B2 = W2;
+                } else {
+                    B0 = c0w; B1 = c1w; B2 = c2w;
+                    const uint32_t need = Mv & Mo;
+                    if (need) {
+                        const uint32_t px0 = c0w & 0xFFFFFFu, px1 = (c0w >> 24) | ((c1w & 0xFFFFu) << 8),
+                                       px2 = (c1w >> 16) | ((c2w & 0xFFu) << 16), px3 = c2w >> 8;
+                        const uint32_t ab = __float_as_uint(p.alpha), bb = __float_as_uint(p.beta);
+                        const unsigned long long a2 = pack2(ab, ab), b2 = pack2(bb, bb);
+                        uint32_t b0 = px0, b1 = px1, b2r = px2, b3 = px3;
+                        if (need & 0x0000FFFFu) blend_pair(px0, px1, wv.x, wv.y, a2, b2, p.magic, b0, b1);
+                        if (need & 0xFFFF0000u) blend_pair(px2, px3, wv.z, wv.w, a2, b2, p.magic, b2r, b3);
+                        B0 = __byte_perm(b0, b1, 0x4210); B1 = __byte_perm(b1, b2r, 0x5421); B2 = __byte_perm(b2r, b3, 0x6542);
+                    }
+                }
+                // result = valid ? (old ? blend : warped) : canvas, per pixel, on the 12 bytes of the group
+                const uint32_t Ev0 = __byte_perm(Mv, Mv, 0x1000), Ev1 = __byte_perm(Mv, Mv, 0x2211), Ev2 = __byte_perm(Mv, Mv, 0x3332);
+                const uint32_t Eo0 = __byte_perm(Mo, Mo, 0x1000), Eo1 = __byte_perm(Mo, Mo, 0x2211), Eo2 = __byte_perm(Mo, Mo, 0x3332);
+                const uint32_t n0 = (Eo0 & B0) | (~Eo0 & W0), n1 = (Eo1 & B1) | (~Eo1 & W1), n2 = (Eo2 & B2) | (~Eo2 & W2);
+                cw[0] = (Ev0 & n0) | (~Ev0 & c0w);
+                cw[1] = (Ev1 & n1) | (~Ev1 & c1w);
+                cw[2] = (Ev2 & n2) | (~Ev2 & c2w);
+                *ms = mk4 | Mv;                                                     // mosaic.py:138
+                fence_proxy_async();
+            }
+        }
+        const int any = __syncthreads_or((int)mb);                                   // F
+        if (tid == 128 && any) {
+            tma_store_2d(&map_cv, tileX * 3, fy, smem_u32(&s_canvas[buf][0][0]));
+            tma_store_2d(&map_mk, tileX, fy, smem_u32(&s_mask[buf][0][0]));
+            bulk_commit();
+        }
+    }
+    if (tid == 128) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn strip_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(q);
+    });
+    return fn;
+}
+
+// 2-D map over a pitched byte image: dim0 bytes per row (in elements of esz bytes), dim1 rows; no swizzle, zero fill outside.
+static int encode_image_map(CUtensorMap *map, const void *base, int esz, long dim0_elems, long rows, size_t pitch, int box0_elems, int box_rows)
+{
+    struct Entry { const void *base; int esz, box0, box1; long d0, d1; size_t pitch; CUtensorMap map; };
+    static thread_local Entry cache[16];
+    static thread_local int next = 0;
+    for (const Entry &e : cache)
+        if (e.base == base && base && e.esz == esz && e.d0 == dim0_elems && e.d1 == rows && e.pitch == pitch && e.box0 == box0_elems && e.box1 == box_rows) {
+            *map = e.map;
+            return MK_OK;
+        }
+    EncodeTiledFn fn = strip_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return MK_ERR_CUDA; }
+    const cuuint64_t dims[2] = { (cuuint64_t)dim0_elems, (cuuint64_t)rows };
+    const cuuint64_t strides[1] = { (cuuint64_t)pitch };
+    const cuuint32_t box[2] = { (cuuint32_t)box0_elems, (cuuint32_t)box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = fn(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image) failed (%d)", (int)r); return MK_ERR_CUDA; }
+    Entry &slot = cache[next];
+    next = (next + 1) % 16;
+    slot.base = base; slot.esz = esz; slot.d0 = dim0_elems; slot.d1 = rows; slot.pitch = pitch; slot.box0 = box0_elems; slot.box1 = box_rows; slot.map = *map;
+    return MK_OK;
+}
+
+// [ymin, ymax] of the convex quad `pts` inside the vertical band xa <= x <= xb; false when the band misses it
+static bool quad_band_rows(const double pts[4][2], double xa, double xb, double &ymin, double &ymax)
+{
+    ymin = 1e300; ymax = -1e300;
+    auto take = [&](double y) { ymin = fmin(ymin, y); ymax = fmax(ymax, y); };
+    for (int i = 0; i < 4; ++i) {
+        const double *a = pts[i], *b = pts[(i + 1) & 3];
+        if (a[0] >= xa && a[0] <= xb) take(a[1]);
+        for (const double xc : { xa, xb }) {
+            if ((a[0] - xc) * (b[0] - xc) < 0.0) {           // edge crosses the line x = xc
+                const double t = (xc - a[0]) / (b[0] - a[0]);
+                take(a[1] + t * (b[1] - a[1]));
+            }
+        }
+    }
+    return ymin <= ymax;
+}
+
+template <int INTERP>
+static int strip_occupancy(int dyn_smem, int *occ)
+{
+    static std::mutex mu;
+    static int configured_dev = -1, configured_smem = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (configured_dev != dev || dyn_smem > configured_smem) {
+        const int want = std::max(dyn_smem, 48 * 1024);
+        MK_CUDA_TRY(cudaFuncSetAttribute(mapper_strip_kernel<INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        configured_dev = dev; configured_smem = want;
+    }
+    MK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, mapper_strip_kernel<INTERP>, STHREADS, (size_t)dyn_smem));
+    return MK_OK;
+}
+
+int launch_strip_update(const MapperParams &P, const double *H, int interp, const int32_t *rect, cudaStream_t st, bool *done)
+{
+    *done = false;
+    static const bool disabled = [] { const char *e = getenv("MK_STRIP"); return e && e[0] == '0'; }();
+    if (disabled) return MK_OK;
+    const FrameDesc &F = P.f0;
+    if (!F.src_aligned || F.roi) return MK_OK;
+    const int tx0 = rect[0] / TW, tx1 = (rect[2] + TW - 1) / TW, ns = tx1 - tx0;
+    if (ns <= 0 || ns > MAX_STRIPS) return MK_OK;
+    const InvMap &M = F.M;
+    // W must keep its sign over the visited rectangle (then every block maps to a convex quad and the frame quad is convex)
+    {
+        int sign = 0;
+        for (int i = 0; i < 4; ++i) {
+            const double x = (i & 1) ? rect[2] + 3.0 : rect[0] - 3.0, y = (i & 2) ? rect[3] + 3.0 : rect[1] - 3.0;
+            const double W = M.m[6] * x + M.m[7] * y + M.m[8];
+            const int sg = (W > 0) - (W < 0);
+            if (sg == 0 || (sign && sg != sign)) return MK_OK;
+            sign = sg;
+        }
+    }
+    // forward image of the source rectangle grown by the interpolation support (same construction as footprint())
+    double pts[4][2];
+    {
+        const double grow = (interp == MK_INTER_CUBIC) ? 3.0 : 2.0;
+        const double xs[4] = { -grow, (double)F.w - 1.0 + grow, (double)F.w - 1.0 + grow, -grow };
+        const double ys[4] = { -grow, -grow, (double)F.h - 1.0 + grow, (double)F.h - 1.0 + grow };
+        int sign = 0;
+        for (int i = 0; i < 4; ++i) {
+            const double X = H[0] * xs[i] + H[1] * ys[i] + H[2], Y = H[3] * xs[i] + H[4] * ys[i] + H[5], W = H[6] * xs[i] + H[7] * ys[i] + H[8];
+            const int sg = (W > 0) - (W < 0);
+            if (sg == 0 || (sign && sg != sign) || !isfinite(X) || !isfinite(Y) || !isfinite(W)) return MK_OK;
+            sign = sg;
+            pts[i][0] = X / W; pts[i][1] = Y / W;
+            if (!isfinite(pts[i][0]) || !isfinite(pts[i][1])) return MK_OK;
+        }
+    }
+    StripParams S{};
+    S.cubic = P.cubic; S.lut = P.lut; S.Hc = P.Hc; S.Wc = P.Wc; S.tx0 = tx0; S.nstrips = ns;
+    S.alpha = P.alpha; S.beta = P.beta; S.magic = P.magic; S.f = F;
+    S.blend_mode = (P.alpha == 0.5f && P.beta == 0.5f) ? 1 : (P.alpha == 1.0f && P.beta == 0.0f) ? 2 : (P.alpha == 0.0f && P.beta == 1.0f) ? 3 : 0;
+    long nchunks = 0;
+    for (int s = 0; s < ns; ++s) {
+        const double xa = (double)(tx0 + s) * TW - HALO - 3.0, xb = (double)(tx0 + s) * TW + TW + HALO + 2.0;
+        double ymin, ymax;
+        int ylo = 0, yhi = 0;
+        if (quad_band_rows(pts, xa, xb, ymin, ymax)) {
+            ylo = (int)fmax((double)rect[1], fmin((double)rect[3], floor(ymin) - 3.0));
+            yhi = (int)fmax((double)rect[1], fmin((double)rect[3], ceil(ymax) + 4.0));
+        }
+        S.rows[s] = make_int4(ylo, yhi, (int)nchunks, 0);
+        if (yhi > ylo) nchunks += (yhi - ylo + CH - 1) / CH;
+    }
+    S.rows[ns] = make_int4(0, 0, (int)nchunks, 0);
+    if (nchunks <= 0) { *done = true; return MK_OK; }
+    // source box: extents of the haloed 20-row block at probes over the visited region (plain double math; a block whose
+    // exact rectangle does not fit samples from global memory instead, so this only has to be a good estimate)
+    int boxW = 0, boxR = 0;
+    {
+        const int lohi = (interp == MK_INTER_CUBIC) ? 5 : 3;
+        double maxc = 0, maxr = 0;
+        for (int a = 0; a < 3; ++a) {
+            const int s = (a == 0) ? 0 : (a == 1) ? ns / 2 : ns - 1;
+            const int ylo = S.rows[s].x, yhi = S.rows[s].y;
+            if (yhi <= ylo) continue;
+            for (int b = 0; b < 3; ++b) {
+                const double y0 = (b == 0) ? ylo - HALO : (b == 1) ? (ylo + yhi) / 2 : std::max(ylo - HALO, yhi + HALO - BR);
+                const double x0 = (double)(tx0 + s) * TW - HALO;
+                double minu = 1e300, maxu = -1e300, minv = 1e300, maxv = -1e300;
+                for (int c = 0; c < 4; ++c) {
+                    const double x = x0 + ((c & 1) ? TW + 2 * HALO - 1 : 0), y = y0 + ((c & 2) ? BR - 1 : 0);
+                    const double W = M.m[6] * x + M.m[7] * y + M.m[8];
+                    const double u = (M.m[0] * x + M.m[1] * y + M.m[2]) / W, v = (M.m[3] * x + M.m[4] * y + M.m[5]) / W;
+                    minu = fmin(minu, u); maxu = fmax(maxu, u); minv = fmin(minv, v); maxv = fmax(maxv, v);
+                }
+                if (!isfinite(minu) || !isfinite(maxu) || !isfinite(minv) || !isfinite(maxv)) return MK_OK;
+                maxc = fmax(maxc, ceil(maxu - minu) + 2 + lohi); maxr = fmax(maxr, ceil(maxv - minv) + 2 + lohi);
+            }
+        }
+        maxc += ceil(maxc / 32); maxr += ceil(maxr / 32);      // slack for blocks between the probes (perspective)
+        if (maxc <= 0 || maxr <= 0 || maxc > 1000 || maxr > 256) return MK_OK;
+        boxW = (((int)maxc * 3 + 3 + 15) + 15) & ~15;      // + 15: the box starts at a 16-byte boundary
+        boxR = (int)maxr;
+    }
+    int esz = 1;
+    if (boxW > 256) {
+        if ((F.w & 3) != 0 || boxW > 1024) return MK_OK;
+        esz = 4;
+    }
+    const int boxbytes = boxW * boxR;
+    if (2 * boxbytes > 96 * 1024) return MK_OK;
+    S.boxW = boxW; S.boxR = boxR; S.esz_shift = esz == 4 ? 2 : 0;
+    const int dyn = 2 * ((boxbytes + 127) & ~127) + 128;
+    int occ = 0;
+    {
+        const int rc = (interp == MK_INTER_LINEAR) ? strip_occupancy<MK_INTER_LINEAR>(dyn, &occ) : strip_occupancy<MK_INTER_CUBIC>(dyn, &occ);
+        if (rc != MK_OK) return rc;
+    }
+    if (occ <= 0) return MK_OK;
+    const long gmax = (long)stream_sm_count(st) * std::min(occ, STRIP_OCC);
+    const long per = (nchunks + gmax - 1) / gmax;
+    if (per > MAX_CHUNKS) return MK_OK;
+    const long grid = (nchunks + per - 1) / per;
+    S.nchunks = (int)nchunks; S.chunks_per_cta = (int)per;
+
+    alignas(64) CUtensorMap map_src, map_cv, map_mk;
+    int rc = encode_image_map(&map_src, F.src, esz, (long)F.w * 3 / esz, F.h, (size_t)F.spitch, boxW / esz, boxR);
+    if (rc == MK_OK) rc = encode_image_map(&map_cv, P.canvas, 1, (long)P.Wc * 3, P.Hc, (size_t)P.cpitch, ROWB, CH);
+    if (rc == MK_OK) rc = encode_image_map(&map_mk, P.cmask, 1, (long)P.Wc, P.Hc, (size_t)P.mpitch, TW, CH);
+    if (rc != MK_OK) return rc;
+    if (interp == MK_INTER_LINEAR) mapper_strip_kernel<MK_INTER_LINEAR><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
+    else mapper_strip_kernel<MK_INTER_CUBIC><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
+    MK_LAUNCH_CHECK("mapper_strip_kernel");
+    *done = true;
+    return MK_OK;
+}
+
+}  // namespace mk

@@ -16,6 +16,8 @@ What produces each expected value:
              without the keypoint-hull ROI (mosaic.py:140-157); canvas + mask after every update.
   pipeline   the reference's own integration test (tests/test_mosaic.py:28-73) run for real on its test video: the
              first Mapper.update calls of SequentialMosaic.generate (mosaic.py:665-691) and the canvas they produce.
+  matchfeatures  SequentialMosaic.match_features / .registration (mosaic.py:402-470) of the same run: descriptor dicts as handed to
+             CompositeMatcher.knn_match, the good matches kept by the ratio comprehension (mosaic.py:430), RANSAC inputs / (H, inliers).
   routing    mosaicking.mosaic.get_corners / get_mosaic_dimensions (mosaic.py:708-768),
              registration.bbox_overlap on int-truncated corners (mosaic.py:614), and
              splitter.calculate_tiles / assign_image_to_tiles (splitter.py:11-58).
@@ -298,15 +300,74 @@ def gen_pipeline(reg, mos):
     print("pipeline.npz", NUPD, "updates, crop", (y0, y1, x0, x1), "frame", rec["calls"][0][0].shape)
 
 
+def gen_matchfeatures(reg, mos):
+    """SequentialMosaic.match_features (mosaic.py:402-438) and .registration (mosaic.py:440-470) of the reference run for real on
+    its test video, instrumented: for the first NP consecutive-frame pairs the descriptor dicts handed to
+    CompositeMatcher.knn_match (query = later frame, train = earlier frame), the good matches the reference keeps after the
+    literal ratio comprehension of mosaic.py:430, and the keypoint arrays + (H, inliers) of the RANSAC call of mosaic.py:459."""
+    import tempfile
+    import yaml
+    NP = 4
+    data = ref_shim.REFERENCE_SRC.parent / "tests" / "data"
+    with open(data / "sparus_time_offset.yaml") as f:
+        offset = yaml.safe_load(f)["video"]
+    K = np.array([405.6384738851233, 0, 189.9054317917407, 0, 405.588335378204, 139.9149578253755, 0, 0, 1]).reshape((3, 3))
+    D = np.array([-0.3670656233416921, 0.203001968694465, 0.003336917744124004, -0.000487426354679637, 0])
+    rec = {"knn": [], "good": [], "ransac": []}
+    real_knn = reg.CompositeMatcher.knn_match
+    real_est = reg.HomographyEstimation.__call__
+
+    def spy_knn(self, query, train, mask=None):
+        out = real_knn(self, query, train, mask)
+        if len(rec["knn"]) < NP:
+            rec["knn"].append(({k: np.ascontiguousarray(v).copy() for k, v in query.items()}, {k: np.ascontiguousarray(v).copy() for k, v in train.items()}))
+            good = {ft: tuple(m[0] for m in ms if len(m) == 2 and m[0].distance < 0.7 * m[1].distance) for ft, ms in out.items()}   # mosaic.py:430
+            rec["good"].append({ft: np.array([(m.queryIdx, m.trainIdx, m.distance) for m in g], np.float64).reshape(-1, 3) for ft, g in good.items()})
+        return out
+
+    def spy_est(self, src_points, dst_points, *args, **kwargs):
+        H, inl = real_est(self, src_points, dst_points, *args, **kwargs)
+        if len(rec["ransac"]) < NP:
+            rec["ransac"].append((np.array(src_points, np.float32), np.array(dst_points, np.float32), np.array(H, np.float64), np.array(inl, np.uint8).ravel(), str(self.method)))
+        return H, inl
+
+    reg.CompositeMatcher.knn_match = spy_knn
+    reg.HomographyEstimation.__call__ = spy_est
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            m = mos.SequentialMosaic(data_path=data / "sparus_snippet.mp4", project_path=Path(tmp), feature_types=("ORB",),
+                                     intrinsics={"K": K, "D": D}, orientation_path=data / "sparus_snippet.csv",
+                                     orientation_time_offset=offset, force_cpu=True, keypoint_roi=True, bovw_clusters=5, alpha=1.0)
+            m.extract_features(); m.match_features(); m.registration()
+    finally:
+        reg.CompositeMatcher.knn_match = real_knn
+        reg.HomographyEstimation.__call__ = real_est
+    assert len(rec["knn"]) == NP and len(rec["ransac"]) >= 1
+    out = {"npairs": np.array(NP), "nransac": np.array(len(rec["ransac"]))}
+    for k, ((q, t), good) in enumerate(zip(rec["knn"], rec["good"])):
+        assert list(q) == ["ORB"], list(q)
+        out[f"q{k}"], out[f"t{k}"], out[f"good{k}"] = q["ORB"], t["ORB"], good["ORB"]
+    for k, (src, dst, H, inl, method) in enumerate(rec["ransac"]):
+        out[f"rsrc{k}"], out[f"rdst{k}"], out[f"rH{k}"], out[f"rinl{k}"] = src, dst, H, inl
+        out["rmethod"] = np.array(method)
+    np.savez_compressed(OUT / "matchfeatures.npz", **out)
+    print("matchfeatures.npz", NP, "pairs", [out[f"q{k}"].shape for k in range(NP)], [len(out[f"good{k}"]) for k in range(NP)], "ransac", len(rec["ransac"]), out["rmethod"],
+          [int(out[f"rinl{k}"].sum()) for k in range(len(rec["ransac"]))])
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     reg, mos = ref_shim.import_reference()
     cv2.setRNGSeed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "matchfeatures":      # add this fixture without regenerating the others
+        gen_matchfeatures(reg, mos)
+        return
     gen_knn(reg)
     gen_warp()
     gen_mapper(mos)
     gen_routing(reg, mos)
     gen_pipeline(reg, mos)
+    gen_matchfeatures(reg, mos)
     (OUT / "PROVENANCE.txt").write_text(
         f"generated by oracle/make_golden.py\ncv2 {cv2.__version__}, numpy {np.__version__}\n"
         f"reference: DTUAqua-ObsTek/mosaic-library checkout at {ref_shim.REFERENCE_SRC.parent}\n")

@@ -62,13 +62,16 @@ def _install_stubs() -> None:
         cv2.xfeatures2d = types.SimpleNamespace(SURF=type("SURF", (), {}))
 
 
-def import_reference():
-    """-> (mosaicking.registration, mosaicking.mosaic) of the real reference, CPU mode."""
-    if not available():
-        raise ImportError(f"reference checkout not found under {REFERENCE_SRC}")
+def import_reference(src: Path | None = None):
+    """-> (mosaicking.registration, mosaicking.mosaic) of the real reference, CPU mode.  `src` = directory that holds the
+    `mosaicking` package: the checkout's src/ (default, build container) or baseline/_ref (the pip-installed, unmodified
+    copy that travels to the GPU box for bench.py --impl reference)."""
+    src = REFERENCE_SRC if src is None else Path(src)
+    if not (src / "mosaicking" / "mosaic.py").exists():
+        raise ImportError(f"reference not found under {src}")
     _install_stubs()
-    if str(REFERENCE_SRC) not in sys.path:
-        sys.path.insert(0, str(REFERENCE_SRC))
+    if str(src) not in sys.path:
+        sys.path.insert(0, str(src))
     import mosaicking
     import mosaicking.mosaic
     import mosaicking.registration

@@ -430,7 +430,7 @@ def test_mapper_full_size_properties():
        (a) alpha = 1 keeps the canvas in overlaps -> re-applying a frame is idempotent;
        (b) an integer translation reproduces the frame exactly inside the eroded footprint;
        (c) the region outside the reported footprint rectangle is untouched;
-       (d) a window around the footprint equals the oracle run on the same window (tile-local H, mosaic.py:617)."""
+       (d) the footprint window equals the oracle evaluated with full-canvas coordinates, bit for bit."""
     rng = np.random.default_rng(77)
     Hc = Wc = 16384
     img = rng.integers(1, 256, (1080, 1920, 3), dtype=np.uint8)
@@ -445,6 +445,7 @@ def test_mapper_full_size_properties():
     before = out.clone()
     mp.update(img, T)
     assert torch.equal(before, mp.output_device)                                                               # (a)
+    mp_mask_before = mp._canvas_mask.clone()
     th = 0.3
     R = np.array([[np.cos(th), -np.sin(th), 3000.3], [np.sin(th), np.cos(th), 2000.7], [2e-6, 1e-6, 1.0]])
     mp.update(img, R)
@@ -453,13 +454,93 @@ def test_mapper_full_size_properties():
     keepmask = torch.ones((Hc, Wc), dtype=torch.bool, device="cuda")
     keepmask[y0:y1, x0:x1] = False
     assert torch.equal(after[keepmask], before[keepmask])                                                      # (c)
-    wx0, wy0 = (x0 // 64) * 64, (y0 // 32) * 32        # window origin on the 64-px block grid keeps cv2's block bases
-    win = np.zeros((y1 - wy0 + 8, x1 - wx0 + 8, 3), np.uint8); wm = np.zeros(win.shape[:2], np.uint8)
-    Rw = mb.homogeneous_translation(-wx0, -wy0) @ R
-    orc.mapper_update(win, wm, img, Rw, 1.0, 1)
-    got = after[wy0:wy0 + win.shape[0], wx0:wx0 + win.shape[1]].cpu().numpy()
-    assert np.abs(got.astype(int) - win.astype(int)).max() <= 1                                                # (d) +-1 LSB
-    assert (got != win).mean() < 1e-3
+    win = np.zeros((y1 - y0, x1 - x0, 3), np.uint8); wm = np.zeros(win.shape[:2], np.uint8)
+    before_np = before[y0:y1, x0:x1].cpu().numpy()
+    win[...] = before_np; wm[...] = (mp_mask_before[y0:y1, x0:x1]).cpu().numpy()
+    orc.mapper_update_window(win, wm, (Hc, Wc), (x0, y0), img, R, 1.0, 1)      # full-canvas coordinates: exact
+    assert np.array_equal(after[y0:y1, x0:x1].cpu().numpy(), win)                                              # (d) bit-exact
+    assert np.array_equal(mp._canvas_mask[y0:y1, x0:x1].cpu().numpy(), wm)
+
+
+@pytest.mark.parametrize("interp,code", [("linear", 1), ("cubic", 2)])
+def test_mapper_4k_frames_full_size_exact(interp, code):
+    """BASELINE configs[2]/[3] frame size: 3840x2160 frames into a 16384^2 canvas, three overlapping updates (rotation,
+    mild perspective, black holes), alpha = 0.5 -> blends in the overlaps.  The visited window equals the oracle evaluated
+    with full-canvas coordinates bit for bit, and nothing outside the reported footprints changes."""
+    rng = np.random.default_rng(100 + code)
+    Hc = Wc = 16384
+    mp = mb.Mapper(Wc, Hc, alpha_blend=0.5, interp=interp)
+    Hs = []
+    for k in range(3):
+        th = 0.11 * k - 0.05
+        Hs.append(np.array([[np.cos(th), -np.sin(th), 9000.3 + 900 * k], [np.sin(th), np.cos(th), 11000.7 + 500 * k], [1e-6 * k, 5e-7 * k, 1.0]]))
+    imgs = [_img(rng, 2160, 3840, black=0.01) for _ in range(3)]
+    regions = []
+    for img, H in zip(imgs, Hs):
+        mp.update(img, H)
+        regions.append(mp.last_region)
+    x0 = min(r[0] for r in regions); y0 = min(r[1] for r in regions); x1 = max(r[2] for r in regions); y1 = max(r[3] for r in regions)
+    x0, y0, x1, y1 = max(0, x0 - 16), max(0, y0 - 16), min(Wc, x1 + 16), min(Hc, y1 + 16)
+    win = np.zeros((y1 - y0, x1 - x0, 3), np.uint8); wm = np.zeros(win.shape[:2], np.uint8)
+    for img, H in zip(imgs, Hs):
+        orc.mapper_update_window(win, wm, (Hc, Wc), (x0, y0), img, H, 0.5, code)
+    out, msk = mp.output_device, mp._canvas_mask
+    assert np.array_equal(out[y0:y1, x0:x1].cpu().numpy(), win)
+    assert np.array_equal(msk[y0:y1, x0:x1].cpu().numpy(), wm)
+    assert int(msk.count_nonzero()) == int(np.count_nonzero(wm))          # nothing outside the window was touched
+    assert int(out.sum(dtype=torch.int64)) == int(win.sum(dtype=np.int64))
+    mp.release()
+
+
+def test_sharded_mosaic_single_gpu_equals_per_tile_oracle():
+    """ShardedMosaic with the real CUDA Mapper (world = 1 owns every tile of a 3 x 2 grid): frames are routed to the tiles
+    their corner quad overlaps (mosaic.py:612-614) with H_tile = T(-tx,-ty) @ H (mosaic.py:617); the gathered mosaic equals
+    rendering every tile with the oracle and pasting them like examples/combine_tiles.py:46-62."""
+    from mosaicking_b200.distributed import ShardedMosaic, tiles_of_footprint
+    dev = torch.device("cuda", 0)
+    TILE, GRID, FRAME, STEPS = (512, 384), (3, 2), (200, 260), 10
+    rng = np.random.default_rng(12)
+    frames = [_img(rng, FRAME[0], FRAME[1]) for _ in range(STEPS)]
+    Hs = []
+    for k in range(STEPS):
+        th = 0.07 * k
+        Hs.append(np.array([[np.cos(th), -np.sin(th), 180.0 + 115 * k], [np.sin(th), np.cos(th), 250.0 + 22 * k], [1e-6, 0, 1.0]]))
+    sm = ShardedMosaic(GRID, TILE, lambda w, h: mb.Mapper(w, h, alpha_blend=0.5, interp="linear", device=dev), FRAME, dev, rank=0, world=1)
+    sm.plan(np.stack(Hs))
+    touched = 0
+    for k in range(STEPS):
+        touched += sm.step_planned(k, torch.from_numpy(frames[k]).to(dev))
+    got = sm.gather(0)
+    tiles = {}
+    multi = 0
+    for k in range(STEPS):
+        tl = tiles_of_footprint(Hs[k], FRAME[1], FRAME[0], TILE, GRID)
+        multi += len(tl) > 1
+        for (xi, yi) in tl:
+            cv, cm = tiles.setdefault((xi, yi), (np.zeros((TILE[1], TILE[0], 3), np.uint8), np.zeros((TILE[1], TILE[0]), np.uint8)))
+            orc.mapper_update(cv, cm, frames[k], mb.homogeneous_translation(-xi * TILE[0], -yi * TILE[1]) @ Hs[k], 0.5, 1)
+    assert multi >= 3 and touched == sum(len(tiles_of_footprint(H, FRAME[1], FRAME[0], TILE, GRID)) for H in Hs)   # frames did cross seams
+    want = {t: cv for t, (cv, _) in tiles.items()}
+    want.setdefault((GRID[0] - 1, GRID[1] - 1), np.zeros((TILE[1], TILE[0], 3), np.uint8))
+    assert np.array_equal(got, mb.combine_tiles(want, TILE))
+
+
+def test_match_features_replay(golden):
+    """SequentialMosaic.match_features (mosaic.py:402-438) replayed on the descriptor dicts the reference handed to its own
+    CompositeMatcher on its test video (tests/golden/matchfeatures.npz): the literal drop-in path -- CompositeMatcher.knn_match
+    -> DMatch tuples -> the ratio comprehension of mosaic.py:430 -- and the array fast path good_matches give the reference's
+    good matches (queryIdx, trainIdx, distance) exactly."""
+    g = golden.matchfeatures
+    m = mb.CompositeMatcher()
+    for k in range(int(g["npairs"])):
+        query, train = {"ORB": g[f"q{k}"]}, {"ORB": g[f"t{k}"]}
+        all_matches = m.knn_match(query, train)
+        good = {ft: tuple(mm[0] for mm in ms if len(mm) == 2 and mm[0].distance < 0.7 * mm[1].distance) for ft, ms in all_matches.items()}
+        got = np.array([(mm.queryIdx, mm.trainIdx, mm.distance) for mm in good["ORB"]], np.float64).reshape(-1, 3)
+        assert np.array_equal(got, g[f"good{k}"]), k
+        fast = m.good_matches(query, train, 0.7)["ORB"]
+        got2 = np.array([(mm.queryIdx, mm.trainIdx, mm.distance) for mm in fast], np.float64).reshape(-1, 3)
+        assert np.array_equal(got2, g[f"good{k}"]), k
 
 
 def test_mapper_unaligned_source_takes_the_global_path():

@@ -93,3 +93,33 @@ def test_reference_pipeline_golden(golden):
     assert np.array_equal(canvas[y0:y1, x0:x1], g["canvas_crop"])
     assert np.array_equal(cmask[y0:y1, x0:x1], g["mask_crop"])
     assert int(canvas.sum()) == int(g["canvas_crop"].sum())    # nothing outside the recorded crop
+
+
+def test_match_features_golden(golden):
+    """The good matches SequentialMosaic.match_features kept on the reference's test video (mosaic.py:426-430, metric NORM_L2
+    on the ORB bytes as registration.py:231 creates it): oracle kNN + ratio test reproduce queryIdx / trainIdx / distance."""
+    g = golden.matchfeatures
+    for k in range(int(g["npairs"])):
+        idx, dist = orc.knn2(g[f"q{k}"], g[f"t{k}"], "l2")
+        keep = orc.ratio_test(idx, dist, 0.7)
+        got = np.stack([np.nonzero(keep)[0].astype(np.float64), idx[keep, 0].astype(np.float64), dist[keep, 0].astype(np.float64)], 1)
+        assert np.array_equal(got, g[f"good{k}"]), k
+
+
+def test_window_oracle_equals_full_canvas_crop():
+    rng = np.random.default_rng(8)
+    Hc, Wc = 420, 560
+    canvas = np.zeros((Hc, Wc, 3), np.uint8); cm = np.zeros((Hc, Wc), np.uint8)
+    for (wx, wy, ww, wh) in ((0, 0, 300, 200), (250, 180, 310, 240), (100, 60, 200, 150)):
+        win = canvas[wy:wy + wh, wx:wx + ww].copy(); wm = cm[wy:wy + wh, wx:wx + ww].copy()
+        full, fm = canvas.copy(), cm.copy()
+        img = rng.integers(0, 256, (150, 220, 3), dtype=np.uint8)
+        img[rng.random((150, 220)) < 0.03] = 0
+        th = rng.uniform(-0.6, 0.6)
+        H = np.array([[np.cos(th), -np.sin(th), wx + 30.0], [np.sin(th), np.cos(th), wy + 40.0], [2e-5, 1e-5, 1.0]])
+        for interp in (orc.INTER_LINEAR, orc.INTER_CUBIC):
+            f2, m2, w2, wm2 = full.copy(), fm.copy(), win.copy(), wm.copy()
+            orc.mapper_update(f2, m2, img, H, 0.4, interp)
+            orc.mapper_update_window(w2, wm2, (Hc, Wc), (wx, wy), img, H, 0.4, interp)
+            assert np.array_equal(f2[wy:wy + wh, wx:wx + ww], w2) and np.array_equal(m2[wy:wy + wh, wx:wx + ww], wm2)
+        orc.mapper_update(canvas, cm, img, H, 0.4, orc.INTER_LINEAR)
