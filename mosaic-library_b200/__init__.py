@@ -27,11 +27,13 @@ HAS_B200 = _has_b200()
 from . import mosaic, registration  # noqa: E402
 from .mosaic import (Mapper, assign_frames_to_tiles, bbox_overlap, combine_tiles, find_nice_homographies,  # noqa: E402
                      get_corners, get_mosaic_dimensions, homogeneous_translation, warp_perspective)
-from .registration import CompositeMatcher, DMatch, Matcher, get_matches  # noqa: E402
+from .registration import (CompositeMatcher, DMatch, HomographyEstimation, HomographyEstimationType, Matcher, gather_matched_keypoints,  # noqa: E402
+                           get_matches, propagate_homographies)
 from .partition import SmPartition  # noqa: E402
 from .hostmem import pinned_empty  # noqa: E402
 
 __all__ = ["HAS_B200", "MosaicB200Error", "build", "launch_count", "Mapper", "Matcher", "CompositeMatcher", "DMatch",
            "get_matches", "get_corners", "get_mosaic_dimensions", "find_nice_homographies", "bbox_overlap",
            "assign_frames_to_tiles", "combine_tiles", "homogeneous_translation", "warp_perspective", "mosaic",
-           "registration", "SmPartition", "pinned_empty"]
+           "registration", "SmPartition", "pinned_empty", "HomographyEstimation", "HomographyEstimationType", "gather_matched_keypoints",
+           "propagate_homographies"]

@@ -577,3 +577,105 @@ def get_matches(descriptors1, descriptors2, matcher: Matcher, minmatches: int):
         mlength += d1.shape[0]
         nlength += d2.shape[0]
     return minmatches <= len(good), good
+
+
+# ------------------------------------------------------------------------------------------------
+# registration glue on the device
+# ------------------------------------------------------------------------------------------------
+from enum import Enum  # noqa: E402
+
+
+class HomographyEstimationType(Enum):
+    """registration.py:383-398."""
+    PERSPECTIVE = "perspective"
+    AFFINE = "affine"
+    PARTIAL = "partial"
+
+    @staticmethod
+    def from_string(s: str) -> "HomographyEstimationType":
+        try:
+            return HomographyEstimationType(s.lower())
+        except ValueError:
+            raise ValueError(f"Unknown homography type: {s.lower()}")
+
+    def __str__(self) -> str:
+        return self.value
+
+
+class HomographyEstimation:
+    """Drop-in for registration.HomographyEstimation (registration.py:399-419): RANSAC model fit on the GPU
+    (csrc/mk_ransac.cu) instead of cv2.findHomography / cv2.estimateAffine2D.
+
+    Called like the reference does (mosaic.py:459): est(kp, kp_prev, method=cv2.RANSAC, ransacReprojThreshold=1.0)
+    -> (H 3x3 float64, inliers uint8 [n, 1]).  PERSPECTIVE fits 8 degrees of freedom; AFFINE and PARTIAL both call
+    cv2.estimateAffine2D in the reference (6 degrees of freedom; PARTIAL drops the caller's arguments, i.e. threshold 3.0),
+    which is reproduced.  The estimator is randomised, like cv2's: same inlier set up to points within rounding of the
+    threshold, same model up to fit noise; deterministic for a given `seed`."""
+
+    def __init__(self, method, device=None, iters: int = 2048, seed: int = 0x5EED):
+        if isinstance(method, HomographyEstimationType):
+            self.method = method
+        elif isinstance(method, str):
+            self.method = HomographyEstimationType.from_string(method)
+        else:
+            raise ValueError("method must be either a HomographyEstimationType or a string")
+        self._device = _cuda_device(device)
+        self._lib = _lib.lib()
+        self.iters, self.seed = int(iters), int(seed)
+        self._ws = None
+
+    def _threshold(self, kwargs) -> float:
+        if self.method == HomographyEstimationType.PARTIAL:
+            return 3.0                                   # registration.py:415 calls estimateAffine2D(src, dst) with cv2's defaults
+        return float(kwargs.get("ransacReprojThreshold", 3.0))
+
+    def estimate_device(self, src: torch.Tensor, dst: torch.Tensor, threshold: float):
+        """src / dst: float32 [n, 2] on the device -> (H float64 [3, 3], inliers uint8 [n], n_inliers int32 [1]), all on the
+        device, asynchronous on the current stream."""
+        dev = self._device
+        src = src.to(dev, torch.float32).contiguous(); dst = dst.to(dev, torch.float32).contiguous()
+        n = int(src.shape[0])
+        if self._ws is None:
+            self._ws = torch.empty(int(self._lib.mk_ransac_workspace_bytes()), dtype=torch.uint8, device=dev)
+        H = torch.empty((3, 3), dtype=torch.float64, device=dev)
+        inl = torch.empty((max(n, 1),), dtype=torch.uint8, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        model = _lib.MODEL_PERSPECTIVE if self.method == HomographyEstimationType.PERSPECTIVE else _lib.MODEL_AFFINE
+        with _current_device(dev):
+            _lib.check(self._lib.mk_ransac_transform(model, src.data_ptr(), dst.data_ptr(), n, None, float(threshold), self.iters, self.seed,
+                                                     H.data_ptr(), inl.data_ptr(), cnt.data_ptr(), self._ws.data_ptr(), _raw_stream(dev)))
+        return H, inl[:n], cnt
+
+    def __call__(self, src_points, dst_points, *args, **kwargs):
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(src_points, np.float32).reshape(-1, 2)))
+        dst = torch.from_numpy(np.ascontiguousarray(np.asarray(dst_points, np.float32).reshape(-1, 2)))
+        H, inl, cnt = self.estimate_device(src, dst, self._threshold(kwargs))
+        if int(cnt.item()) == 0:
+            return None, None                                        # what cv2 returns when no model is found
+        return H.cpu().numpy(), inl.cpu().numpy().reshape(-1, 1)
+
+
+def gather_matched_keypoints(kp_query: torch.Tensor, kp_train: torch.Tensor, idx: torch.Tensor, keep: torch.Tensor):
+    """mosaic.py:449-457 on the device: keypoints of the ratio-test survivors in match order.  kp_*: float32 [n, 2], idx int32
+    [nq, 2] and keep uint8 [nq] as Matcher.knn_match_device returns them -> (src [nq, 2], dst [nq, 2], count int32 [1]); only the
+    first `count` rows are meaningful.  No host round trip."""
+    dev = kp_query.device
+    nq = int(idx.shape[0])
+    src = torch.empty((max(nq, 1), 2), dtype=torch.float32, device=dev)
+    dst = torch.empty((max(nq, 1), 2), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    with _current_device(dev):
+        _lib.check(_lib.lib().mk_gather_matches(kp_query.contiguous().data_ptr(), kp_train.contiguous().data_ptr(), idx.contiguous().data_ptr(),
+                                                keep.contiguous().data_ptr(), nq, src.data_ptr(), dst.data_ptr(), None, cnt.data_ptr(), _raw_stream(dev)))
+    return src, dst, cnt
+
+
+def propagate_homographies(H_seq, device=None) -> np.ndarray:
+    """core/interface.py:97-113 (_propagate_homographies) for an ordered chain: [H0, H1, ...] -> accumulate(matmul), float64,
+    computed on the device (one launch, left to right like itertools.accumulate)."""
+    dev = _cuda_device(device)
+    H = torch.from_numpy(np.ascontiguousarray(np.asarray(H_seq, np.float64).reshape(-1, 3, 3))).to(dev)
+    out = torch.empty_like(H)
+    with _current_device(dev):
+        _lib.check(_lib.lib().mk_chain_homographies(H.data_ptr(), int(H.shape[0]), out.data_ptr(), _raw_stream(dev)))
+    return out.cpu().numpy()
