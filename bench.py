@@ -469,6 +469,10 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
     torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
     K, W = args.steps, args.warmup
     nfr = len(frames)
+    # the pipelined loop hands the mapper page-locked frames out of a ring of 4 and never has more than 3 uploads in flight
+    # (Mapper(async_upload=True): the copy of frame k overlaps the kernel of frame k-1; documented ring contract, mosaic.py);
+    # the blocking loop below uses the default synchronous Mapper, like the reference's update()
+    amapper = mb.Mapper(CANVAS, CANVAS, alpha_blend=ALPHA, interp="linear", device=dev, async_upload=True)
     # page-locked host inputs out of a huge-page backed, CUDA-registered region (mosaicking_b200.pinned_empty): buffers from
     # pin_memory() are made of 4 KB pages and cycled through the copy engine at 16-45 GB/s on some hosts (tools/pin_probe3.py)
     pin_frames = [torch.from_numpy(mb.pinned_empty((fh, fw, 3))) for _ in range(4)]
@@ -494,7 +498,7 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
         for k in range(k0, k0 + n):
             img, q, t = inputs(k)
             nxt = matcher.knn_match_arrays_async(q, t, RATIO)
-            mapper.update(img, Hs[k % len(Hs)])
+            amapper.update(img, Hs[k % len(Hs)])
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
@@ -541,6 +545,7 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
         wd.copy_(pin_frames[0], non_blocking=True)
     torch.cuda.synchronize()
     link_gbs = 20 * wd.numel() / (time.perf_counter() - t0) / 1e9
+    amapper.release()
     return {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
                      "while frame k is in flight; wall clock incl. Python, median of 5 passes of K frames; untimed frames first until the PCIe path is warm"),

@@ -30,7 +30,7 @@ namespace mk {
 
 constexpr int CH = 16;               // canvas rows finalised per chunk
 constexpr int BR = CH + 2 * HALO;    // rows of the first phase-1 block of a segment
-constexpr int RING = 32;             // ring of warped rows / bit rows, indexed by (canvas row & 31)
+constexpr int RING = 64;             // ring of warped rows / bit rows, indexed by (canvas row & 63): two blocks never alias
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
 constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
@@ -67,6 +67,7 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, int what = 0)
 {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t ok;
         asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
@@ -105,15 +106,15 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     __shared__ __align__(128) uint8_t s_canvas[2][CH][ROWB];
     __shared__ __align__(128) uint8_t s_mask[2][CH][TW];
     __shared__ __align__(16) uint32_t s_warp[RING][TW];
-    __shared__ __align__(16) double s_row[2][3][BR][4];     // X0, Y0, W0 of the left / centre / right coordinate block, two blocks in flight
+    __shared__ __align__(16) double s_row[3][3][BR][4];     // X0, Y0, W0 of the left / centre / right coordinate block; three blocks in flight
     __shared__ unsigned long long s_m0[RING];
     __shared__ unsigned long long s_h[RING];
     __shared__ unsigned long long s_v[CH];
     __shared__ uint8_t s_side[RING][4];
     __shared__ __align__(8) unsigned long long s_bar_src[2];
     __shared__ __align__(8) unsigned long long s_bar_cv[2];
-    __shared__ int s_tile[2][4];                // per source buffer: sy0, bx0, staged?
     __shared__ __align__(16) int4 s_blk[MAX_CHUNKS];     // per chunk of this CTA: tileX, first finalised row, first phase-1 row, phase-1 rows
+    __shared__ __align__(16) int4 s_rect[MAX_CHUNKS];    // per chunk: source box origin (row sy0, byte bx0), fits-in-the-box flag
     extern __shared__ __align__(128) uint8_t s_dyn[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,7 +123,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     const int boxstride = (boxbytes + 127) & ~127;        // TMA destinations are 128-byte aligned
     const uint32_t src_base = (smem_u32(s_dyn) + 127u) & ~127u;
 
-    // ---- chunks [c0, c1) of the flat list belong to this CTA: strip (binary search in the host's prefix sums) and rows ----
+    // ---- chunks [c0, c0 + n) of the flat list belong to this CTA: strip (binary search in the host's prefix sums) and rows ----
     const int c0 = (int)blockIdx.x * p.chunks_per_cta, n = min(p.nchunks, c0 + p.chunks_per_cta) - c0;
     if (n <= 0) return;
     if (tid < n) {
@@ -136,23 +137,24 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
         s_blk[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
     }
-    if (tid == 128) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); }
+    if (tid == 224) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); }
     __syncthreads();
 
-    // ---- source box of a block: quantised images of the four corners of the haloed block (columns tileX-2 .. tileX+65)
-    //      bound every tap of the block as long as W keeps its sign; one warp, result in s_tile[buf], TMA issued by lane 0 ----
-    auto stage_src = [&](int j, int buf) {
-        const int4 blk = s_blk[j];
+    // ---- source boxes of ALL chunks of this CTA, four lanes per chunk: the quantised images of the four corners of the haloed
+    //      block (columns tileX-2 .. tileX+65) bound every tap of the block as long as W keeps its sign ----
+    if (warp * 8 < n) {
+        const int jj = min(tid >> 2, n - 1), cnr = tid & 3;
+        const int4 blk = s_blk[jj];
         const int tileX = blk.x, first = blk.z, nr = blk.w;
-        int X = 0, Y = 0, sg = 0;
-        if (lane < 4) {
-            const int x0 = (lane & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (lane & 1) ? HALO - 1 : BLOCK_W - HALO;
-            const int y = (lane & 2) ? min(first + nr - 1, p.Hc - 1) : max(first, 0);
+        int X, Y, sg;
+        {
+            const int x0 = (cnr & 1) ? tileX + BLOCK_W : tileX - BLOCK_W, x1 = (cnr & 1) ? HALO - 1 : BLOCK_W - HALO;
+            const int y = (cnr & 2) ? min(first + nr - 1, p.Hc - 1) : max(first, 0);
             double X0, Y0, W0;
             row_base(F.M, x0, y, X0, Y0, W0);
-            const double dx1 = (double)x1;
-            quantize(F.M, X0, Y0, W0, dmul(F.M.m[0], dx1), dmul(F.M.m[3], dx1), dmul(F.M.m[6], dx1), X, Y);
-            const double W = F.M.affine ? F.M.m[8] : dadd(W0, dmul(F.M.m[6], dx1));
+            const double d1 = (double)x1;
+            quantize(F.M, X0, Y0, W0, dmul(F.M.m[0], d1), dmul(F.M.m[3], d1), dmul(F.M.m[6], d1), X, Y);
+            const double W = F.M.affine ? F.M.m[8] : dadd(W0, dmul(F.M.m[6], d1));
             const bool sane = abs(X) < (1 << 30) && abs(Y) < (1 << 30);
             sg = !sane ? 0 : ((W > 0.0) ? 1 : ((W < 0.0) ? -1 : 0));
         }
@@ -163,23 +165,15 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
             smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
         }
-        if (lane == 0) {
+        if (cnr == 0 && (tid >> 2) < n) {
             constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;   // tap reach + 1 px safety ring
             const int sx_lo = (xlo >> 5) - LO, sx_hi = (xhi >> 5) + HI, sy_lo = (ylo >> 5) - LO, sy_hi = (yhi >> 5) + HI;
             const int bx0 = (sx_lo * 3) & ~15;      // the TMA needs a 16-byte aligned global start address
             const bool convex = smin == smax && smin != 0;
             const bool fits = convex && (sx_hi * 3 + 3 - bx0) <= p.boxW && (sy_hi - sy_lo + 1) <= p.boxR;
-            s_tile[buf][0] = sy_lo; s_tile[buf][1] = bx0; s_tile[buf][2] = fits ? 1 : 0;
-            mbar_arrive_expect_tx(&s_bar_src[buf], fits ? (uint32_t)boxbytes : 0u);
-            if (fits) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, bx0 >> p.esz_shift, sy_lo, &s_bar_src[buf]);
+            s_rect[jj] = make_int4(sy_lo, bx0, fits ? 1 : 0, 0);
         }
-    };
-    auto load_canvas = [&](int j, int cb) {      // one thread
-        const int4 blk = s_blk[j];
-        mbar_arrive_expect_tx(&s_bar_cv[cb], (uint32_t)(CH * ROWB + CH * TW));
-        tma_load_2d(smem_u32(&s_canvas[cb][0][0]), &map_cv, blk.x * 3, blk.y, &s_bar_cv[cb]);
-        tma_load_2d(smem_u32(&s_mask[cb][0][0]), &map_mk, blk.x, blk.y, &s_bar_cv[cb]);
-    };
+    }
     // per-row coordinate bases of block j for the left / centre / right 64-px blocks; 60 threads (idx)
     auto row_bases = [&](int j, int idx) {
         const int4 blk = s_blk[j];
@@ -187,20 +181,54 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         if (b < 3 && r < blk.w) {
             double X0, Y0, W0;
             row_base(F.M, blk.x + (b - 1) * BLOCK_W, blk.z + r, X0, Y0, W0);
-            double *d = s_row[j & 1][b][r];
+            double *d = s_row[j % 3][b][r];
             d[0] = X0; d[1] = Y0; d[2] = W0;
         }
     };
+    if (warp == 2 || warp == 3) row_bases(0, tid - 64);
+    else if ((warp == 4 || warp == 5) && n > 1) row_bases(1, tid - 128);
+    __syncthreads();
 
-    if (warp == 0) {
-        stage_src(0, 0);
-        if (n > 1) stage_src(1, 1);
-    } else if (warp == 2 || warp == 3) {
-        row_bases(0, tid - 64);
-    } else if (tid == 128) {
+    auto issue_src = [&](int j) {                 // one thread
+        const int buf = j & 1;
+        const int4 rc = s_rect[j];
+        mbar_arrive_expect_tx(&s_bar_src[buf], rc.z ? (uint32_t)boxbytes : 0u);
+        if (rc.z) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, rc.y >> p.esz_shift, rc.x, &s_bar_src[buf]);
+    };
+    auto load_canvas = [&](int j, int cb) {      // one thread
+        const int4 blk = s_blk[j];
+        mbar_arrive_expect_tx(&s_bar_cv[cb], (uint32_t)(CH * ROWB + CH * TW));
+        tma_load_2d(smem_u32(&s_canvas[cb][0][0]), &map_cv, blk.x * 3, blk.y, &s_bar_cv[cb]);
+        tma_load_2d(smem_u32(&s_mask[cb][0][0]), &map_mk, blk.x, blk.y, &s_bar_cv[cb]);
+    };
+    // the 2 + 2 side-halo columns of block j (they live in the neighbouring coordinate blocks): thread t = 4 * row + column
+    auto side_halo = [&](int j, int t) {
+        const int4 blk = s_blk[j];
+        const int tileX = blk.x, first = blk.z, nr = blk.w;
+        if (t >= nr * 4) return;
+        const int4 rc = s_rect[j];
+        SrcTile T;
+        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + (j & 1) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
+        const int r = t >> 2, cc = t & 3, y = first + r;
+        const int x = (cc < 2) ? tileX - HALO + cc : tileX + TW + (cc - 2);
+        const int b = (cc < 2) ? 0 : 2, x1 = (cc < 2) ? BLOCK_W - HALO + cc : cc - 2;
+        uint32_t mv = 255;
+        if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
+            const double d1 = (double)x1;
+            const double *rb = s_row[j % 3][b][r];
+            int X, Y;
+            quantize(F.M, rb[0], rb[1], rb[2], dmul(F.M.m[0], d1), dmul(F.M.m[3], d1), dmul(F.M.m[6], d1), X, Y);
+            mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
+        }
+        s_side[y & (RING - 1)][cc] = (uint8_t)mv;
+    };
+
+    if (tid == 0) {
+        issue_src(0);
+        if (n > 1) issue_src(1);
+    } else if (tid == 224) {
         load_canvas(0, 0);
     }
-    __syncthreads();
 
     const int half = warp & 1, cx = half * 32 + lane;
     const double dx1 = (double)cx;
@@ -216,11 +244,10 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
 
         if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf], (uint32_t)(j >> 1) & 1u, 100 + j);
         __syncwarp();
-        const int sy0 = s_tile[buf][0], bx0 = s_tile[buf][1];
-        const bool staged = s_tile[buf][2] != 0;
+        const int4 rc = s_rect[j];
+        const int sy0 = rc.x, bx0 = rc.y;
+        const bool staged = rc.z != 0;
         const uint32_t box = src_base + (uint32_t)(buf * boxstride);
-        SrcTile T;
-        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + buf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
 
         // ---- phase 1, lanes = consecutive columns, two rows per iteration ----------------------------
         {
@@ -230,7 +257,8 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 for (int r = warp >> 1; r < nr; r += 4)
                     if ((r < r_lo || r >= r_hi) && lane == 0) reinterpret_cast<uint32_t *>(&s_m0[(first + r) & (RING - 1)])[half] = ~0u;
             }
-            const uint32_t rowb = smem_u32(&s_row[buf][1][0][0]);
+            uint32_t rowb = smem_u32(&s_row[j % 3][1][0][0]);
+            asm volatile("" : "+r"(rowb));           // keep the address in a register (otherwise it is re-derived inside the row loop)
             auto finish_row = [&](int r, uint32_t px) {
                 const unsigned bal = __ballot_sync(0xffffffffu, xvalid ? (px != 0u) : true);   // columns outside the canvas count as set
                 const uint32_t ri = (uint32_t)(first + r) & (RING - 1);
@@ -240,6 +268,8 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             auto body = [&](auto fast_tag, auto affine_tag) {
                 constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
                 const double wr = F.M.wr;
+                SrcTile T;
+                T.s = s_dyn + (src_base - smem_u32(s_dyn)) + buf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
                 auto one = [&](int r) -> uint32_t {
                     double X0, Y0, W0 = 0.0;
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(X0), "=d"(Y0) : "r"(rowb + (uint32_t)r * 32u));
@@ -270,27 +300,13 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 body(std::false_type{}, std::false_type{});
             }
         }
-        // ---- phase 1b: the 2 + 2 side-halo columns (they live in the neighbouring coordinate blocks) ------
-        if (tid < nr * 4) {
-            const int r = tid >> 2, cc = tid & 3, y = first + r;
-            const int x = (cc < 2) ? tileX - HALO + cc : tileX + TW + (cc - 2);
-            const int b = (cc < 2) ? 0 : 2, x1 = (cc < 2) ? BLOCK_W - HALO + cc : cc - 2;
-            uint32_t mv = 255;
-            if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
-                const double d1 = (double)x1;
-                const double *rb = s_row[buf][b][r];
-                int X, Y;
-                quantize(F.M, rb[0], rb[1], rb[2], dmul(F.M.m[0], d1), dmul(F.M.m[3], d1), dmul(F.M.m[6], d1), X, Y);
-                mv = sample_c3_tile<INTERP>(staged, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
-            }
-            s_side[y & (RING - 1)][cc] = (uint8_t)mv;
-        }
+        if (j == 0) side_halo(0, tid);           // later blocks get theirs one iteration ahead, between the phases
         __syncthreads();                                                             // D
 
-        // ---- between the phases, one job per warp: source box of chunk j+2 (its buffer is free now), horizontal + vertical
-        //      erosion of the new rows, coordinate bases of chunk j+1, canvas + mask tile of chunk j+1 --------------------
+        // ---- between the phases, one job per warp: the source box of chunk j+2 (its buffer is free now), horizontal + vertical
+        //      erosion of the new rows, the coordinate bases of chunk j+2, the side halo of chunk j+1, the canvas tile of chunk j+1 ----
         if (warp == 0) {
-            if (j + 2 < n) stage_src(j + 2, buf);
+            if (lane == 0 && j + 2 < n) issue_src(j + 2);
         } else if (warp == 1) {
             if (lane < nr) {
                 const int ri = (first + lane) & (RING - 1);
@@ -308,8 +324,14 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                             s_h[(y + 2) & (RING - 1)];
             }
         } else if (warp == 2 || warp == 3) {
-            if (j + 1 < n) row_bases(j + 1, tid - 64);
-        } else if (tid == 128) {
+            if (j + 2 < n) row_bases(j + 2, tid - 64);
+        } else if (warp < 7) {
+            if (j + 1 < n) {
+                if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf ^ 1], (uint32_t)((j + 1) >> 1) & 1u, 300 + j);
+                __syncwarp();
+                side_halo(j + 1, tid - 128);
+            }
+        } else if (tid == 224) {
             if (j + 1 < n) {
                 bulk_wait_read0();                    // the store of chunk j-1 has read its buffer
                 load_canvas(j + 1, buf ^ 1);
@@ -373,15 +395,14 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             }
         }
         const int any = __syncthreads_or((int)mb);                                   // F
-        if (tid == 128 && any) {
+        if (tid == 224 && any) {
             tma_store_2d(&map_cv, tileX * 3, fy, smem_u32(&s_canvas[buf][0][0]));
             tma_store_2d(&map_mk, tileX, fy, smem_u32(&s_mask[buf][0][0]));
             bulk_commit();
         }
     }
-    if (tid == 128) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
+    if (tid == 224) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Host side
@@ -461,7 +482,12 @@ static int strip_occupancy(int dyn_smem, int *occ)
         MK_CUDA_TRY(cudaFuncSetAttribute(mapper_strip_kernel<INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
         configured_dev = dev; configured_smem = want;
     }
-    MK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, mapper_strip_kernel<INTERP>, STHREADS, (size_t)dyn_smem));
+    static int cached_dev = -1, cached_smem = -1, cached_occ = 0;       // the query costs microseconds: once per (device, shared-memory size)
+    if (cached_dev != dev || cached_smem != dyn_smem) {
+        MK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_occ, mapper_strip_kernel<INTERP>, STHREADS, (size_t)dyn_smem));
+        cached_dev = dev; cached_smem = dyn_smem;
+    }
+    *occ = cached_occ;
     return MK_OK;
 }
 
