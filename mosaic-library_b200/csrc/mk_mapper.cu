@@ -876,14 +876,21 @@ extern "C" int mk_warp_perspective_u8(const uint8_t *src, int src_h, int src_w, 
     P.src = src; P.dst = dst; P.cubic = nullptr; P.spitch = src_pitch; P.dpitch = dst_pitch;
     P.h = src_h; P.w = src_w; P.Hd = dst_h; P.Wd = dst_w;
     make_invmap(H_host, P.M);
+    const uint2 *lut = nullptr;
     {
         DeviceTables tb;
         const int st = device_tables(tb);
         if (st != MK_OK) return st;
-        P.cubic = tb.cubic;
+        P.cubic = tb.cubic; lut = tb.lut;
     }
     dim3 grid((dst_w + TW - 1) / TW, (dst_h + TH - 1) / TH);
     cudaStream_t st = (cudaStream_t)stream;
+    if (channels == 3) {          // source footprint staged in shared memory by TMA (mk_strip.cu) whenever it applies
+        bool done = false;
+        const int rc = launch_warp_staged(src, src_h, src_w, src_pitch, P.M, dst, dst_h, dst_w, dst_pitch, interp, P.cubic, lut, st, &done);
+        if (rc != MK_OK) return rc;
+        if (done) return MK_OK;
+    }
     if (interp == MK_INTER_LINEAR) {
         if (channels == 3) warp_kernel<MK_INTER_LINEAR, 3><<<grid, NTHREADS, 0, st>>>(P);
         else warp_kernel<MK_INTER_LINEAR, 1><<<grid, NTHREADS, 0, st>>>(P);

@@ -162,4 +162,8 @@ int device_tables(DeviceTables &out);
 // minification).  Returns MK_OK and sets *done = true when it launched; *done = false means "not applicable, use the tile kernel".
 int launch_strip_update(const MapperParams &P, const double *H_host, int interp, const int32_t *rect, cudaStream_t st, bool *done);
 
+// mk_strip.cu: staged form of the plain warp (3 channels, 16-byte aligned source); *done = false -> use warp_kernel
+int launch_warp_staged(const uint8_t *src, int h, int w, size_t spitch, const InvMap &M, uint8_t *dst, int Hd, int Wd, size_t dpitch, int interp,
+                       const short *cubic, const uint2 *lut, cudaStream_t st, bool *done);
+
 }  // namespace mk

@@ -34,7 +34,7 @@ constexpr int RING = 64;             // ring of warped rows / bit rows, indexed 
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
 constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
-constexpr int STRIP_OCC = 4;         // CTAs per SM the register budget is set for
+constexpr int STRIP_OCC = 3;         // CTAs per SM the register budget is set for (four rows per warp in flight need ~80 registers)
 
 struct StripParams {
     const short *cubic;
@@ -90,7 +90,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
 __device__ __forceinline__ uint32_t sample_linear_box(uint32_t base, int pitch, int sy0, int bx0, int X, int Y, const uint2 *__restrict__ lut)
 {
     const int r = (Y >> 5) - sy0, cb = (X >> 5) * 3 - bx0;
-    const uint2 wt = __ldg(lut + ((Y & 31) * 32 + (X & 31)));
+    // the four integer weights as two int16 pairs, (w00 | w01 << 16, w10 | w11 << 16) = ((32-ay) * u, ay * u) with
+    // u = (32-ax) | ax << 16: three IMADs on the FMA pipe instead of a 32-way divergent table read (8.5 L1 wavefronts per warp)
+    const uint32_t ax = (uint32_t)X & 31u, ay = (uint32_t)Y & 31u;
+    const uint32_t u = ax * 65535u + 32u;
+    const uint2 wt = make_uint2((32u - ay) * u, ay * u);
+    (void)lut;
     const uint32_t a = base + r * pitch + (cb & ~3), b = a + pitch;
     const unsigned sh = (unsigned)(cb & 3) * 8;
     const uint32_t a0 = lds32(a), a1 = lds32(a + 4), a2 = lds32(a + 8), b0 = lds32(b), b1 = lds32(b + 4), b2 = lds32(b + 8);
@@ -113,6 +118,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     __shared__ uint8_t s_side[RING][4];
     __shared__ __align__(8) unsigned long long s_bar_src[2];
     __shared__ __align__(8) unsigned long long s_bar_cv[2];
+    __shared__ __align__(8) unsigned long long s_bar_v;      // eroded bit rows of the current chunk are ready (warp 1 -> everyone)
     __shared__ __align__(16) int4 s_blk[MAX_CHUNKS];     // per chunk of this CTA: tileX, first finalised row, first phase-1 row, phase-1 rows
     __shared__ __align__(16) int4 s_rect[MAX_CHUNKS];    // per chunk: source box origin (row sy0, byte bx0), fits-in-the-box flag
     extern __shared__ __align__(128) uint8_t s_dyn[];
@@ -137,7 +143,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
         s_blk[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
     }
-    if (tid == 224) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); }
+    if (tid == 224) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); mbar_init(&s_bar_v, 1); }
     __syncthreads();
 
     // ---- source boxes of ALL chunks of this CTA, four lanes per chunk: the quantised images of the four corners of the haloed
@@ -216,9 +222,16 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
             const double d1 = (double)x1;
             const double *rb = s_row[j % 3][b][r];
+            const double sx = dmul(F.M.m[0], d1), sy = dmul(F.M.m[3], d1), sw = dmul(F.M.m[6], d1);
             int X, Y;
-            quantize(F.M, rb[0], rb[1], rb[2], dmul(F.M.m[0], d1), dmul(F.M.m[3], d1), dmul(F.M.m[6], d1), X, Y);
-            mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
+            if (rc.z != 0 && INTERP == 1) {        // staged: the box holds the halo columns' taps too (its corners are columns tileX-2 / tileX+65)
+                if (F.M.affine) quantize_fast_t<true>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
+                else quantize_fast_t<false>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
+                mv = sample_linear_box(src_base + (uint32_t)((j & 1) * boxstride), p.boxW, rc.x, rc.y, X, Y, p.lut) ? 255u : 0u;
+            } else {
+                quantize(F.M, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
+                mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
+            }
         }
         s_side[y & (RING - 1)][cc] = (uint8_t)mv;
     };
@@ -231,19 +244,32 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     }
 
     const int half = warp & 1, cx = half * 32 + lane;
+    // lanes whose column lies outside the canvas (last strip only) sample column 0 of the strip instead and discard the result:
+    // no divergence in the row loop, and every tap stays inside the staged box
+    const bool xvalid_all = (p.tx0 + p.nstrips) * TW <= p.Wc;      // no strip of this launch reaches beyond the canvas
     const double dx1 = (double)cx;
-    const double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
+    double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
     const uint32_t warp_base = smem_u32(&s_warp[0][0]) + (uint32_t)cx * 4u;
     const uint32_t m0_base = smem_u32(&s_m0[0]) + (uint32_t)half * 4u;
 
+#ifdef MK_STRIP_TRACE
+    long long tr[8][9];
+    __shared__ long long s_role[8][8];
+    const long long t_start = clock64();
+#define TRW(w, k) if (tid == 32 * (w) && j < 8) tr[j][k] = clock64() - t_start
+#else
+#define TRW(w, k)
+#endif
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
         const int buf = j & 1;
         const int4 blk = s_blk[j];
         const int tileX = blk.x, fy = blk.y, first = blk.z, nr = blk.w;
+        TRW(5, 0);
 
         if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf], (uint32_t)(j >> 1) & 1u, 100 + j);
         __syncwarp();
+        TRW(5, 1);
         const int4 rc = s_rect[j];
         const int sy0 = rc.x, bx0 = rc.y;
         const bool staged = rc.z != 0;
@@ -251,7 +277,11 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
 
         // ---- phase 1, lanes = consecutive columns, two rows per iteration ----------------------------
         {
-            const bool xvalid = tileX + cx < p.Wc;
+            const bool xvalid = xvalid_all || tileX + cx < p.Wc;
+            if (!xvalid_all) {
+                const double dxs = xvalid ? (double)cx : 0.0;
+                mx = dmul(F.M.m[0], dxs); my = dmul(F.M.m[3], dxs); mw = dmul(F.M.m[6], dxs);
+            }
             const int r_lo = max(0, -first), r_hi = min(nr, p.Hc - first);    // block rows inside the canvas
             if (r_lo > 0 || r_hi < nr) {      // rows outside the canvas count as set (cv2.erode's default border)
                 for (int r = warp >> 1; r < nr; r += 4)
@@ -281,16 +311,16 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                     else return sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
                 };
                 int r = r_lo + (warp >> 1);
-#pragma unroll 1
-                for (; r + 4 < r_hi; r += 8) {
-                    uint32_t pa = 0, pb = 0;
-                    if (xvalid) { pa = one(r); pb = one(r + 4); }
-                    finish_row(r, pa); finish_row(r + 4, pb);
+                if (r + 12 < r_hi) {              // the usual case (16 or 20 rows inside the canvas): four independent rows in flight
+                    const uint32_t pa = one(r), pb = one(r + 4), pc = one(r + 8), pd = one(r + 12);
+                    finish_row(r, xvalid ? pa : 0u); finish_row(r + 4, xvalid ? pb : 0u);
+                    finish_row(r + 8, xvalid ? pc : 0u); finish_row(r + 12, xvalid ? pd : 0u);
+                    r += 16;
                 }
-                if (r < r_hi) {
-                    uint32_t pa = 0;
-                    if (xvalid) pa = one(r);
-                    finish_row(r, pa);
+#pragma unroll 1
+                for (; r < r_hi; r += 4) {
+                    const uint32_t pa = one(r);
+                    finish_row(r, xvalid ? pa : 0u);
                 }
             };
             if (staged) {
@@ -301,7 +331,9 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             }
         }
         if (j == 0) side_halo(0, tid);           // later blocks get theirs one iteration ahead, between the phases
+        TRW(5, 2);
         __syncthreads();                                                             // D
+        TRW(5, 3);
 
         // ---- between the phases, one job per warp: the source box of chunk j+2 (its buffer is free now), horizontal + vertical
         //      erosion of the new rows, the coordinate bases of chunk j+2, the side halo of chunk j+1, the canvas tile of chunk j+1 ----
@@ -323,13 +355,17 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 s_v[lane] = s_h[(y - 2) & (RING - 1)] & s_h[(y - 1) & (RING - 1)] & s_h[y & (RING - 1)] & s_h[(y + 1) & (RING - 1)] &
                             s_h[(y + 2) & (RING - 1)];
             }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&s_bar_v)) : "memory");
         } else if (warp == 2 || warp == 3) {
             if (j + 2 < n) row_bases(j + 2, tid - 64);
         } else if (warp < 7) {
             if (j + 1 < n) {
                 if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf ^ 1], (uint32_t)((j + 1) >> 1) & 1u, 300 + j);
                 __syncwarp();
+                TRW(5, 7);
                 side_halo(j + 1, tid - 128);
+                TRW(5, 8);
             }
         } else if (tid == 224) {
             if (j + 1 < n) {
@@ -337,7 +373,13 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 load_canvas(j + 1, buf ^ 1);
             }
         }
-        __syncthreads();                                                             // E
+#ifdef MK_STRIP_TRACE
+        if (lane == 0 && j < 8) s_role[j][warp] = clock64() - t_start;
+#endif
+        // E: phase 2 only needs warp 1's bit rows; the prefetch jobs of the other warps are for later chunks and are ordered by barrier F
+        if (lane == 0) mbar_wait_or_trap(&s_bar_v, (uint32_t)j & 1u, 500 + j);
+        __syncwarp();
+        TRW(5, 4);
 
         // ---- phase 2: thread = 4 consecutive pixels = 3 packed BGR words ---------------------------
         unsigned mb;
@@ -394,7 +436,9 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 fence_proxy_async();
             }
         }
+        TRW(5, 5);
         const int any = __syncthreads_or((int)mb);                                   // F
+        TRW(5, 6);
         if (tid == 224 && any) {
             tma_store_2d(&map_cv, tileX * 3, fy, smem_u32(&s_canvas[buf][0][0]));
             tma_store_2d(&map_mk, tileX, fy, smem_u32(&s_mask[buf][0][0]));
@@ -402,6 +446,145 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         }
     }
     if (tid == 224) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
+#ifdef MK_STRIP_TRACE
+    if (tid == 160 && (blockIdx.x == 0 || blockIdx.x == 200 || blockIdx.x == gridDim.x - 1)) {
+        unsigned smid; asm("mov.u32 %0, %smid;" : "=r"(smid));
+        for (int j = 0; j < n && j < 8; ++j)
+            printf("   blk %d roles j %d (end of between job, per warp): %lld %lld %lld %lld %lld %lld %lld %lld\n", blockIdx.x, j, s_role[j][0], s_role[j][1], s_role[j][2], s_role[j][3], s_role[j][4], s_role[j][5], s_role[j][6], s_role[j][7]),
+            printf("blk %d sm %u j %d: top %lld srcwait %lld | p1 end %lld D %lld | src(j+1) %lld halo end %lld | E %lld | p2 end %lld F %lld\n", blockIdx.x, smid, j, tr[j][0], tr[j][1], tr[j][2], tr[j][3],
+                   tr[j][7], tr[j][8], tr[j][4], tr[j][5], tr[j][6]);
+    }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3s: plain cv2.warpPerspective (3 channels) with the source footprint staged in shared memory.  One CTA per 64 x 32 output
+// tile (= one OpenCV coordinate block wide): the quantised images of the tile corners give the source rectangle, ONE 2-D TMA box
+// brings it in (zero fill outside the frame = BORDER_CONSTANT 0), the 8 warps sample it (two rows per iteration, the same
+// unchecked sampler as the compositing kernel), and the tile leaves as whole 16-byte vectors (three per 16 pixels).
+// ---------------------------------------------------------------------------------------------
+struct WarpStagedParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    const short *cubic;
+    const uint2 *lut;
+    unsigned long long spitch, dpitch;
+    int h, w, Hd, Wd;
+    int boxW, boxR, esz_shift;
+    InvMap M;
+};
+
+template <int INTERP>
+__global__ void __launch_bounds__(256, 4) warp_staged_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ WarpStagedParams p)
+{
+    __shared__ __align__(16) uint32_t s_px[TH][TW];
+    __shared__ __align__(16) double s_rowb[TH][4];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_rc[4];
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tileX = (int)blockIdx.x * TW, tileY = (int)blockIdx.y * TH;
+    const uint32_t box = (smem_u32(s_dyn) + 127u) & ~127u;
+    const int rows = min(TH, p.Hd - tileY);
+    if (tid == 64) mbar_init(&s_bar, 1);
+    if (warp == 0) {
+        int X = 0, Y = 0, sg = 0;
+        if (lane < 4) {
+            const int x1 = (lane & 1) ? min(TW, p.Wd - tileX) - 1 : 0, y = (lane & 2) ? tileY + rows - 1 : tileY;
+            double X0, Y0, W0;
+            row_base(p.M, tileX, y, X0, Y0, W0);
+            const double d1 = (double)x1;
+            quantize(p.M, X0, Y0, W0, dmul(p.M.m[0], d1), dmul(p.M.m[3], d1), dmul(p.M.m[6], d1), X, Y);
+            const double W = p.M.affine ? p.M.m[8] : dadd(W0, dmul(p.M.m[6], d1));
+            const bool sane = abs(X) < (1 << 30) && abs(Y) < (1 << 30);
+            sg = !sane ? 0 : ((W > 0.0) ? 1 : ((W < 0.0) ? -1 : 0));
+        }
+        int xlo = X, xhi = X, ylo = Y, yhi = Y, smin = sg, smax = sg;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+            ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+            smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        }
+        if (lane == 0) {
+            constexpr int LO = (INTERP == 1) ? 1 : 2, HI = (INTERP == 1) ? 2 : 3;
+            const int sx_lo = (xlo >> 5) - LO, sx_hi = (xhi >> 5) + HI, sy_lo = (ylo >> 5) - LO, sy_hi = (yhi >> 5) + HI;
+            const int bx0 = (sx_lo * 3) & ~15;
+            const bool fits = smin == smax && smin != 0 && (sx_hi * 3 + 3 - bx0) <= p.boxW && (sy_hi - sy_lo + 1) <= p.boxR;
+            s_rc[0] = sy_lo; s_rc[1] = bx0; s_rc[2] = fits ? 1 : 0;
+        }
+    } else if (warp == 1) {
+        if (lane < rows) {
+            double X0, Y0, W0;
+            row_base(p.M, tileX, tileY + lane, X0, Y0, W0);
+            s_rowb[lane][0] = X0; s_rowb[lane][1] = Y0; s_rowb[lane][2] = W0;
+        }
+    }
+    __syncthreads();
+    const int sy0 = s_rc[0], bx0 = s_rc[1];
+    const bool staged = s_rc[2] != 0;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s_bar, staged ? (uint32_t)(p.boxW * p.boxR) : 0u);
+        if (staged) tma_load_2d(box, &map_src, bx0 >> p.esz_shift, sy0, &s_bar);
+    }
+    const int cx = (warp & 1) * 32 + lane;
+    const double d1 = (double)cx;
+    const double mx = dmul(p.M.m[0], d1), my = dmul(p.M.m[3], d1), mw = dmul(p.M.m[6], d1);
+    if (lane == 0) mbar_wait_or_trap(&s_bar, 0u, 400);
+    __syncwarp();
+    {
+        const bool xvalid = tileX + cx < p.Wd;
+        auto body = [&](auto fast_tag, auto affine_tag) {
+            constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
+            const double wr = p.M.wr;
+            SrcTile T;
+            T.s = s_dyn + (box - smem_u32(s_dyn)); T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
+            auto one = [&](int r) -> uint32_t {
+                const double X0 = s_rowb[r][0], Y0 = s_rowb[r][1], W0 = s_rowb[r][2];
+                int X, Y;
+                if constexpr (FAST) quantize_fast_t<AFF>(p.M, wr, X0, Y0, W0, mx, my, mw, X, Y);
+                else quantize(p.M, X0, Y0, W0, mx, my, mw, X, Y);
+                if constexpr (FAST && INTERP == 1) return sample_linear_box(box, p.boxW, sy0, bx0, X, Y, p.lut);
+                else return sample_c3_tile<INTERP>(FAST, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
+            };
+            int r = warp >> 1;
+#pragma unroll 1
+            for (; r + 4 < rows; r += 8) {
+                uint32_t pa = 0, pb = 0;
+                if (xvalid) { pa = one(r); pb = one(r + 4); }
+                s_px[r][cx] = pa; s_px[r + 4][cx] = pb;
+            }
+            if (r < rows) s_px[r][cx] = xvalid ? one(r) : 0u;
+        };
+        if (staged) {
+            if (p.M.affine) body(std::true_type{}, std::true_type{});
+            else body(std::true_type{}, std::false_type{});
+        } else {
+            body(std::false_type{}, std::false_type{});
+        }
+    }
+    __syncthreads();
+    // 16 pixels = 48 bytes = three 16-byte vectors per thread
+    if (tid < TH * 4) {
+        const int r = tid >> 2, seg = tid & 3, y = tileY + r, x = tileX + 16 * seg;
+        if (r < rows && x < p.Wd) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(&s_px[r][16 * seg]);
+            uint32_t o[12];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 v = q[g];
+                o[3 * g + 0] = __byte_perm(v.x, v.y, 0x4210); o[3 * g + 1] = __byte_perm(v.y, v.z, 0x5421); o[3 * g + 2] = __byte_perm(v.z, v.w, 0x6542);
+            }
+            uint8_t *d = p.dst + (size_t)y * p.dpitch + (size_t)x * 3;
+            const int nb = min(16, p.Wd - x) * 3;
+            if (nb == 48) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(d);
+                d4[0] = make_uint4(o[0], o[1], o[2], o[3]); d4[1] = make_uint4(o[4], o[5], o[6], o[7]); d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            } else {
+                for (int b = 0; b < nb; ++b) d[b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -573,6 +756,7 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
         maxc += ceil(maxc / 32); maxr += ceil(maxr / 32);      // slack for blocks between the probes (perspective)
         if (maxc <= 0 || maxr <= 0 || maxc > 1000 || maxr > 256) return MK_OK;
         boxW = (((int)maxc * 3 + 3 + 15) + 15) & ~15;      // + 15: the box starts at a 16-byte boundary
+        if (!(boxW & 16)) boxW += 16;                      // odd number of 16-byte units per row: the rows a warp touches fall into different banks
         boxR = (int)maxr;
     }
     int esz = 1;
@@ -604,6 +788,72 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
     if (interp == MK_INTER_LINEAR) mapper_strip_kernel<MK_INTER_LINEAR><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
     else mapper_strip_kernel<MK_INTER_CUBIC><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
     MK_LAUNCH_CHECK("mapper_strip_kernel");
+    *done = true;
+    return MK_OK;
+}
+
+// Staged form of mk_warp_perspective_u8 for 3-channel images whose source is 16-byte aligned; *done = false -> use warp_kernel.
+int launch_warp_staged(const uint8_t *src, int h, int w, size_t spitch, const InvMap &M, uint8_t *dst, int Hd, int Wd, size_t dpitch, int interp,
+                       const short *cubic, const uint2 *lut, cudaStream_t st, bool *done)
+{
+    *done = false;
+    static const bool disabled = [] { const char *e = getenv("MK_STRIP"); return e && e[0] == '0'; }();
+    if (disabled || !aligned(src, 16) || (spitch & 15)) return MK_OK;
+    const int lohi = (interp == MK_INTER_CUBIC) ? 5 : 3;
+    double maxc = 0, maxr = 0;
+    int sign = 0;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            const double x0 = (a == 0) ? 0 : (a == 1) ? (Wd / 2 / TW) * TW : ((Wd - 1) / TW) * TW, y0 = (b == 0) ? 0 : (b == 1) ? (Hd / 2 / TH) * TH : ((Hd - 1) / TH) * TH;
+            double minu = 1e300, maxu = -1e300, minv = 1e300, maxv = -1e300;
+            for (int c = 0; c < 4; ++c) {
+                const double x = x0 + ((c & 1) ? TW - 1 : 0), y = y0 + ((c & 2) ? TH - 1 : 0);
+                const double W = M.m[6] * x + M.m[7] * y + M.m[8];
+                const int sg = (W > 0) - (W < 0);
+                if (sg == 0 || (sign && sg != sign)) return MK_OK;
+                sign = sg;
+                const double u = (M.m[0] * x + M.m[1] * y + M.m[2]) / W, v = (M.m[3] * x + M.m[4] * y + M.m[5]) / W;
+                minu = fmin(minu, u); maxu = fmax(maxu, u); minv = fmin(minv, v); maxv = fmax(maxv, v);
+            }
+            if (!isfinite(minu) || !isfinite(maxu) || !isfinite(minv) || !isfinite(maxv)) return MK_OK;
+            maxc = fmax(maxc, ceil(maxu - minu) + 2 + lohi); maxr = fmax(maxr, ceil(maxv - minv) + 2 + lohi);
+        }
+    maxc += ceil(maxc / 32); maxr += ceil(maxr / 32);
+    if (maxc <= 0 || maxr <= 0 || maxc > 1000 || maxr > 256) return MK_OK;
+    int boxW = (((int)maxc * 3 + 3 + 15) + 15) & ~15;
+    if (!(boxW & 16)) boxW += 16;          // odd number of 16-byte units per row (shared-memory banks)
+    const int boxR = (int)maxr;
+    int esz = 1;
+    if (boxW > 256) {
+        if ((w & 3) != 0 || boxW > 1024) return MK_OK;
+        esz = 4;
+    }
+    const int dyn = ((boxW * boxR + 127) & ~127) + 128;
+    if (dyn > 64 * 1024) return MK_OK;
+    {
+        static std::mutex mu;
+        static int conf_dev[2] = { -1, -1 }, conf_smem[2] = { 0, 0 };
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        const int k = interp == MK_INTER_LINEAR ? 0 : 1;
+        if (conf_dev[k] != dev || dyn > conf_smem[k]) {
+            const int want = std::max(dyn, 48 * 1024);
+            if (k == 0) MK_CUDA_TRY(cudaFuncSetAttribute(warp_staged_kernel<MK_INTER_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            else MK_CUDA_TRY(cudaFuncSetAttribute(warp_staged_kernel<MK_INTER_CUBIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+            conf_dev[k] = dev; conf_smem[k] = want;
+        }
+    }
+    WarpStagedParams P{};
+    P.src = src; P.dst = dst; P.cubic = cubic; P.lut = lut; P.spitch = spitch; P.dpitch = dpitch; P.h = h; P.w = w; P.Hd = Hd; P.Wd = Wd;
+    P.boxW = boxW; P.boxR = boxR; P.esz_shift = esz == 4 ? 2 : 0; P.M = M;
+    alignas(64) CUtensorMap map_src;
+    const int rc = encode_image_map(&map_src, src, esz, (long)w * 3 / esz, h, spitch, boxW / esz, boxR);
+    if (rc != MK_OK) return rc;
+    dim3 grid((Wd + TW - 1) / TW, (Hd + TH - 1) / TH);
+    if (interp == MK_INTER_LINEAR) warp_staged_kernel<MK_INTER_LINEAR><<<grid, 256, (size_t)dyn, st>>>(map_src, P);
+    else warp_staged_kernel<MK_INTER_CUBIC><<<grid, 256, (size_t)dyn, st>>>(map_src, P);
+    MK_LAUNCH_CHECK("warp_staged_kernel");
     *done = true;
     return MK_OK;
 }
