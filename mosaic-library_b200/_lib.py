@@ -11,7 +11,8 @@ import subprocess
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libmosaic_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("MOSAIC_B200_LIB", PKG_DIR / "libmosaic_b200.so"))     # the override is for A/B builds of the same sources
 CSRC = PKG_DIR / "csrc"
 
 MK_OK = 0

@@ -34,7 +34,13 @@ constexpr int RING = 64;             // ring of warped rows / bit rows, indexed 
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
 constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
-constexpr int STRIP_OCC = 3;         // CTAs per SM the register budget is set for (four rows per warp in flight need ~80 registers)
+#ifndef MK_STRIP_OCC
+#define MK_STRIP_OCC 3
+#endif
+#ifndef MK_STRIP_ILP
+#define MK_STRIP_ILP 4
+#endif
+constexpr int STRIP_OCC = MK_STRIP_OCC;   // CTAs per SM the register budget is set for (four rows per warp in flight need ~76 registers)
 
 struct StripParams {
     const short *cubic;
@@ -311,12 +317,20 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                     else return sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
                 };
                 int r = r_lo + (warp >> 1);
+#if MK_STRIP_ILP == 4
                 if (r + 12 < r_hi) {              // the usual case (16 or 20 rows inside the canvas): four independent rows in flight
                     const uint32_t pa = one(r), pb = one(r + 4), pc = one(r + 8), pd = one(r + 12);
                     finish_row(r, xvalid ? pa : 0u); finish_row(r + 4, xvalid ? pb : 0u);
                     finish_row(r + 8, xvalid ? pc : 0u); finish_row(r + 12, xvalid ? pd : 0u);
                     r += 16;
                 }
+#else
+#pragma unroll 1
+                for (; r + 4 < r_hi; r += 8) {    // two independent rows in flight
+                    const uint32_t pa = one(r), pb = one(r + 4);
+                    finish_row(r, xvalid ? pa : 0u); finish_row(r + 4, xvalid ? pb : 0u);
+                }
+#endif
 #pragma unroll 1
                 for (; r < r_hi; r += 4) {
                     const uint32_t pa = one(r);
