@@ -458,6 +458,7 @@ def single_gpu(ctx) -> dict:
     del frames, desc_d
     torch.cuda.empty_cache()
     out["config2"] = config2_record(ctx, iso)
+    out["config3"] = config3_record(ctx, torch.cuda.synchronize, lambda x: x, lambda vals: [float(v) for v in vals])
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(ctx, Hs, desc_h, fw, fh, W, budget_s=args.cpu_budget)
     return out
@@ -936,17 +937,25 @@ def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
     dev_ring = [torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
     main = torch.cuda.current_stream(dev)
 
+    slot_free = [torch.cuda.Event() for _ in range(3)]       # the step that last read ring slot s has finished
+    slot_full = [torch.cuda.Event() for _ in range(3)]
+    for e in slot_free:
+        e.record(main)
+
     def loop(k0, n):
         kept, pending = 0, None
         for k in range(k0, k0 + n):
             q, t = pin_desc[(k + 1) % 8].numpy(), pin_desc[k % 8].numpy()
             nxt = matcher.knn_match_arrays_async(q, t, RATIO)
-            d = dev_ring[k % 3]
-            with torch.cuda.stream(copy_stream):
-                d.copy_(pin_frames[k % 4], non_blocking=True)          # H2D of the frame on a side stream
-            main.wait_stream(copy_stream)
+            sl = k % 3
+            d = dev_ring[sl]
+            with torch.cuda.stream(copy_stream):                       # H2D of frame k on a side stream: it overlaps the step of frame k-1
+                copy_stream.wait_event(slot_free[sl])
+                d.copy_(pin_frames[k % 4], non_blocking=True)
+                slot_full[sl].record(copy_stream)
+            main.wait_event(slot_full[sl])
             mosaic.step_planned(k % nfr, d)
-            copy_stream.wait_stream(main)
+            slot_free[sl].record(main)
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
@@ -1003,7 +1012,7 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
         Hs = []
         for l in lanes:
             Hs += [lane_pose(k, l, fw, fh) for k in range(nper)]
-        mosaic = ShardedMosaic(BIG_GRID, (CANVAS, CANVAS), factory, (fh, fw), dev)
+        mosaic = ShardedMosaic(BIG_GRID, (CANVAS, CANVAS), factory, (fh, fw), dev, rank=rank, world=world)
         mosaic.connect()
         mosaic.plan(np.stack(Hs))
         n = len(Hs)
