@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .mosaic import bbox_overlap, combine_tiles, get_corners, homogeneous_translation
+from .mosaic import bbox_overlap, get_corners, homogeneous_translation
 
 
 def tiles_of_footprint(H: np.ndarray, width: int, height: int, tile_size: tuple[int, int], grid: tuple[int, int]):
@@ -65,6 +65,7 @@ class ShardedMosaic:
         self._posted = {}        # step -> exchange posted ahead of time (step_planned with next_frame)
         self.frames_applied = 0
         self.bytes_sent = 0
+        self._host_group = None   # gloo group for the host-side pose exchange of the unplanned step()
 
     def owner(self, tile: tuple[int, int]) -> int:
         return (tile[1] * self.grid[0] + tile[0]) % self.world
@@ -95,10 +96,22 @@ class ShardedMosaic:
             mine = torch.from_numpy(np.ascontiguousarray(np.asarray(H, np.float64).reshape(9)))
         if self.world == 1:
             return [None if H is None else np.asarray(H, np.float64).reshape(3, 3)]
-        mine = mine.to(self.device)
-        out = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(out, mine)
-        allH = torch.stack(out).cpu().numpy()
+        # the poses are needed on the HOST (routing is host logic): exchange them over a host-side (gloo) group, so the
+        # per-frame path neither copies them to the device and back nor synchronises the GPU
+        if self._host_group is None and self.device.type == "cuda":
+            try:
+                self._host_group = dist.new_group(backend="gloo")
+            except Exception:            # no gloo in this build: fall back to the device group (one small D2H per frame)
+                self._host_group = False
+        if self._host_group:
+            out = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(out, mine, group=self._host_group)
+            allH = torch.stack(out).numpy()
+        else:
+            mine = mine.to(self.device)
+            out = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(out, mine)
+            allH = torch.stack(out).cpu().numpy()
         return [None if np.isnan(a[0]) else a.reshape(3, 3) for a in allH]
 
     def connect(self) -> None:
@@ -197,22 +210,44 @@ class ShardedMosaic:
         self.frames_applied += done
         return done
 
-    def gather(self, dst: int = 0) -> np.ndarray | None:
-        """combine_tiles (examples/combine_tiles.py:46-62): every tile travels to rank `dst`, which
-        pastes tile (x, y) at (x*tile_w, y*tile_h).  Tiles nobody touched stay black, like missing PNGs."""
-        local = {t: m.output for t, m in self.mappers.items()}
+    def _tile_tensor(self, tile) -> torch.Tensor:
+        """Contiguous [tile_h, tile_w, 3] uint8 tensor of an owned tile on self.device."""
+        m = self.mappers[tile]
+        t = m.output_device if hasattr(m, "output_device") else torch.from_numpy(np.ascontiguousarray(m.output))
+        return t.to(self.device).contiguous()
+
+    def gather(self, dst: int = 0, out: np.ndarray | None = None) -> np.ndarray | None:
+        """combine_tiles (examples/combine_tiles.py:46-62): every touched tile travels to rank `dst`, which pastes tile (x, y) at
+        (x*tile_w, y*tile_h) of one host canvas.  Tiles nobody touched stay black, like missing PNGs.  The tiles move as
+        device tensors (ncclSend / ncclRecv, one tile-sized staging buffer on `dst`), never through pickle; `out` may be a
+        caller-provided (e.g. page-locked) [grid_h*tile_h, grid_w*tile_w, 3] uint8 array."""
+        tw, th = self.tile_size
+        mine = sorted(self.mappers.keys())
         if self.world == 1:
-            tiles = local
+            owned = [mine]
         else:
-            box = [None] * self.world if self.rank == dst else None
-            dist.gather_object(local, box, dst=dst)
-            if self.rank != dst:
-                return None
-            tiles = {}
-            for part in box:
-                tiles.update(part)
-        tiles.setdefault((self.grid[0] - 1, self.grid[1] - 1), np.zeros((self.tile_size[1], self.tile_size[0], 3), np.uint8))
-        return combine_tiles(tiles, self.tile_size)
+            owned = [None] * self.world
+            dist.all_gather_object(owned, mine)            # tile coordinates only (a few bytes)
+        if self.rank != dst:
+            for t in mine:
+                dist.send(self._tile_tensor(t), dst)
+            return None
+        if out is None:
+            out = np.zeros((self.grid[1] * th, self.grid[0] * tw, 3), np.uint8)
+        else:
+            assert out.shape == (self.grid[1] * th, self.grid[0] * tw, 3) and out.dtype == np.uint8
+        stage = None
+        for r, tiles in enumerate(owned):
+            for (xi, yi) in tiles:
+                if r == self.rank:
+                    src = self._tile_tensor((xi, yi))
+                else:
+                    if stage is None:
+                        stage = torch.empty((th, tw, 3), dtype=torch.uint8, device=self.device)
+                    dist.recv(stage, r)
+                    src = stage
+                out[yi * th:(yi + 1) * th, xi * tw:(xi + 1) * tw] = src.cpu().numpy()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(512) k(uint32_t *out, uint32_t seed, long long
             if (MODE == 5) { a[i] = __byte_perm(a[i], b[i], 0x5410); b[i] = __byte_perm(b[i], a[i], 0x1032); } // 2 PRMT
             if (MODE == 6) { a[i] = __float_as_uint(__uint_as_float(a[i]) + 8388608.0f); b[i] = __float_as_uint(__uint_as_float(b[i]) + 8388608.0f); }  // 2 FADD
             if (MODE == 7) { a[i] = min((int)a[i], (int)c[i]); b[i] = max((int)b[i], (int)c[i]); }             // 2 VIMNMX (s32)
+            if (MODE == 9) { a[i] = __popc(a[i] ^ c[i]) + a[i]; b[i] = __popc(b[i] ^ c[i]) + b[i]; }           // 2 (POPC + dependent IADD): the POPC issue rate is what is read off
+            if (MODE == 10) { a[i] = __dp2a_lo((int)a[i], (int)c[i], (int)a[i]); b[i] = __dp2a_hi((int)b[i], (int)c[i], (int)b[i]); }   // 2 IDP.2A
             if (MODE == 8) { __half2 x = *(__half2 *)&a[i], y = *(__half2 *)&b[i]; __half2 z = *(__half2 *)&c[i]; x = __hmin2(x, z); a[i] = *(uint32_t *)&x; b[i] = b[i] * 0x10001u + c[i]; }  // HMNMX2 + IMAD
         }
     }
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(512) k(uint32_t *out, uint32_t seed, long long
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
+
+static double g_last = 0;   // warp-instructions / cycle / SM of the last run()
 
 template <int MODE>
 void run(const char *name)
@@ -50,6 +54,7 @@ void run(const char *name)
     double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
     const double winst = 16.0 * ITER * NCH * 2;   // warp-instructions per SM (16 warps)
     printf("%-22s %8.0f cycles  %.2f warp-inst/cycle/SM (%.2f per SMSP)\n", name, c, winst / c, winst / c / 4);
+    g_last = winst / c;
     cudaFree(out); cudaFree(cyc);
 }
 
@@ -57,5 +62,13 @@ int main()
 {
     run<0>("VIMNMX.U16x2 x2"); run<7>("VIMNMX.S32 x2"); run<1>("HMNMX2 x2"); run<2>("IMAD x2"); run<5>("PRMT x2"); run<6>("FADD x2");
     run<3>("VIMNMX16 + HMNMX2"); run<4>("VIMNMX16 + IMAD"); run<8>("HMNMX2 + IMAD");
+    run<10>("IDP.2A x2");
+    // POPC: the loop body issues one POPC and one IADD per chain step; the pair count per cycle is the POPC rate when POPC is the slower pipe
+    run<9>("(POPC + IADD) x2");
+    int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const double popc_warp_per_clk_sm = g_last;                 // run() counts two instructions per chain step = the two POPCs
+    printf("{\"popc_warp_inst_per_clk_per_sm\": %.3f, \"popc_lanes_per_clk_per_sm\": %.1f, \"sms\": %d, \"sm_clock_mhz\": %.0f, \"popc32_per_s\": %.4e}\n",
+           popc_warp_per_clk_sm, popc_warp_per_clk_sm * 32, sms, clk_khz / 1e3, popc_warp_per_clk_sm * 32 * sms * (clk_khz * 1e3));
     return 0;
 }
