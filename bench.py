@@ -1007,8 +1007,10 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
     factory = lambda w_, h_: mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", device=dev)  # noqa: E731
     res = {"workload": "BASELINE configs[3]: 3840x2160 frames, 65536x65536 canvas = 4x4 tiles of 16384^2 sharded over the ranks, footprint routing (ncclSend/Recv), compositing only"}
 
-    def run(lanes, nper, tag):
-        """this rank ingests `lanes` (list of lane ids), nper frames each, lane after lane"""
+    def run(lanes, nper, tag, transport="nccl"):
+        """this rank ingests `lanes` (list of lane ids), nper frames each, lane after lane; transport "nccl" sends a routed frame to
+        the neighbour (ncclSend/Recv, posted one step ahead), "peer" lets the neighbour's kernel read it in place over NVLink"""
+        from mosaicking_b200.distributed import PeerFrames
         Hs = []
         for l in lanes:
             Hs += [lane_pose(k, l, fw, fh) for k in range(nper)]
@@ -1020,8 +1022,14 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
             for s, dests in enumerate(mosaic._plan_table[k]):
                 for t in dests.get(rank, []):
                     mosaic._mapper(t)
+        peers = PeerFrames([ring[k % 4] for k in range(n)], dev, rank=rank, world=world) if transport == "peer" else None
+        def step(k, last):
+            if peers is not None:
+                mosaic.step_planned(k, None, peers=peers)
+            else:
+                mosaic.step_planned(k, ring[k % 4], None if last else ring[(k + 1) % 4])
         for k in range(min(2, n)):                       # warm-up (first launches, NCCL buffers)
-            mosaic.step_planned(k, ring[k % 4], ring[(k + 1) % 4] if k + 1 < min(2, n) else None)
+            step(k, k + 1 >= min(2, n))
         mosaic._posted.clear()
         barrier()
         sent0, app0 = mosaic.bytes_sent, mosaic.frames_applied
@@ -1029,9 +1037,11 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
         barrier()
         e0.record()
         for k in range(n):
-            mosaic.step_planned(k, ring[k % 4], ring[(k + 1) % 4] if k + 1 < n else None)
+            step(k, k + 1 >= n)
         e1.record()
         barrier()
+        if peers is not None:
+            peers.close()
         ms = max_over_ranks(e0.elapsed_time(e1))
         routed, applied = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - app0])
         mosaic.mappers.clear()
@@ -1044,6 +1054,12 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
     res["weak"]["note"] = f"{kw} frames per rank, one lane per rank, device-resident 4K frames (ring of 4 per rank), back to back, CUDA events, max over ranks"
     res["strong"] = run([l for l in range(8) if l % world == rank], 8, "strong")
     res["strong"]["note"] = "fixed 64-frame set (8 lanes x 8 frames), lane l ingested by rank l % N; divide by the N=1 time for the speed-up"
+    if world > 1:
+        res["weak_peer"] = run([rank], kw, "weak", "peer")
+        res["strong_peer"] = run([l for l in range(8) if l % world == rank], 8, "strong", "peer")
+        res["strong_peer"]["note"] = ("same sets, no frame copies: the owner of the neighbouring tile composites straight out of the ingest GPU's memory "
+                                      "(cudaIpc mapping, the kernel's TMA source boxes cross NVLink); frame_bytes_routed is the upper bound (whole frames), "
+                                      "only the footprint's source rectangles move")
     return res
 
 

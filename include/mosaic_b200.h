@@ -214,6 +214,21 @@ int mk_ransac_transform(int model, const float *src_xy, const float *dst_xy, int
                         void *stream);
 int mk_chain_homographies(const double *H, int n, double *H_abs, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Peer memory over NVLink / NVSwitch for the tile-sharded canvas (one process per GPU; src/mosaicking/mosaic.py:595-622 routes a
+ * frame to every tile its footprint overlaps).  The rank that holds a frame exports its allocation, the ranks owning the other
+ * overlapped tiles map it and pass the mapped pointer as `src` of mk_mapper_update: the compositing kernel then pulls exactly the
+ * source rectangles its tiles need out of the ingest GPU's HBM (2-D TMA boxes over NVLink) -- no copy of the whole frame, no
+ * collective, the transfer overlaps the arithmetic tile by tile.
+ *   mk_ipc_export   handle_out[64] + byte offset of dev_ptr inside its allocation (cudaIpcGetMemHandle on the allocation base)
+ *   mk_ipc_open     maps the allocation in the calling process (peer access enabled lazily); pointer = *base_out + offset.
+ *                   Open a given handle once per process and mk_ipc_close it before the exporter frees the memory.
+ * Ordering is the callers' business: the exporter must have finished writing the frame, and must keep it, while peers read it.
+ * ------------------------------------------------------------------------------------- */
+int mk_ipc_export(const void *dev_ptr, uint8_t *handle_out, uint64_t *offset_out);
+int mk_ipc_open(const uint8_t *handle, void **base_out);
+int mk_ipc_close(void *base);
+
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */
 int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,

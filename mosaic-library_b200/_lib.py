@@ -27,6 +27,7 @@ EXPORTS = (
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
     "mk_event_create", "mk_event_destroy", "mk_stream_follow", "mk_sm_partition_create", "mk_sm_partition_destroy",
     "mk_gather_matches", "mk_ransac_workspace_bytes", "mk_ransac_transform", "mk_chain_homographies",
+    "mk_ipc_export", "mk_ipc_open", "mk_ipc_close",
 )
 MODEL_AFFINE, MODEL_PERSPECTIVE = 0, 1
 
@@ -101,6 +102,12 @@ def lib() -> C.CDLL:
     L.mk_ransac_transform.argtypes = [i32, vp, vp, i32, vp, f64, i32, C.c_uint64, vp, vp, vp, vp, vp]
     L.mk_chain_homographies.restype = i32
     L.mk_chain_homographies.argtypes = [vp, i32, vp, vp]
+    L.mk_ipc_export.restype = i32
+    L.mk_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.mk_ipc_open.restype = i32
+    L.mk_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    L.mk_ipc_close.restype = i32
+    L.mk_ipc_close.argtypes = [vp]
     if L.mk_abi_version() != 1:
         raise MosaicB200Error("libmosaic_b200 ABI version mismatch")
     _lib = L

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include <stdarg.h>
+#include <string.h>
 
 namespace mk {
 
@@ -197,3 +198,46 @@ int stream_sm_count(cudaStream_t stream)
     return count;
 }
 }  // namespace mk
+
+// ---------------------------------------------------------------------------------------------
+// Peer memory over NVLink / NVSwitch for the tile-sharded canvas (one process per GPU): export a device allocation, map it in
+// the other ranks, hand the mapped pointer to mk_mapper_update as `src`.
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+
+extern "C" int mk_ipc_export(const void *dev_ptr, uint8_t *handle_out, uint64_t *offset_out)
+{
+    if (!dev_ptr || !handle_out || !offset_out) { mk::set_error("mk_ipc_export: null pointer"); return MK_ERR_ARG; }
+    static GetAddressRangeFn fn = [] {
+        void *q = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) q = nullptr;
+        return reinterpret_cast<GetAddressRangeFn>(q);
+    }();
+    if (!fn) { mk::set_error("mk_ipc_export: cuMemGetAddressRange not available"); return MK_ERR_CUDA; }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS) { mk::set_error("mk_ipc_export: cuMemGetAddressRange failed (not a device allocation?)"); return MK_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    MK_CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(base)));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, 64);
+    *offset_out = (uint64_t)((CUdeviceptr)dev_ptr - base);
+    return MK_OK;
+}
+
+extern "C" int mk_ipc_open(const uint8_t *handle, void **base_out)
+{
+    if (!handle || !base_out) { mk::set_error("mk_ipc_open: null pointer"); return MK_ERR_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    MK_CUDA_TRY(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return MK_OK;
+}
+
+extern "C" int mk_ipc_close(void *base)
+{
+    if (!base) return MK_OK;
+    MK_CUDA_TRY(cudaIpcCloseMemHandle(base));
+    return MK_OK;
+}

@@ -46,6 +46,69 @@ def tiles_of_footprint(H: np.ndarray, width: int, height: int, tile_size: tuple[
     return out
 
 
+class PeerFrames:
+    """The frames of EVERY rank, readable from this rank without a copy: local tensors stay where they are, the other ranks'
+    frames are mapped into this process through cudaIpc (mk_ipc_export / mk_ipc_open, include/mosaic_b200.h) and read by the
+    compositing kernel over NVLink / NVSwitch -- it pulls only the source rectangles its tiles need.
+
+    frames: this rank's frames, uint8 [h, w, 3] contiguous CUDA tensors (all ranks pass the same number).  Collective: every rank
+    must construct it at the same time.  The frames must stay alive and unchanged until every rank has called close()."""
+
+    def __init__(self, frames: Sequence[torch.Tensor], device, rank: int | None = None, world: int | None = None):
+        import ctypes as C
+
+        from . import _lib
+        self._lib = _lib.lib()
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.device = device
+        self.frames = list(frames)
+        for f in self.frames:
+            assert f.is_cuda and f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.is_contiguous()
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)                     # the frames are complete before anybody else may read them
+        mine = []
+        for f in self.frames:
+            h = (C.c_uint8 * 64)()
+            off = C.c_uint64(0)
+            _lib.check(self._lib.mk_ipc_export(f.data_ptr(), h, C.byref(off)))
+            mine.append((bytes(h), int(off.value), int(f.shape[0]), int(f.shape[1])))
+        if self.world == 1:
+            everyone = [mine]
+        else:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)            # 64-byte handles + offsets, once
+        self._bases: dict[bytes, int] = {}
+        self.ptr: list[list[tuple[int, int, int]]] = []        # [source rank][k] -> (device pointer, h, w)
+        with torch.cuda.device(device):
+            for r, lst in enumerate(everyone):
+                row = []
+                for k, (hb, off, fh, fw) in enumerate(lst):
+                    if r == self.rank:
+                        row.append((self.frames[k].data_ptr(), fh, fw))
+                        continue
+                    base = self._bases.get(hb)
+                    if base is None:
+                        out = C.c_void_p(0)
+                        buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                        _lib.check(self._lib.mk_ipc_open(buf, C.byref(out)))
+                        base = self._bases[hb] = int(out.value)
+                    row.append((base + off, fh, fw))
+                self.ptr.append(row)
+        if self.world > 1:
+            dist.barrier()                                     # everyone has mapped everyone before anyone may finish and free
+
+    def close(self) -> None:
+        """Collective: unmap the peers' allocations (after every rank is done reading)."""
+        if self.world > 1:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            dist.barrier()
+        for base in self._bases.values():
+            self._lib.mk_ipc_close(base)
+        self._bases.clear()
+
+
 class ShardedMosaic:
     """Canvas of grid[0] x grid[1] tiles, tile (xi, yi) owned by rank (yi * grid[0] + xi) % world.
 
@@ -146,12 +209,17 @@ class ShardedMosaic:
         self._plan_H = allH.reshape(self.world, -1, 3, 3)
         self._plan_table = [self.routing([self._plan_H[s, k] for s in range(self.world)]) for k in range(self._plan_H.shape[1])]
 
-    def step_planned(self, k: int, frame: torch.Tensor, next_frame: torch.Tensor | None = None) -> int:
+    def step_planned(self, k: int, frame: torch.Tensor | None, next_frame: torch.Tensor | None = None, peers: "PeerFrames | None" = None) -> int:
         """Step k of a planned sequence: no collective, only the frame send/recv the routing asks for.
         With `next_frame` (this rank's frame of step k+1, already on the device) the exchange of step k+1 is posted BEFORE
         step k is composited, so the NVLink transfer runs under the kernels of step k (receive buffers alternate by step
-        parity).  Every rank must then pass next_frame for the same steps, and the next call must be step k+1."""
+        parity).  Every rank must then pass next_frame for the same steps, and the next call must be step k+1.
+        With `peers` (PeerFrames over every rank's frames of the planned sequence) nothing is sent at all: a frame that another
+        rank ingested is composited straight out of that GPU's memory (the kernel's TMA loads cross NVLink), frame k of rank s
+        being peers.ptr[s][k]."""
         H_all = [self._plan_H[s, k] for s in range(self.world)]
+        if peers is not None:
+            return self._composite_peer(k, H_all, self._plan_table[k], peers)
         posted = self._posted.pop(k, None)
         if posted is None:
             posted = self._post(frame, self._plan_table[k], k & 1)
@@ -215,6 +283,21 @@ class ShardedMosaic:
         m = self.mappers[tile]
         t = m.output_device if hasattr(m, "output_device") else torch.from_numpy(np.ascontiguousarray(m.output))
         return t.to(self.device).contiguous()
+
+    def _composite_peer(self, k: int, H_all, table, peers: "PeerFrames") -> int:
+        done = 0
+        for s, dests in enumerate(table):
+            if self.rank not in dests:
+                continue
+            ptr, fh, fw = peers.ptr[s][k]
+            for (xi, yi) in dests[self.rank]:
+                H_tile = homogeneous_translation(-xi * self.tile_size[0], -yi * self.tile_size[1]) @ H_all[s]   # mosaic.py:617
+                self._mapper((xi, yi)).update_pointer(ptr, fh, fw, fw * 3, H_tile)
+                done += 1
+                if s != self.rank:
+                    self.bytes_sent += fh * fw * 3        # upper bound of what crosses NVLink: only the footprint's source rectangles do
+        self.frames_applied += done
+        return done
 
     def gather(self, dst: int = 0, out: np.ndarray | None = None) -> np.ndarray | None:
         """combine_tiles (examples/combine_tiles.py:46-62): every touched tile travels to rank `dst`, which pastes tile (x, y) at

@@ -143,6 +143,12 @@ class Mapper:
             return
         self._update_any(frame, H, roi)
 
+    def update_pointer(self, ptr: int, h: int, w: int, pitch: int, H: np.ndarray) -> None:
+        """update_device for a raw device pointer to a BGR uint8 frame [h][pitch] -- e.g. a frame that lives in ANOTHER GPU's
+        memory and was mapped with distributed.PeerFrames (cudaIpc): the kernel reads the footprint it needs over NVLink.
+        The pointer must be 4-byte aligned with pitch % 4 == 0 (16 / 16 for the TMA-staged fast path)."""
+        self._launch_raw(int(ptr), int(h), int(w), int(pitch), H, self._device)
+
     def _launch_raw(self, ptr: int, h: int, w: int, pitch: int, H, device) -> None:
         Hm = H if (isinstance(H, np.ndarray) and H.dtype == np.float64 and H.shape == (3, 3) and H.flags.c_contiguous) else \
             np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
