@@ -823,15 +823,38 @@ def multi_gpu(ctx) -> dict:
     s_match = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
 
+    from mosaicking_b200.distributed import PeerFrames
+    peers = PeerFrames(frames, dev)          # every rank's frames mapped into every rank (cudaIpc): the "peer" transport reads them in place
+    transport = {"mode": args.transport}
+
     def one_step(k, ev=None, last=False):
         if ev: ev[0].record(main)
         s_match.wait_stream(main)
         with torch.cuda.stream(s_match):
             matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
-        mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # frame exchange of step k+1 posted under step k
+        if transport["mode"] == "peer":
+            mosaic.step_planned(k, None, peers=peers)                            # routed frames are composited straight out of the ingest GPU's memory
+        else:
+            mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # ncclSend/Recv, the exchange of step k+1 posted under step k
         main.wait_stream(s_match)
         if ev: ev[1].record(main)
 
+    def timed_steps():
+        evs_ = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+        barrier()
+        for k in range(K):
+            flush.zero_()
+            one_step(W + k, evs_[k], last=(k == K - 1))
+        barrier()
+        return max_over_ranks(float(sum(e[0].elapsed_time(e[1]) for e in evs_)))
+
+    other = "nccl" if args.transport == "peer" else "peer"
+    transport["mode"] = other                        # the other transport first (untimed warm-up + one timed pass), then the headline
+    for k in range(W):
+        one_step(k, last=(k == W - 1))
+    other_ms = timed_steps()
+    mosaic._posted.clear()
+    transport["mode"] = args.transport
     for k in range(W):
         one_step(k, last=(k == W - 1))
     barrier()
@@ -894,14 +917,19 @@ def multi_gpu(ctx) -> dict:
             "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching on its own (ordinary) stream, same policy as N=1",
             "blend": "alpha", "interp": "linear", "canvas": [BIG_GRID[0] * CANVAS, BIG_GRID[1] * CANVAS], "tile": [CANVAS, CANVAS], "frame": [fw, fh],
             "tile_updates_total": int(applied), "frame_bytes_routed_total": int(routed), "frame_bytes_routed_per_step": routed / K,
+            "transport": (args.transport + (": no frame copies -- the owner of the neighbouring tile composites straight out of the ingest GPU's memory (cudaIpc mapping, the "
+                                            "kernel's 2-D TMA source boxes cross NVLink); routed bytes are counted as whole frames (upper bound)" if args.transport == "peer"
+                                            else ": ncclSend/Recv of the whole frame, posted one step ahead")),
         },
+        "other_transport": {"mode": other, "value": world * K / (other_ms * 1e-3), "ms_per_step": other_ms / K},
         "gpu_launches": int(launches_all), "clocks": ck,
         "limiter": {"match_alone_us": stats_us(match_iso), "k4_own_tile_launch_us": stats_us(k4_iso), "nccl_sendrecv_one_frame_us": sr_us,
                     "nccl_sendrecv_gbs": frames[0].numel() / sr_us / 1e3,
                     "note": ("a step costs max(matching, compositing); compositing = this rank's frame into its own tile plus, every second step, the neighbour's frame "
                              "into the same tile (a second K4 launch); the NVLink transfer of step k+1 is posted before step k is composited and hides under it")},
     }
-    del frames, desc_d
+    peers.close()
+    del frames, desc_d, peers
     mosaic.mappers.clear()
     torch.cuda.empty_cache()
     out["e2e"] = e2e_multi(ctx, barrier, max_over_ranks, fw, fh)
@@ -1079,19 +1107,28 @@ def config4_sample(ctx, barrier, max_over_ranks) -> dict:
         idx = rng.integers(0, nkp, nkp // 4)
         s[idx] = np.clip(s[idx] + rng.integers(-3, 4, (len(idx), 128)), 0, 255)
         sets.append(s[rng.permutation(nkp)])
-    sm = ShardedMatcher(mb.Matcher(norm="l2", device=dev), dev)
+    matcher = mb.Matcher(norm="l2", device=dev)
+    sm = ShardedMatcher(matcher, dev)
     sm.match_all_pairs(sets[:32], RATIO)                  # warm-up
     barrier()
     t0 = time.perf_counter()
-    _, counts = sm.match_all_pairs(sets, RATIO)
+    handle = matcher.upload_sets(sets)                    # replicated on every rank, once
     barrier()
-    s = max_over_ranks(time.perf_counter() - t0)
+    s_up = max_over_ranks(time.perf_counter() - t0)
+    sm.match_all_pairs(sets, RATIO, handle=handle)        # warm the batched launch at this size
+    barrier()
+    t0 = time.perf_counter()
+    _, counts = sm.match_all_pairs(sets, RATIO, handle=handle)
+    barrier()
+    s_match = max_over_ranks(time.perf_counter() - t0)
+    s = s_up + s_match
     npairs = nimg * (nimg - 1) // 2
     return {"workload": f"BASELINE configs[4] sample: all pairs of {nimg} keyframes x SIFT-like {nkp}x128 (L2, tcgen05 GEMM), {npairs} image pairs over {world} GPUs",
-            "seconds": s, "image_pairs_per_s": npairs / s, "descriptor_pairs_per_s": npairs * nkp * nkp / s,
-            "tflops_bf16_gemm_incl_upload_and_epilogue": 2.0 * npairs * nkp * nkp * 128 / s / 1e12,
-            "extrapolated_seconds_for_2000_images": 1999000 / (npairs / s), "survivor_counts_checksum": int(counts.sum()),
-            "note": "wall clock incl. the upload of the 256 descriptor sets (replicated on every rank) and the all_reduce of the count matrix; max over ranks"}
+            "seconds_upload": s_up, "seconds_match": s_match, "image_pairs_per_s": npairs / s_match, "descriptor_pairs_per_s": npairs * nkp * nkp / s_match,
+            "tflops_bf16_gemm_incl_epilogue": 2.0 * npairs * nkp * nkp * 128 / s_match / 1e12,
+            "extrapolated_seconds_for_2000_images": 1999000 / (npairs / s_match) + s_up * 2000 / nimg, "survivor_counts_checksum": int(counts.sum()),
+            "note": ("seconds_match: all pairs with the descriptor sets resident (batched launches of this rank's pair blocks, counts back, all_reduce of the count matrix), wall clock, max over "
+                     "ranks; seconds_upload: host -> device of the 256 sets, replicated on every rank; the extrapolation scales matching by pairs and the upload by images")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1219,6 +1256,8 @@ def main():
     ap.add_argument("--sm-partition", type=int, default=40,
                     help="N=1 only: ALSO time the step with matching in its own group of at least this many SMs (green contexts), reported "
                          "under sm_partition_variant; the headline always uses two ordinary streams; 0 = skip the variant")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how a frame reaches the other ranks whose tiles its footprint overlaps (the other one is timed too, as other_transport)")
     ap.add_argument("--no-feather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)

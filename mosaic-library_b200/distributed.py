@@ -379,7 +379,7 @@ class ShardedMatcher:
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
 
-    def match_all_pairs(self, sets: Sequence[np.ndarray], ratio: float = 0.7, chunk: int = 4096, keep_results: bool = False):
+    def match_all_pairs(self, sets: Sequence[np.ndarray], ratio: float = 0.7, chunk: int = 4096, keep_results: bool = False, handle=None):
         """-> (local, counts): counts [n, n] int64 on the host with counts[query, train] = number of ratio-test survivors,
         summed over ranks; local = {(query, train): (idx, dist, keep)} for the pairs this rank owns when keep_results is
         set (host copies of the match lists), else just the list of owned pairs.  The descriptor sets are uploaded once
@@ -388,7 +388,8 @@ class ShardedMatcher:
         mine = all_pairs_schedule(n, self.world, self.rank, self.block)
         local = {} if keep_results else list(mine)
         counts = torch.zeros((n, n), dtype=torch.int64)
-        handle = self.matcher.upload_sets(sets) if mine and hasattr(self.matcher, "upload_sets") else sets
+        if handle is None:       # `handle` = Matcher.upload_sets(sets) from an earlier call: the sets are already resident
+            handle = self.matcher.upload_sets(sets) if mine and hasattr(self.matcher, "upload_sets") else sets
         for lo in range(0, len(mine), chunk):
             part = mine[lo:lo + chunk]
             if keep_results:
