@@ -34,6 +34,8 @@ constexpr int RING = 64;             // ring of warped rows / bit rows, indexed 
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
 constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
+constexpr int NSRC = 3;             // source boxes in flight per CTA (three: the box of chunk j+3 is requested while chunk j is computed --
+                                    // enough lead for a frame that lives in another GPU's memory and arrives over NVLink)
 #ifndef MK_STRIP_OCC
 #define MK_STRIP_OCC 3
 #endif
@@ -122,7 +124,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     __shared__ unsigned long long s_h[RING];
     __shared__ unsigned long long s_v[CH];
     __shared__ uint8_t s_side[RING][4];
-    __shared__ __align__(8) unsigned long long s_bar_src[2];
+    __shared__ __align__(8) unsigned long long s_bar_src[NSRC];
     __shared__ __align__(8) unsigned long long s_bar_cv[2];
     __shared__ __align__(8) unsigned long long s_bar_v;      // eroded bit rows of the current chunk are ready (warp 1 -> everyone)
     __shared__ __align__(16) int4 s_blk[MAX_CHUNKS];     // per chunk of this CTA: tileX, first finalised row, first phase-1 row, phase-1 rows
@@ -149,7 +151,10 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
         s_blk[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
     }
-    if (tid == 224) { mbar_init(&s_bar_src[0], 1); mbar_init(&s_bar_src[1], 1); mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); mbar_init(&s_bar_v, 1); }
+    if (tid == 224) {
+        for (int i = 0; i < NSRC; ++i) mbar_init(&s_bar_src[i], 1);
+        mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); mbar_init(&s_bar_v, 1);
+    }
     __syncthreads();
 
     // ---- source boxes of ALL chunks of this CTA, four lanes per chunk: the quantised images of the four corners of the haloed
@@ -202,7 +207,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     __syncthreads();
 
     auto issue_src = [&](int j) {                 // one thread
-        const int buf = j & 1;
+        const int buf = j % NSRC;
         const int4 rc = s_rect[j];
         mbar_arrive_expect_tx(&s_bar_src[buf], rc.z ? (uint32_t)boxbytes : 0u);
         if (rc.z) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, rc.y >> p.esz_shift, rc.x, &s_bar_src[buf]);
@@ -220,7 +225,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         if (t >= nr * 4) return;
         const int4 rc = s_rect[j];
         SrcTile T;
-        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + (j & 1) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
+        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + (j % NSRC) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
         const int r = t >> 2, cc = t & 3, y = first + r;
         const int x = (cc < 2) ? tileX - HALO + cc : tileX + TW + (cc - 2);
         const int b = (cc < 2) ? 0 : 2, x1 = (cc < 2) ? BLOCK_W - HALO + cc : cc - 2;
@@ -233,7 +238,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             if (rc.z != 0 && INTERP == 1) {        // staged: the box holds the halo columns' taps too (its corners are columns tileX-2 / tileX+65)
                 if (F.M.affine) quantize_fast_t<true>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
                 else quantize_fast_t<false>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
-                mv = sample_linear_box(src_base + (uint32_t)((j & 1) * boxstride), p.boxW, rc.x, rc.y, X, Y, p.lut) ? 255u : 0u;
+                mv = sample_linear_box(src_base + (uint32_t)((j % NSRC) * boxstride), p.boxW, rc.x, rc.y, X, Y, p.lut) ? 255u : 0u;
             } else {
                 quantize(F.M, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
                 mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
@@ -243,8 +248,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     };
 
     if (tid == 0) {
-        issue_src(0);
-        if (n > 1) issue_src(1);
+        for (int j = 0; j < NSRC && j < n; ++j) issue_src(j);
     } else if (tid == 224) {
         load_canvas(0, 0);
     }
@@ -268,18 +272,19 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
 #endif
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
-        const int buf = j & 1;
+        const int buf = j & 1;             // canvas / mask tile buffer
+        const int sbuf = j % NSRC;         // source box buffer
         const int4 blk = s_blk[j];
         const int tileX = blk.x, fy = blk.y, first = blk.z, nr = blk.w;
         TRW(5, 0);
 
-        if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf], (uint32_t)(j >> 1) & 1u, 100 + j);
+        if (lane == 0) mbar_wait_or_trap(&s_bar_src[sbuf], (uint32_t)(j / NSRC) & 1u, 100 + j);
         __syncwarp();
         TRW(5, 1);
         const int4 rc = s_rect[j];
         const int sy0 = rc.x, bx0 = rc.y;
         const bool staged = rc.z != 0;
-        const uint32_t box = src_base + (uint32_t)(buf * boxstride);
+        const uint32_t box = src_base + (uint32_t)(sbuf * boxstride);
 
         // ---- phase 1, lanes = consecutive columns, two rows per iteration ----------------------------
         {
@@ -305,7 +310,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
                 const double wr = F.M.wr;
                 SrcTile T;
-                T.s = s_dyn + (src_base - smem_u32(s_dyn)) + buf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
+                T.s = s_dyn + (src_base - smem_u32(s_dyn)) + sbuf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
                 auto one = [&](int r) -> uint32_t {
                     double X0, Y0, W0 = 0.0;
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(X0), "=d"(Y0) : "r"(rowb + (uint32_t)r * 32u));
@@ -352,7 +357,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         // ---- between the phases, one job per warp: the source box of chunk j+2 (its buffer is free now), horizontal + vertical
         //      erosion of the new rows, the coordinate bases of chunk j+2, the side halo of chunk j+1, the canvas tile of chunk j+1 ----
         if (warp == 0) {
-            if (lane == 0 && j + 2 < n) issue_src(j + 2);
+            if (lane == 0 && j + NSRC < n) issue_src(j + NSRC);      // into the buffer phase 1 of this chunk has just finished reading
         } else if (warp == 1) {
             if (lane < nr) {
                 const int ri = (first + lane) & (RING - 1);
@@ -375,7 +380,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             if (j + 2 < n) row_bases(j + 2, tid - 64);
         } else if (warp < 7) {
             if (j + 1 < n) {
-                if (lane == 0) mbar_wait_or_trap(&s_bar_src[buf ^ 1], (uint32_t)((j + 1) >> 1) & 1u, 300 + j);
+                if (lane == 0) mbar_wait_or_trap(&s_bar_src[(j + 1) % NSRC], (uint32_t)((j + 1) / NSRC) & 1u, 300 + j);
                 __syncwarp();
                 TRW(5, 7);
                 side_halo(j + 1, tid - 128);
@@ -779,9 +784,9 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
         esz = 4;
     }
     const int boxbytes = boxW * boxR;
-    if (2 * boxbytes > 96 * 1024) return MK_OK;
+    if (NSRC * boxbytes > 120 * 1024) return MK_OK;
     S.boxW = boxW; S.boxR = boxR; S.esz_shift = esz == 4 ? 2 : 0;
-    const int dyn = 2 * ((boxbytes + 127) & ~127) + 128;
+    const int dyn = NSRC * ((boxbytes + 127) & ~127) + 128;
     int occ = 0;
     {
         const int rc = (interp == MK_INTER_LINEAR) ? strip_occupancy<MK_INTER_LINEAR>(dyn, &occ) : strip_occupancy<MK_INTER_CUBIC>(dyn, &occ);

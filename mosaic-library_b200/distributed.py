@@ -107,6 +107,8 @@ class PeerFrames:
         for base in self._bases.values():
             self._lib.mk_ipc_close(base)
         self._bases.clear()
+        if self.world > 1:
+            dist.barrier()          # nobody frees an exported frame while another rank still has it mapped
 
 
 class ShardedMosaic:
