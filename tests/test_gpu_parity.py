@@ -758,3 +758,28 @@ def test_gather_matches_and_pose_chain():
     want = np.array(tuple(itertools.accumulate(np.stack(Hs), np.matmul)))       # core/interface.py:111-113
     got = mb.propagate_homographies(Hs)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-9)                          # fp64, same left-to-right order; FMA contraction in BLAS may differ in the last bits
+
+
+def test_peer_frames_single_process_and_update_pointer():
+    """distributed.PeerFrames at world = 1 (export works on sub-allocated torch tensors, own frames are used in place) and
+    Mapper.update_pointer (the raw-pointer entry the peer transport uses): same canvas as update_device.  The cross-process
+    mapping itself needs two GPUs and is checked by tools/sharded_check.py (profiles/r02_sharded_check_n{2,8}.log)."""
+    import ctypes as C
+    from mosaicking_b200.distributed import PeerFrames, ShardedMosaic
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(21)
+    frames = [torch.from_numpy(_img(rng, 240, 320)).to(dev) for _ in range(3)]
+    h = (C.c_uint8 * 64)(); off = C.c_uint64(0)
+    mb._lib.check(mb._lib.lib().mk_ipc_export(frames[1].data_ptr(), h, C.byref(off)))
+    assert any(h) and off.value < (1 << 34)
+    peers = PeerFrames(frames, dev, rank=0, world=1)
+    assert [p[0] for p in peers.ptr[0]] == [f.data_ptr() for f in frames]
+    Hs = [np.array([[1.0, 0.05 * k, 40.0 + 60 * k], [-0.05 * k, 1.0, 30.0 + 25 * k], [0, 0, 1.0]]) for k in range(3)]
+    a = ShardedMosaic((2, 1), (400, 360), lambda w, hh: mb.Mapper(w, hh, alpha_blend=0.5, interp="linear", device=dev), (240, 320), dev, rank=0, world=1)
+    b = ShardedMosaic((2, 1), (400, 360), lambda w, hh: mb.Mapper(w, hh, alpha_blend=0.5, interp="linear", device=dev), (240, 320), dev, rank=0, world=1)
+    a.plan(np.stack(Hs)); b.plan(np.stack(Hs))
+    for k in range(3):
+        a.step_planned(k, frames[k])
+        b.step_planned(k, None, peers=peers)
+    peers.close()
+    assert np.array_equal(a.gather(0), b.gather(0)) and a.frames_applied == b.frames_applied >= 4
