@@ -30,12 +30,14 @@ namespace mk {
 
 constexpr int CH = 16;               // canvas rows finalised per chunk
 constexpr int BR = CH + 2 * HALO;    // rows of the first phase-1 block of a segment
-constexpr int RING = 64;             // ring of warped rows / bit rows, indexed by (canvas row & 63): two blocks never alias
+constexpr int RING = 64;             // ring of warped rows / bit rows, indexed by a running row counter of the CTA (three chunks in flight)
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
 constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
 constexpr int NSRC = 3;             // source boxes in flight per CTA (three: the box of chunk j+3 is requested while chunk j is computed --
                                     // enough lead for a frame that lives in another GPU's memory and arrives over NVLink)
+constexpr int NCV = 4;              // canvas / mask tile buffers: tile i+1 is loading, i-1 is blended, i-2 is being stored, i-3 has left
+constexpr int NROWB = 4;            // coordinate-base buffers (bases of chunk i+2 are written while chunk i-1 may still be read)
 #ifndef MK_STRIP_OCC
 #define MK_STRIP_OCC 3
 #endif
@@ -43,6 +45,31 @@ constexpr int NSRC = 3;             // source boxes in flight per CTA (three: th
 #define MK_STRIP_ILP 4
 #endif
 constexpr int STRIP_OCC = MK_STRIP_OCC;   // CTAs per SM the register budget is set for (four rows per warp in flight need ~76 registers)
+
+// shared-memory layout of the strip kernel: ONE dynamic block, every array at a constant offset from its 128-byte aligned base, so
+// every shared address is `base register + immediate` (static __shared__ arrays cost an S2R / LEA pair per address on sm_100)
+constexpr int OFF_CANVAS = 0;                                   // [NCV][CH][ROWB]   TMA destination / source
+constexpr int OFF_MASK = OFF_CANVAS + NCV * CH * ROWB;          // [NCV][CH][TW]
+constexpr int OFF_WARP = OFF_MASK + NCV * CH * TW;              // [RING][TW] uint32 warped pixels
+constexpr int OFF_ROW = OFF_WARP + RING * TW * 4;               // [NROWB][3][BR] x 32 bytes: X0, Y0, W0 of the left / centre / right block
+constexpr int OFF_M0 = OFF_ROW + NROWB * 3 * BR * 32;           // [RING] 64-bit validity rows
+constexpr int OFF_H = OFF_M0 + RING * 8;                        // [RING] horizontally eroded rows
+constexpr int OFF_V = OFF_H + RING * 8;                         // [2][CH] fully eroded rows of a chunk
+constexpr int OFF_SIDE = OFF_V + 2 * CH * 8;                    // [RING][4] validity of the 2 + 2 side-halo columns
+constexpr int OFF_BAR = OFF_SIDE + RING * 4;                    // mbarriers, see BAR_*
+constexpr int OFF_ANY = OFF_BAR + 128;                          // [4] "chunk has a valid pixel"
+constexpr int OFF_BLK = OFF_ANY + 16;                           // [MAX_CHUNKS] int4: tileX, first finalised row, first phase-1 row, phase-1 rows
+constexpr int OFF_RECT = OFF_BLK + MAX_CHUNKS * 16;             // [MAX_CHUNKS] int4: source box row, byte, fits flag, ring offset
+constexpr int OFF_SRC = (OFF_RECT + MAX_CHUNKS * 16 + 127) & ~127;   // [NSRC] source boxes
+constexpr int BAR_SRC = OFF_BAR;                 // [NSRC] source box landed (tx bytes)
+constexpr int BAR_CV = BAR_SRC + 8 * NSRC;       // [NCV]  canvas + mask tile landed
+constexpr int BAR_V = BAR_CV + 8 * NCV;          // [2]    eroded bit rows of chunk i ready (warp 1 -> everyone)
+constexpr int BAR_RR = BAR_V + 16;               // [2]    all eight warps have written their phase-1 rows of chunk i
+constexpr int BAR_P2 = BAR_RR + 16;              // [2]    all eight warps have blended chunk i
+// Two barriers, used alternately, wherever several warps arrive: a warp may be one chunk ahead of the slowest one, and an mbarrier
+// cannot tell which phase an arrival is meant for -- on a single barrier the early arrival would complete the previous phase.
+static_assert(BAR_P2 + 16 <= OFF_BAR + 128, "barrier block");
+static_assert((OFF_M0 & 7) == 0 && (OFF_BLK & 15) == 0 && (OFF_ROW & 31) == 0, "alignment");
 
 struct StripParams {
     const short *cubic;
@@ -59,10 +86,14 @@ struct StripParams {
     int4 rows[MAX_STRIPS + 1]; // .x/.y: [ylo, yhi) of every strip (ylo >= yhi: the frame does not reach it), .z: chunks in the strips before it
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
-                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+{
+    tma_load_2d(dst, map, c0, c1, smem_u32(bar));
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src)
 {
@@ -70,15 +101,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-// mbarrier wait that traps instead of hanging the GPU if a transfer never completes (bad tensor map, lost transaction)
-__device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, int what = 0)
+// mbarrier wait (every lane polls; the hardware suspends the warp for up to the hint between polls) that traps instead of hanging
+// the GPU if a transfer never completes (bad tensor map, lost transaction)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity, int what = 0)
 {
-    const uint32_t a = smem_u32(bar);
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
         uint32_t ok;
-        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(10000u) : "memory");
+#ifdef MK_E3
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+#endif
         if (ok) return;
     }
 #ifdef MK_STRIP_DEBUG
@@ -87,12 +123,34 @@ __device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint3
 #endif
     __trap();
 }
+__device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, int what = 0) { mbar_wait_addr(smem_u32(bar), parity, what); }
+__device__ __forceinline__ void mbar_init_addr(uint32_t a, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t a) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t a, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ unsigned long long lds64(uint32_t a)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds128i(uint32_t a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
 
 // INTER_LINEAR from the staged box, no containment test (see sample_linear_c3_smem_fast); `base` = shared address of the box
 __device__ __forceinline__ uint32_t sample_linear_box(uint32_t base, int pitch, int sy0, int bx0, int X, int Y, const uint2 *__restrict__ lut)
@@ -111,31 +169,25 @@ __device__ __forceinline__ uint32_t sample_linear_box(uint32_t base, int pitch, 
                       __funnelshift_r(b1, b2, sh), wt);
 }
 
+// The kernel is a software pipeline over the chunks of a CTA with NO CTA-wide barrier in the loop.  Iteration i of every warp:
+//     phase 1 of chunk i (warp its rows into the ring)  ->  arrive on "rows ready"  ->  its side job  ->  phase 2 of chunk i-1 (blend)
+// so the erosion of chunk i (warp 1, needs everybody's rows) runs while the other warps blend chunk i-1 and warp chunk i+1, and the only
+// waits a warp meets are on things produced an iteration earlier.  Side jobs: warp 1 erodes chunk i and requests source box i+3,
+// warps 2-3 the coordinate bases of chunk i+2, warps 4-6 the side-halo columns of chunk i+1, warp 7 stores tile i-2 and loads tile i+1.
 template <int INTERP>
 __global__ void __launch_bounds__(STHREADS, STRIP_OCC)
 mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_cv,
                     const __grid_constant__ CUtensorMap map_mk, const __grid_constant__ StripParams p)
 {
-    __shared__ __align__(128) uint8_t s_canvas[2][CH][ROWB];
-    __shared__ __align__(128) uint8_t s_mask[2][CH][TW];
-    __shared__ __align__(16) uint32_t s_warp[RING][TW];
-    __shared__ __align__(16) double s_row[3][3][BR][4];     // X0, Y0, W0 of the left / centre / right coordinate block; three blocks in flight
-    __shared__ unsigned long long s_m0[RING];
-    __shared__ unsigned long long s_h[RING];
-    __shared__ unsigned long long s_v[CH];
-    __shared__ uint8_t s_side[RING][4];
-    __shared__ __align__(8) unsigned long long s_bar_src[NSRC];
-    __shared__ __align__(8) unsigned long long s_bar_cv[2];
-    __shared__ __align__(8) unsigned long long s_bar_v;      // eroded bit rows of the current chunk are ready (warp 1 -> everyone)
-    __shared__ __align__(16) int4 s_blk[MAX_CHUNKS];     // per chunk of this CTA: tileX, first finalised row, first phase-1 row, phase-1 rows
-    __shared__ __align__(16) int4 s_rect[MAX_CHUNKS];    // per chunk: source box origin (row sy0, byte bx0), fits-in-the-box flag
     extern __shared__ __align__(128) uint8_t s_dyn[];
+    const uint32_t sb = (smem_u32(s_dyn) + 127u) & ~127u;          // shared address of the layout's base
+    uint8_t *const sp = s_dyn + (sb - smem_u32(s_dyn));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FrameDesc &F = p.f;
     const int boxbytes = p.boxW * p.boxR;                 // bytes one TMA box delivers
     const int boxstride = (boxbytes + 127) & ~127;        // TMA destinations are 128-byte aligned
-    const uint32_t src_base = (smem_u32(s_dyn) + 127u) & ~127u;
+    const uint32_t src_base = sb + OFF_SRC;
 
     // ---- chunks [c0, c0 + n) of the flat list belong to this CTA: strip (binary search in the host's prefix sums) and rows ----
     const int c0 = (int)blockIdx.x * p.chunks_per_cta, n = min(p.nchunks, c0 + p.chunks_per_cta) - c0;
@@ -149,19 +201,25 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         }
         const int q = c - p.rows[lo].z, fy = p.rows[lo].x + q * CH;
         const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
-        s_blk[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
+        reinterpret_cast<int4 *>(sp + OFF_BLK)[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
     }
     if (tid == 224) {
-        for (int i = 0; i < NSRC; ++i) mbar_init(&s_bar_src[i], 1);
-        mbar_init(&s_bar_cv[0], 1); mbar_init(&s_bar_cv[1], 1); mbar_init(&s_bar_v, 1);
+        for (int i = 0; i < NSRC; ++i) mbar_init_addr(sb + BAR_SRC + 8 * i, 1);
+        for (int i = 0; i < NCV; ++i) mbar_init_addr(sb + BAR_CV + 8 * i, 1);
+        mbar_init_addr(sb + BAR_V, 32); mbar_init_addr(sb + BAR_V + 8, 32);
+        mbar_init_addr(sb + BAR_RR, STHREADS); mbar_init_addr(sb + BAR_RR + 8, STHREADS);
+        mbar_init_addr(sb + BAR_P2, STHREADS); mbar_init_addr(sb + BAR_P2 + 8, STHREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
     // ---- source boxes of ALL chunks of this CTA, four lanes per chunk: the quantised images of the four corners of the haloed
-    //      block (columns tileX-2 .. tileX+65) bound every tap of the block as long as W keeps its sign ----
+    //      block (columns tileX-2 .. tileX+65) bound every tap of the block as long as W keeps its sign; and the ring offset of the
+    //      chunk (ring slot of canvas row y = (y + offset) & 63: a running count of the rows this CTA warps, so consecutive chunks of
+    //      a strip share their halo rows and chunks of different strips never alias) ----
     if (warp * 8 < n) {
         const int jj = min(tid >> 2, n - 1), cnr = tid & 3;
-        const int4 blk = s_blk[jj];
+        const int4 blk = lds128i(sb + OFF_BLK + 16 * jj);
         const int tileX = blk.x, first = blk.z, nr = blk.w;
         int X, Y, sg;
         {
@@ -188,17 +246,19 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             const int bx0 = (sx_lo * 3) & ~15;      // the TMA needs a 16-byte aligned global start address
             const bool convex = smin == smax && smin != 0;
             const bool fits = convex && (sx_hi * 3 + 3 - bx0) <= p.boxW && (sy_hi - sy_lo + 1) <= p.boxR;
-            s_rect[jj] = make_int4(sy_lo, bx0, fits ? 1 : 0, 0);
+            int rows_before = 0;
+            for (int k = 0; k < jj; ++k) rows_before += (int)lds32(sb + OFF_BLK + 16 * k + 12);
+            reinterpret_cast<int4 *>(sp + OFF_RECT)[jj] = make_int4(sy_lo, bx0, fits ? 1 : 0, rows_before - first);
         }
     }
     // per-row coordinate bases of block j for the left / centre / right 64-px blocks; 60 threads (idx)
     auto row_bases = [&](int j, int idx) {
-        const int4 blk = s_blk[j];
+        const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
         const int b = idx / BR, r = idx - b * BR;
         if (b < 3 && r < blk.w) {
             double X0, Y0, W0;
             row_base(F.M, blk.x + (b - 1) * BLOCK_W, blk.z + r, X0, Y0, W0);
-            double *d = s_row[j % 3][b][r];
+            double *d = reinterpret_cast<double *>(sp + OFF_ROW + (((j & (NROWB - 1)) * 3 + b) * BR + r) * 32);
             d[0] = X0; d[1] = Y0; d[2] = W0;
         }
     };
@@ -208,31 +268,32 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
 
     auto issue_src = [&](int j) {                 // one thread
         const int buf = j % NSRC;
-        const int4 rc = s_rect[j];
-        mbar_arrive_expect_tx(&s_bar_src[buf], rc.z ? (uint32_t)boxbytes : 0u);
-        if (rc.z) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, rc.y >> p.esz_shift, rc.x, &s_bar_src[buf]);
+        const int4 rc = lds128i(sb + OFF_RECT + 16 * j);
+        mbar_expect_tx_addr(sb + BAR_SRC + 8 * buf, rc.z ? (uint32_t)boxbytes : 0u);
+        if (rc.z) tma_load_2d(src_base + (uint32_t)(buf * boxstride), &map_src, rc.y >> p.esz_shift, rc.x, sb + BAR_SRC + 8 * buf);
     };
-    auto load_canvas = [&](int j, int cb) {      // one thread
-        const int4 blk = s_blk[j];
-        mbar_arrive_expect_tx(&s_bar_cv[cb], (uint32_t)(CH * ROWB + CH * TW));
-        tma_load_2d(smem_u32(&s_canvas[cb][0][0]), &map_cv, blk.x * 3, blk.y, &s_bar_cv[cb]);
-        tma_load_2d(smem_u32(&s_mask[cb][0][0]), &map_mk, blk.x, blk.y, &s_bar_cv[cb]);
+    auto load_canvas = [&](int j) {               // one thread
+        const int cb = j & (NCV - 1);
+        const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
+        mbar_expect_tx_addr(sb + BAR_CV + 8 * cb, (uint32_t)(CH * ROWB + CH * TW));
+        tma_load_2d(sb + OFF_CANVAS + cb * (CH * ROWB), &map_cv, blk.x * 3, blk.y, sb + BAR_CV + 8 * cb);
+        tma_load_2d(sb + OFF_MASK + cb * (CH * TW), &map_mk, blk.x, blk.y, sb + BAR_CV + 8 * cb);
     };
     // the 2 + 2 side-halo columns of block j (they live in the neighbouring coordinate blocks): thread t = 4 * row + column
     auto side_halo = [&](int j, int t) {
-        const int4 blk = s_blk[j];
+        const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
         const int tileX = blk.x, first = blk.z, nr = blk.w;
         if (t >= nr * 4) return;
-        const int4 rc = s_rect[j];
+        const int4 rc = lds128i(sb + OFF_RECT + 16 * j);
         SrcTile T;
-        T.s = s_dyn + (src_base - smem_u32(s_dyn)) + (j % NSRC) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
+        T.s = sp + OFF_SRC + (j % NSRC) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
         const int r = t >> 2, cc = t & 3, y = first + r;
         const int x = (cc < 2) ? tileX - HALO + cc : tileX + TW + (cc - 2);
         const int b = (cc < 2) ? 0 : 2, x1 = (cc < 2) ? BLOCK_W - HALO + cc : cc - 2;
         uint32_t mv = 255;
         if (y >= 0 && y < p.Hc && x >= 0 && x < p.Wc) {
             const double d1 = (double)x1;
-            const double *rb = s_row[j % 3][b][r];
+            const double *rb = reinterpret_cast<const double *>(sp + OFF_ROW + (((j & (NROWB - 1)) * 3 + b) * BR + r) * 32);
             const double sx = dmul(F.M.m[0], d1), sy = dmul(F.M.m[3], d1), sw = dmul(F.M.m[6], d1);
             int X, Y;
             if (rc.z != 0 && INTERP == 1) {        // staged: the box holds the halo columns' taps too (its corners are columns tileX-2 / tileX+65)
@@ -244,13 +305,20 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
             }
         }
-        s_side[y & (RING - 1)][cc] = (uint8_t)mv;
+        sts8(sb + OFF_SIDE + (uint32_t)((y + rc.w) & (RING - 1)) * 4u + (uint32_t)cc, mv);
+#ifdef MK_STRIP_CHECK
+        sts32(src_base + NSRC * boxstride + 512 + (uint32_t)((y + rc.w) & (RING - 1)) * 16u + (uint32_t)cc * 4u, (uint32_t)(1000 * (j + 1) + r));
+#endif
     };
 
     if (tid == 0) {
         for (int j = 0; j < NSRC && j < n; ++j) issue_src(j);
     } else if (tid == 224) {
-        load_canvas(0, 0);
+        load_canvas(0);
+    }
+    if (warp < 3) {                       // side halo of chunk 0 (later chunks get theirs one iteration ahead)
+        mbar_wait_addr(sb + BAR_SRC, 0u, 90);
+        side_halo(0, tid);
     }
 
     const int half = warp & 1, cx = half * 32 + lane;
@@ -259,35 +327,32 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     const bool xvalid_all = (p.tx0 + p.nstrips) * TW <= p.Wc;      // no strip of this launch reaches beyond the canvas
     const double dx1 = (double)cx;
     double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
-    const uint32_t warp_base = smem_u32(&s_warp[0][0]) + (uint32_t)cx * 4u;
-    const uint32_t m0_base = smem_u32(&s_m0[0]) + (uint32_t)half * 4u;
+    const uint32_t warp_base = sb + OFF_WARP + (uint32_t)cx * 4u;
+    const uint32_t m0_base = sb + OFF_M0 + (uint32_t)half * 4u;
 
-#ifdef MK_STRIP_TRACE
-    long long tr[8][9];
-    __shared__ long long s_role[8][8];
-    const long long t_start = clock64();
-#define TRW(w, k) if (tid == 32 * (w) && j < 8) tr[j][k] = clock64() - t_start
-#else
-#define TRW(w, k)
-#endif
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) {
-        const int buf = j & 1;             // canvas / mask tile buffer
-        const int sbuf = j % NSRC;         // source box buffer
-        const int4 blk = s_blk[j];
-        const int tileX = blk.x, fy = blk.y, first = blk.z, nr = blk.w;
-        TRW(5, 0);
+    for (int i = 0; i <= n + 1; ++i) {
+#ifdef MK_E1
+        __syncthreads();
+#endif
+        // =========================== phase 1 of chunk i: lanes = consecutive columns, four rows in flight ===========================
+        if (i < n) {
+            const int4 blk = lds128i(sb + OFF_BLK + 16 * i);
+            const int tileX = blk.x, first = blk.z, nr = blk.w;
+            const int4 rc = lds128i(sb + OFF_RECT + 16 * i);
+            const int sy0 = rc.x, bx0 = rc.y;
+            const bool staged = rc.z != 0;
+            const int rbase = first + rc.w;                 // ring slot of block row r = (rbase + r) & 63
+            const int sbuf = i % NSRC;
+            const uint32_t box = src_base + (uint32_t)(sbuf * boxstride);
+            // the ring slots of chunk i were last used by chunk i-4 (or later): everybody must have blended chunk i-3
+#ifdef MK_E2
+            if (i >= 2) mbar_wait_addr(sb + BAR_P2 + 8 * ((i - 2) & 1), (uint32_t)((i - 2) >> 1) & 1u, 600 + i);
+#else
+            if (i >= 3) mbar_wait_addr(sb + BAR_P2 + 8 * ((i - 3) & 1), (uint32_t)((i - 3) >> 1) & 1u, 600 + i);
+#endif
+            mbar_wait_addr(sb + BAR_SRC + 8 * sbuf, (uint32_t)(i / NSRC) & 1u, 100 + i);
 
-        if (lane == 0) mbar_wait_or_trap(&s_bar_src[sbuf], (uint32_t)(j / NSRC) & 1u, 100 + j);
-        __syncwarp();
-        TRW(5, 1);
-        const int4 rc = s_rect[j];
-        const int sy0 = rc.x, bx0 = rc.y;
-        const bool staged = rc.z != 0;
-        const uint32_t box = src_base + (uint32_t)(sbuf * boxstride);
-
-        // ---- phase 1, lanes = consecutive columns, two rows per iteration ----------------------------
-        {
             const bool xvalid = xvalid_all || tileX + cx < p.Wc;
             if (!xvalid_all) {
                 const double dxs = xvalid ? (double)cx : 0.0;
@@ -296,21 +361,24 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             const int r_lo = max(0, -first), r_hi = min(nr, p.Hc - first);    // block rows inside the canvas
             if (r_lo > 0 || r_hi < nr) {      // rows outside the canvas count as set (cv2.erode's default border)
                 for (int r = warp >> 1; r < nr; r += 4)
-                    if ((r < r_lo || r >= r_hi) && lane == 0) reinterpret_cast<uint32_t *>(&s_m0[(first + r) & (RING - 1)])[half] = ~0u;
+                    if ((r < r_lo || r >= r_hi) && lane == 0) sts32(m0_base + (uint32_t)((rbase + r) & (RING - 1)) * 8u, ~0u);
             }
-            uint32_t rowb = smem_u32(&s_row[j % 3][1][0][0]);
+            uint32_t rowb = sb + OFF_ROW + (uint32_t)(((i & (NROWB - 1)) * 3 + 1) * BR * 32);
             asm volatile("" : "+r"(rowb));           // keep the address in a register (otherwise it is re-derived inside the row loop)
             auto finish_row = [&](int r, uint32_t px) {
                 const unsigned bal = __ballot_sync(0xffffffffu, xvalid ? (px != 0u) : true);   // columns outside the canvas count as set
-                const uint32_t ri = (uint32_t)(first + r) & (RING - 1);
-                if (lane == 0) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(m0_base + ri * 8u), "r"(bal) : "memory");
-                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(warp_base + ri * (TW * 4)), "r"(px) : "memory");
+                const uint32_t ri = (uint32_t)(rbase + r) & (RING - 1);
+                if (lane == 0) sts32(m0_base + ri * 8u, bal);
+#ifdef MK_STRIP_CHECK
+                if (lane == 0) sts32(src_base + NSRC * boxstride + ri * 8u + half * 4u, (uint32_t)(1000 * (i + 1) + r));
+#endif
+                sts32(warp_base + ri * (TW * 4), px);
             };
             auto body = [&](auto fast_tag, auto affine_tag) {
                 constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
                 const double wr = F.M.wr;
                 SrcTile T;
-                T.s = s_dyn + (src_base - smem_u32(s_dyn)) + sbuf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
+                T.s = sp + OFF_SRC + sbuf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
                 auto one = [&](int r) -> uint32_t {
                     double X0, Y0, W0 = 0.0;
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(X0), "=d"(Y0) : "r"(rowb + (uint32_t)r * 32u));
@@ -348,72 +416,56 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             } else {
                 body(std::false_type{}, std::false_type{});
             }
+            // coordinate bases of chunk i+2: published by this warp's "rows ready" arrival -> warp 1's erosion -> BAR_V of chunk i,
+            // which every warp has waited for before it warps chunk i+2
+            if ((warp == 2 || warp == 3) && i + 2 < n) row_bases(i + 2, tid - 64);
+            mbar_arrive_addr(sb + BAR_RR + 8 * (i & 1));
         }
-        if (j == 0) side_halo(0, tid);           // later blocks get theirs one iteration ahead, between the phases
-        TRW(5, 2);
-        __syncthreads();                                                             // D
-        TRW(5, 3);
 
-        // ---- between the phases, one job per warp: the source box of chunk j+2 (its buffer is free now), horizontal + vertical
-        //      erosion of the new rows, the coordinate bases of chunk j+2, the side halo of chunk j+1, the canvas tile of chunk j+1 ----
-        if (warp == 0) {
-            if (lane == 0 && j + NSRC < n) issue_src(j + NSRC);      // into the buffer phase 1 of this chunk has just finished reading
-        } else if (warp == 1) {
-            if (lane < nr) {
-                const int ri = (first + lane) & (RING - 1);
-                const unsigned long long m = s_m0[ri];
-                const unsigned long long l2 = s_side[ri][0] ? 1ull : 0ull, l1 = s_side[ri][1] ? 1ull : 0ull;
-                const unsigned long long r1 = s_side[ri][2] ? 1ull : 0ull, r2 = s_side[ri][3] ? 1ull : 0ull;
-                const unsigned long long sl1 = (m << 1) | l1, sl2 = (m << 2) | (l1 << 1) | l2;
-                const unsigned long long sr1 = (m >> 1) | (r1 << 63), sr2 = (m >> 2) | (r1 << 62) | (r2 << 63);
-                s_h[ri] = m & sl1 & sl2 & sr1 & sr2;
+        // =========================== side jobs (warp 1 does its job after blending) ===========================
+        if (warp >= 4 && warp < 7) {
+            if (i + 1 < n) {               // side halo of chunk i+1: its bases are visible once BAR_V of chunk i-1 has completed
+                if (i >= 1) mbar_wait_addr(sb + BAR_V + 8 * ((i - 1) & 1), (uint32_t)((i - 1) >> 1) & 1u, 700 + i);
+                mbar_wait_addr(sb + BAR_SRC + 8 * ((i + 1) % NSRC), (uint32_t)((i + 1) / NSRC) & 1u, 300 + i);
+                side_halo(i + 1, tid - 128);
+            }
+        } else if (warp == 7) {
+            if (lane == 0) {
+                if (i >= 2) {              // tile i-2 has been blended by everybody: store it
+                    const int j = i - 2;
+                    mbar_wait_addr(sb + BAR_P2 + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 800 + i);
+                    if (lds32(sb + OFF_ANY + 4 * (j & 3))) {
+                        const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
+                        tma_store_2d(&map_cv, blk.x * 3, blk.y, sb + OFF_CANVAS + (j & (NCV - 1)) * (CH * ROWB));
+                        tma_store_2d(&map_mk, blk.x, blk.y, sb + OFF_MASK + (j & (NCV - 1)) * (CH * TW));
+                    }
+                    bulk_commit();
+                }
+                if (i + 1 < n) {
+                    if (i + 1 >= NCV) bulk_wait_read1();     // the store of tile i-3 (issued an iteration ago) has read this buffer
+                    load_canvas(i + 1);
+                }
             }
             __syncwarp();
-            if (lane < CH) {
-                const int y = fy + lane;
-                s_v[lane] = s_h[(y - 2) & (RING - 1)] & s_h[(y - 1) & (RING - 1)] & s_h[y & (RING - 1)] & s_h[(y + 1) & (RING - 1)] &
-                            s_h[(y + 2) & (RING - 1)];
-            }
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&s_bar_v)) : "memory");
-        } else if (warp == 2 || warp == 3) {
-            if (j + 2 < n) row_bases(j + 2, tid - 64);
-        } else if (warp < 7) {
-            if (j + 1 < n) {
-                if (lane == 0) mbar_wait_or_trap(&s_bar_src[(j + 1) % NSRC], (uint32_t)((j + 1) / NSRC) & 1u, 300 + j);
-                __syncwarp();
-                TRW(5, 7);
-                side_halo(j + 1, tid - 128);
-                TRW(5, 8);
-            }
-        } else if (tid == 224) {
-            if (j + 1 < n) {
-                bulk_wait_read0();                    // the store of chunk j-1 has read its buffer
-                load_canvas(j + 1, buf ^ 1);
-            }
         }
-#ifdef MK_STRIP_TRACE
-        if (lane == 0 && j < 8) s_role[j][warp] = clock64() - t_start;
-#endif
-        // E: phase 2 only needs warp 1's bit rows; the prefetch jobs of the other warps are for later chunks and are ordered by barrier F
-        if (lane == 0) mbar_wait_or_trap(&s_bar_v, (uint32_t)j & 1u, 500 + j);
-        __syncwarp();
-        TRW(5, 4);
 
-        // ---- phase 2: thread = 4 consecutive pixels = 3 packed BGR words ---------------------------
-        unsigned mb;
-        {
+        // =========================== phase 2 of chunk i-1: thread = 4 consecutive pixels = 3 packed BGR words ===========================
+        if (i >= 1 && i <= n) {
+            const int j = i - 1, cbuf = j & (NCV - 1);
+            const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
+            const int fy = blk.y;
+            const int roff = (int)lds32(sb + OFF_RECT + 16 * j + 12);
+            mbar_wait_addr(sb + BAR_V + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 500 + i);
             const int r = tid >> 4, g = tid & 15;
-            const unsigned long long v = s_v[r];
+            const unsigned long long v = lds64(sb + OFF_V + (uint32_t)((j & 1) * CH + r) * 8u);
             const uint32_t vw = (g & 8) ? (uint32_t)(v >> 32) : (uint32_t)v;
-            mb = (vw >> (4 * (g & 7))) & 15u;
-            if (lane == 0) mbar_wait_or_trap(&s_bar_cv[buf], (uint32_t)(j >> 1) & 1u, 200 + j);
-            __syncwarp();
+            const unsigned mb = (vw >> (4 * (g & 7))) & 15u;
+            mbar_wait_addr(sb + BAR_CV + 8 * cbuf, (uint32_t)(j / NCV) & 1u, 200 + i);
             if (mb) {
-                uint32_t *cw = reinterpret_cast<uint32_t *>(&s_canvas[buf][r][12 * g]);
-                uint32_t *ms = reinterpret_cast<uint32_t *>(&s_mask[buf][r][4 * g]);
+                uint32_t *cw = reinterpret_cast<uint32_t *>(sp + OFF_CANVAS + cbuf * (CH * ROWB) + r * ROWB + 12 * g);
+                uint32_t *ms = reinterpret_cast<uint32_t *>(sp + OFF_MASK + cbuf * (CH * TW) + r * TW + 4 * g);
                 const uint32_t c0w = cw[0], c1w = cw[1], c2w = cw[2], mk4 = *ms;
-                const uint4 wv = *reinterpret_cast<const uint4 *>(&s_warp[(fy + r) & (RING - 1)][4 * g]);
+                const uint4 wv = *reinterpret_cast<const uint4 *>(sp + OFF_WARP + ((fy + r + roff) & (RING - 1)) * (TW * 4) + 16 * g);
                 const uint32_t W0 = __byte_perm(wv.x, wv.y, 0x4210), W1 = __byte_perm(wv.y, wv.z, 0x5421), W2 = __byte_perm(wv.z, wv.w, 0x6542);
                 // per-pixel byte masks: valid (eroded mask bit), old (canvas mask byte > 1, mosaic.py:123)
                 const uint32_t Mv = ((mb * 0x00204081u) & 0x01010101u) * 0xFFu;
@@ -454,26 +506,53 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 *ms = mk4 | Mv;                                                     // mosaic.py:138
                 fence_proxy_async();
             }
+            mbar_arrive_addr(sb + BAR_P2 + 8 * (j & 1));
         }
-        TRW(5, 5);
-        const int any = __syncthreads_or((int)mb);                                   // F
-        TRW(5, 6);
-        if (tid == 224 && any) {
-            tma_store_2d(&map_cv, tileX * 3, fy, smem_u32(&s_canvas[buf][0][0]));
-            tma_store_2d(&map_mk, tileX, fy, smem_u32(&s_mask[buf][0][0]));
-            bulk_commit();
+
+        // =========================== warp 1: erosion of chunk i (everybody's rows are in), source box of chunk i+3 ===========================
+        if (warp == 1 && i < n) {
+            mbar_wait_addr(sb + BAR_RR + 8 * (i & 1), (uint32_t)(i >> 1) & 1u, 400 + i);
+            if (lane == 0 && i + NSRC < n) issue_src(i + NSRC);      // into the buffer phase 1 of this chunk has finished reading
+            const int4 blk = lds128i(sb + OFF_BLK + 16 * i);
+            const int fy = blk.y, first = blk.z, nr = blk.w;
+            const int roff = (int)lds32(sb + OFF_RECT + 16 * i + 12);
+            if (lane < nr) {
+                const uint32_t ri = (uint32_t)(first + lane + roff) & (RING - 1);
+                const unsigned long long m = lds64(sb + OFF_M0 + ri * 8u);
+#ifdef MK_STRIP_CHECK
+                {
+                    const uint32_t want = (uint32_t)(1000 * (i + 1) + lane);
+                    const uint32_t t0 = lds32(src_base + NSRC * boxstride + ri * 8u), t1 = lds32(src_base + NSRC * boxstride + ri * 8u + 4u);
+                    const bool oob = first + lane < 0 || first + lane >= p.Hc;
+                    if (!oob && (t0 != want || t1 != want)) printf("STALE m0: blk %d chunk %d/%d row %d tags %u %u want %u\n", blockIdx.x, i, n, lane, t0, t1, want);
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const uint32_t ts = lds32(src_base + NSRC * boxstride + 512 + ri * 16u + cc * 4u);
+                        if (ts != want) printf("STALE side: blk %d chunk %d/%d row %d cc %d tag %u want %u\n", blockIdx.x, i, n, lane, cc, ts, want);
+                    }
+                }
+#endif
+                const uint32_t sd = lds32(sb + OFF_SIDE + ri * 4u);
+                const unsigned long long l2 = (sd & 0xFFu) ? 1ull : 0ull, l1 = (sd & 0xFF00u) ? 1ull : 0ull;
+                const unsigned long long r1 = (sd & 0xFF0000u) ? 1ull : 0ull, r2 = (sd & 0xFF000000u) ? 1ull : 0ull;
+                const unsigned long long sl1 = (m << 1) | l1, sl2 = (m << 2) | (l1 << 1) | l2;
+                const unsigned long long sr1 = (m >> 1) | (r1 << 63), sr2 = (m >> 2) | (r1 << 62) | (r2 << 63);
+                sts64(sb + OFF_H + ri * 8u, m & sl1 & sl2 & sr1 & sr2);
+            }
+            __syncwarp();
+            unsigned long long ev = 0;
+            if (lane < CH) {
+                const int y = fy + lane + roff;
+                ev = lds64(sb + OFF_H + (uint32_t)((y - 2) & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y - 1) & (RING - 1)) * 8u) &
+                     lds64(sb + OFF_H + (uint32_t)(y & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y + 1) & (RING - 1)) * 8u) &
+                     lds64(sb + OFF_H + (uint32_t)((y + 2) & (RING - 1)) * 8u);
+                sts64(sb + OFF_V + (uint32_t)((i & 1) * CH + lane) * 8u, ev);
+            }
+            const int any = __any_sync(0xffffffffu, ev != 0ull);
+            if (lane == 0) sts32(sb + OFF_ANY + 4 * (i & 3), (uint32_t)any);
+            mbar_arrive_addr(sb + BAR_V + 8 * (i & 1));
         }
     }
     if (tid == 224) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
-#ifdef MK_STRIP_TRACE
-    if (tid == 160 && (blockIdx.x == 0 || blockIdx.x == 200 || blockIdx.x == gridDim.x - 1)) {
-        unsigned smid; asm("mov.u32 %0, %smid;" : "=r"(smid));
-        for (int j = 0; j < n && j < 8; ++j)
-            printf("   blk %d roles j %d (end of between job, per warp): %lld %lld %lld %lld %lld %lld %lld %lld\n", blockIdx.x, j, s_role[j][0], s_role[j][1], s_role[j][2], s_role[j][3], s_role[j][4], s_role[j][5], s_role[j][6], s_role[j][7]),
-            printf("blk %d sm %u j %d: top %lld srcwait %lld | p1 end %lld D %lld | src(j+1) %lld halo end %lld | E %lld | p2 end %lld F %lld\n", blockIdx.x, smid, j, tr[j][0], tr[j][1], tr[j][2], tr[j][3],
-                   tr[j][7], tr[j][8], tr[j][4], tr[j][5], tr[j][6]);
-    }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -784,9 +863,13 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
         esz = 4;
     }
     const int boxbytes = boxW * boxR;
-    if (NSRC * boxbytes > 120 * 1024) return MK_OK;
+    if (OFF_SRC + NSRC * boxbytes > 160 * 1024) return MK_OK;
     S.boxW = boxW; S.boxR = boxR; S.esz_shift = esz == 4 ? 2 : 0;
-    const int dyn = NSRC * ((boxbytes + 127) & ~127) + 128;
+    #ifdef MK_STRIP_CHECK
+    const int dyn = OFF_SRC + NSRC * ((boxbytes + 127) & ~127) + 128 + 2048;
+#else
+    const int dyn = OFF_SRC + NSRC * ((boxbytes + 127) & ~127) + 128;
+#endif
     int occ = 0;
     {
         const int rc = (interp == MK_INTER_LINEAR) ? strip_occupancy<MK_INTER_LINEAR>(dyn, &occ) : strip_occupancy<MK_INTER_CUBIC>(dyn, &occ);
