@@ -912,7 +912,7 @@ def multi_gpu(ctx) -> dict:
         "config": {
             "workload": (f"BASELINE configs[1] step per GPU (1920x1080 frame, 5000x32B Hamming kNN k=2 + ratio 0.7, warp+blend alpha=0.5 INTER_LINEAR) composited into "
                          f"BASELINE configs[3]'s canvas: 65536x65536 = 4x4 tiles of 16384^2 owned round-robin by {world} GPUs; one lane of the frame sequence per rank along a "
-                         "tile seam, every second frame straddles the seam and is routed to the neighbouring owner by warped footprint (ncclSend/Recv), poses all-gathered once"),
+                         "tile seam, every second frame straddles the seam and is routed to the neighbouring owner by warped footprint, poses all-gathered once"),
             "l2": f"flushed between steps ({args.flush_mb} MiB memset outside the timed events)",
             "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching on its own (ordinary) stream, same policy as N=1",
             "blend": "alpha", "interp": "linear", "canvas": [BIG_GRID[0] * CANVAS, BIG_GRID[1] * CANVAS], "tile": [CANVAS, CANVAS], "frame": [fw, fh],
@@ -1256,7 +1256,7 @@ def main():
     ap.add_argument("--sm-partition", type=int, default=40,
                     help="N=1 only: ALSO time the step with matching in its own group of at least this many SMs (green contexts), reported "
                          "under sm_partition_variant; the headline always uses two ordinary streams; 0 = skip the variant")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"],
                     help="N > 1: how a frame reaches the other ranks whose tiles its footprint overlaps (the other one is timed too, as other_transport)")
     ap.add_argument("--no-feather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

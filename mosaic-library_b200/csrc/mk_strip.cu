@@ -83,7 +83,7 @@ struct StripParams {
     uint32_t magic;
     int blend_mode;         // 0 general alpha, 1 alpha == 0.5, 2 alpha == 1 (keep canvas), 3 alpha == 0 (take frame)
     FrameDesc f;
-    int4 rows[MAX_STRIPS + 1]; // .x/.y: [ylo, yhi) of every strip (ylo >= yhi: the frame does not reach it), .z: chunks in the strips before it
+    int2 rows[MAX_STRIPS + 1]; // .x: first row of every strip, .y: chunks in the strips before it (kernel parameters are copied per launch: keep them small)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
@@ -112,9 +112,6 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity, int 
         uint32_t ok;
         asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\nselp.u32 %0, 1, 0, P1;\n}\n"
                      : "=r"(ok) : "r"(a), "r"(parity), "r"(10000u) : "memory");
-#ifdef MK_E3
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-#endif
         if (ok) return;
     }
 #ifdef MK_STRIP_DEBUG
@@ -194,12 +191,12 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     if (n <= 0) return;
     if (tid < n) {
         const int c = c0 + tid;
-        int lo = 0, hi = p.nstrips;      // rows[lo].z <= c < rows[hi].z
+        int lo = 0, hi = p.nstrips;      // rows[lo].y <= c < rows[hi].y
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (p.rows[mid].z <= c) lo = mid; else hi = mid;
+            if (p.rows[mid].y <= c) lo = mid; else hi = mid;
         }
-        const int q = c - p.rows[lo].z, fy = p.rows[lo].x + q * CH;
+        const int q = c - p.rows[lo].y, fy = p.rows[lo].x + q * CH;
         const bool seg_start = (tid == 0) || (q == 0);     // no rows of the previous chunk in the rings: warp the 2-row halo above too
         reinterpret_cast<int4 *>(sp + OFF_BLK)[tid] = make_int4((p.tx0 + lo) * TW, fy, seg_start ? fy - HALO : fy + HALO, seg_start ? BR : CH);
     }
@@ -217,6 +214,12 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     //      block (columns tileX-2 .. tileX+65) bound every tap of the block as long as W keeps its sign; and the ring offset of the
     //      chunk (ring slot of canvas row y = (y + offset) & 63: a running count of the rows this CTA warps, so consecutive chunks of
     //      a strip share their halo rows and chunks of different strips never alias) ----
+    if (tid == 224) {              // canvas + mask tile of chunk 0
+        const int4 blk = lds128i(sb + OFF_BLK);
+        mbar_expect_tx_addr(sb + BAR_CV, (uint32_t)(CH * ROWB + CH * TW));
+        tma_load_2d(sb + OFF_CANVAS, &map_cv, blk.x * 3, blk.y, sb + BAR_CV);
+        tma_load_2d(sb + OFF_MASK, &map_mk, blk.x, blk.y, sb + BAR_CV);
+    }
     if (warp * 8 < n) {
         const int jj = min(tid >> 2, n - 1), cnr = tid & 3;
         const int4 blk = lds128i(sb + OFF_BLK + 16 * jj);
@@ -249,6 +252,10 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             int rows_before = 0;
             for (int k = 0; k < jj; ++k) rows_before += (int)lds32(sb + OFF_BLK + 16 * k + 12);
             reinterpret_cast<int4 *>(sp + OFF_RECT)[jj] = make_int4(sy_lo, bx0, fits ? 1 : 0, rows_before - first);
+            if (jj < NSRC) {               // the first boxes leave right away: nothing can be computed before box 0 is here
+                mbar_expect_tx_addr(sb + BAR_SRC + 8 * jj, fits ? (uint32_t)boxbytes : 0u);
+                if (fits) tma_load_2d(src_base + (uint32_t)(jj * boxstride), &map_src, bx0 >> p.esz_shift, sy_lo, sb + BAR_SRC + 8 * jj);
+            }
         }
     }
     // per-row coordinate bases of block j for the left / centre / right 64-px blocks; 60 threads (idx)
@@ -306,16 +313,8 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             }
         }
         sts8(sb + OFF_SIDE + (uint32_t)((y + rc.w) & (RING - 1)) * 4u + (uint32_t)cc, mv);
-#ifdef MK_STRIP_CHECK
-        sts32(src_base + NSRC * boxstride + 512 + (uint32_t)((y + rc.w) & (RING - 1)) * 16u + (uint32_t)cc * 4u, (uint32_t)(1000 * (j + 1) + r));
-#endif
     };
 
-    if (tid == 0) {
-        for (int j = 0; j < NSRC && j < n; ++j) issue_src(j);
-    } else if (tid == 224) {
-        load_canvas(0);
-    }
     if (warp < 3) {                       // side halo of chunk 0 (later chunks get theirs one iteration ahead)
         mbar_wait_addr(sb + BAR_SRC, 0u, 90);
         side_halo(0, tid);
@@ -332,9 +331,6 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
 
 #pragma unroll 1
     for (int i = 0; i <= n + 1; ++i) {
-#ifdef MK_E1
-        __syncthreads();
-#endif
         // =========================== phase 1 of chunk i: lanes = consecutive columns, four rows in flight ===========================
         if (i < n) {
             const int4 blk = lds128i(sb + OFF_BLK + 16 * i);
@@ -346,11 +342,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             const int sbuf = i % NSRC;
             const uint32_t box = src_base + (uint32_t)(sbuf * boxstride);
             // the ring slots of chunk i were last used by chunk i-4 (or later): everybody must have blended chunk i-3
-#ifdef MK_E2
-            if (i >= 2) mbar_wait_addr(sb + BAR_P2 + 8 * ((i - 2) & 1), (uint32_t)((i - 2) >> 1) & 1u, 600 + i);
-#else
             if (i >= 3) mbar_wait_addr(sb + BAR_P2 + 8 * ((i - 3) & 1), (uint32_t)((i - 3) >> 1) & 1u, 600 + i);
-#endif
             mbar_wait_addr(sb + BAR_SRC + 8 * sbuf, (uint32_t)(i / NSRC) & 1u, 100 + i);
 
             const bool xvalid = xvalid_all || tileX + cx < p.Wc;
@@ -369,9 +361,6 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 const unsigned bal = __ballot_sync(0xffffffffu, xvalid ? (px != 0u) : true);   // columns outside the canvas count as set
                 const uint32_t ri = (uint32_t)(rbase + r) & (RING - 1);
                 if (lane == 0) sts32(m0_base + ri * 8u, bal);
-#ifdef MK_STRIP_CHECK
-                if (lane == 0) sts32(src_base + NSRC * boxstride + ri * 8u + half * 4u, (uint32_t)(1000 * (i + 1) + r));
-#endif
                 sts32(warp_base + ri * (TW * 4), px);
             };
             auto body = [&](auto fast_tag, auto affine_tag) {
@@ -519,18 +508,6 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             if (lane < nr) {
                 const uint32_t ri = (uint32_t)(first + lane + roff) & (RING - 1);
                 const unsigned long long m = lds64(sb + OFF_M0 + ri * 8u);
-#ifdef MK_STRIP_CHECK
-                {
-                    const uint32_t want = (uint32_t)(1000 * (i + 1) + lane);
-                    const uint32_t t0 = lds32(src_base + NSRC * boxstride + ri * 8u), t1 = lds32(src_base + NSRC * boxstride + ri * 8u + 4u);
-                    const bool oob = first + lane < 0 || first + lane >= p.Hc;
-                    if (!oob && (t0 != want || t1 != want)) printf("STALE m0: blk %d chunk %d/%d row %d tags %u %u want %u\n", blockIdx.x, i, n, lane, t0, t1, want);
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const uint32_t ts = lds32(src_base + NSRC * boxstride + 512 + ri * 16u + cc * 4u);
-                        if (ts != want) printf("STALE side: blk %d chunk %d/%d row %d cc %d tag %u want %u\n", blockIdx.x, i, n, lane, cc, ts, want);
-                    }
-                }
-#endif
                 const uint32_t sd = lds32(sb + OFF_SIDE + ri * 4u);
                 const unsigned long long l2 = (sd & 0xFFu) ? 1ull : 0ull, l1 = (sd & 0xFF00u) ? 1ull : 0ull;
                 const unsigned long long r1 = (sd & 0xFF0000u) ? 1ull : 0ull, r2 = (sd & 0xFF000000u) ? 1ull : 0ull;
@@ -814,6 +791,7 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
     S.alpha = P.alpha; S.beta = P.beta; S.magic = P.magic; S.f = F;
     S.blend_mode = (P.alpha == 0.5f && P.beta == 0.5f) ? 1 : (P.alpha == 1.0f && P.beta == 0.0f) ? 2 : (P.alpha == 0.0f && P.beta == 1.0f) ? 3 : 0;
     long nchunks = 0;
+    int yhis[MAX_STRIPS];
     for (int s = 0; s < ns; ++s) {
         const double xa = (double)(tx0 + s) * TW - HALO - 3.0, xb = (double)(tx0 + s) * TW + TW + HALO + 2.0;
         double ymin, ymax;
@@ -822,10 +800,10 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
             ylo = (int)fmax((double)rect[1], fmin((double)rect[3], floor(ymin) - 3.0));
             yhi = (int)fmax((double)rect[1], fmin((double)rect[3], ceil(ymax) + 4.0));
         }
-        S.rows[s] = make_int4(ylo, yhi, (int)nchunks, 0);
+        S.rows[s] = make_int2(ylo, (int)nchunks); yhis[s] = yhi;
         if (yhi > ylo) nchunks += (yhi - ylo + CH - 1) / CH;
     }
-    S.rows[ns] = make_int4(0, 0, (int)nchunks, 0);
+    S.rows[ns] = make_int2(0, (int)nchunks);
     if (nchunks <= 0) { *done = true; return MK_OK; }
     // source box: extents of the haloed 20-row block at probes over the visited region (plain double math; a block whose
     // exact rectangle does not fit samples from global memory instead, so this only has to be a good estimate)
@@ -835,7 +813,7 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
         double maxc = 0, maxr = 0;
         for (int a = 0; a < 3; ++a) {
             const int s = (a == 0) ? 0 : (a == 1) ? ns / 2 : ns - 1;
-            const int ylo = S.rows[s].x, yhi = S.rows[s].y;
+            const int ylo = S.rows[s].x, yhi = yhis[s];
             if (yhi <= ylo) continue;
             for (int b = 0; b < 3; ++b) {
                 const double y0 = (b == 0) ? ylo - HALO : (b == 1) ? (ylo + yhi) / 2 : std::max(ylo - HALO, yhi + HALO - BR);
@@ -865,11 +843,7 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
     const int boxbytes = boxW * boxR;
     if (OFF_SRC + NSRC * boxbytes > 160 * 1024) return MK_OK;
     S.boxW = boxW; S.boxR = boxR; S.esz_shift = esz == 4 ? 2 : 0;
-    #ifdef MK_STRIP_CHECK
-    const int dyn = OFF_SRC + NSRC * ((boxbytes + 127) & ~127) + 128 + 2048;
-#else
     const int dyn = OFF_SRC + NSRC * ((boxbytes + 127) & ~127) + 128;
-#endif
     int occ = 0;
     {
         const int rc = (interp == MK_INTER_LINEAR) ? strip_occupancy<MK_INTER_LINEAR>(dyn, &occ) : strip_occupancy<MK_INTER_CUBIC>(dyn, &occ);
