@@ -229,6 +229,26 @@ int mk_ipc_export(const void *dev_ptr, uint8_t *handle_out, uint64_t *offset_out
 int mk_ipc_open(const uint8_t *handle, void **base_out);
 int mk_ipc_close(void *base);
 
+/* ---------------------------------------------------------------------------------------
+ * Per-frame pre-processing on the device (row N4): a frame that is already in device memory is
+ * converted / undistorted there instead of on the host.
+ *
+ * mk_cvt_color_u8 replaces the cv2.cvtColor calls of preprocessing.make_gray / make_bgr
+ *   (src/mosaicking/preprocessing.py:314-346; used at mosaic.py:66,112,312, registration.py:100-149):
+ *   code MK_CVT_BGR2GRAY / MK_CVT_BGRA2GRAY (3 or 4 -> 1 channel, gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15),
+ *        MK_CVT_GRAY2BGR / MK_CVT_BGRA2BGR (1 or 4 -> 3 channels).  Bit-identical to cv2 for uint8.
+ *   16-byte aligned src/dst with pitches % 16 == 0 take the vector path; anything else works too.
+ *
+ * mk_remap_u8 replaces cv2.remap(image, xmap, ymap, interp) with float32 maps and BORDER_CONSTANT 0
+ *   (preprocessing.DistortionMapper.apply, preprocessing.py:76-98; the maps come from
+ *   cv2.initUndistortRectifyMap once per camera).  map_x / map_y: float [dst_h][dst_w], pitch in bytes.
+ *   uint8, channels = 1 or 3; src and maps 4-byte aligned, pitches multiples of 4; src dims <= 32767.
+ * ------------------------------------------------------------------------------------- */
+typedef enum mk_cvt { MK_CVT_BGR2GRAY = 0, MK_CVT_BGRA2GRAY = 1, MK_CVT_GRAY2BGR = 2, MK_CVT_BGRA2BGR = 3 } mk_cvt;
+int mk_cvt_color_u8(const uint8_t *src, int h, int w, size_t src_pitch, int code, uint8_t *dst, size_t dst_pitch, void *stream);
+int mk_remap_u8(const uint8_t *src, int src_h, int src_w, int channels, size_t src_pitch, const float *map_x, const float *map_y,
+                size_t map_pitch, uint8_t *dst, int dst_h, int dst_w, size_t dst_pitch, int interp, void *stream);
+
 /* Algorithmic bytes of one mk_mapper_update: src + 2*3*A + 2*A (+ 8*A feather),
  * A = area of the canvas rectangle visited.  Pure host arithmetic. */
 int mk_mapper_footprint(int canvas_h, int canvas_w, int src_h, int src_w, const double *H_host,

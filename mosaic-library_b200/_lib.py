@@ -27,7 +27,7 @@ EXPORTS = (
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
     "mk_event_create", "mk_event_destroy", "mk_stream_follow", "mk_sm_partition_create", "mk_sm_partition_destroy",
     "mk_gather_matches", "mk_ransac_workspace_bytes", "mk_ransac_transform", "mk_chain_homographies",
-    "mk_ipc_export", "mk_ipc_open", "mk_ipc_close",
+    "mk_ipc_export", "mk_ipc_open", "mk_ipc_close", "mk_cvt_color_u8", "mk_remap_u8",
 )
 MODEL_AFFINE, MODEL_PERSPECTIVE = 0, 1
 
@@ -93,6 +93,10 @@ def lib() -> C.CDLL:
     L.mk_sm_partition_create.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.mk_sm_partition_destroy.restype = None
     L.mk_sm_partition_destroy.argtypes = [vp]
+    L.mk_cvt_color_u8.restype = i32
+    L.mk_cvt_color_u8.argtypes = [vp, i32, i32, sz, i32, vp, sz, vp]
+    L.mk_remap_u8.restype = i32
+    L.mk_remap_u8.argtypes = [vp, i32, i32, i32, sz, vp, vp, sz, vp, i32, i32, sz, i32, vp]
     L.mk_mapper_footprint.restype = i32
     L.mk_mapper_footprint.argtypes = [i32, i32, i32, i32, vp, i32, vp]
     L.mk_gather_matches.restype = i32

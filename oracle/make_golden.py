@@ -18,6 +18,9 @@ What produces each expected value:
              first Mapper.update calls of SequentialMosaic.generate (mosaic.py:665-691) and the canvas they produce.
   matchfeatures  SequentialMosaic.match_features / .registration (mosaic.py:402-470) of the same run: descriptor dicts as handed to
              CompositeMatcher.knn_match, the good matches kept by the ratio comprehension (mosaic.py:430), RANSAC inputs / (H, inliers).
+  preproc    mosaicking.preprocessing.make_gray / make_bgr (preprocessing.py:314-346) and DistortionMapper.apply, forward and
+             inverse (preprocessing.py:68-98: cv2.remap INTER_CUBIC with the maps of cv2.initUndistortRectifyMap), on odd-sized
+             random images; the float32 maps are stored next to the outputs.
   routing    mosaicking.mosaic.get_corners / get_mosaic_dimensions (mosaic.py:708-768),
              registration.bbox_overlap on int-truncated corners (mosaic.py:614), and
              splitter.calculate_tiles / assign_image_to_tiles (splitter.py:11-58).
@@ -355,10 +358,41 @@ def gen_matchfeatures(reg, mos):
           [int(out[f"rinl{k}"].sum()) for k in range(len(rec["ransac"]))])
 
 
+def gen_preproc():
+    import mosaicking.preprocessing as pre      # the real reference module (imported after ref_shim.import_reference())
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, (h, w) in {"a": (131, 203), "b": (96, 160)}.items():      # odd width: scalar row tails; 160: the 16-pixel vector path
+        bgr = smooth_img(rng, h, w); bgra = np.dstack([bgr, rng.integers(0, 256, (h, w), dtype=np.uint8)]); gray = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out[f"{tag}_bgr"] = bgr; out[f"{tag}_bgra"] = bgra; out[f"{tag}_gray"] = gray
+        out[f"{tag}_gray_of_bgr"] = pre.make_gray(bgr); out[f"{tag}_gray_of_bgra"] = pre.make_gray(bgra)
+        out[f"{tag}_bgr_of_gray"] = pre.make_bgr(gray); out[f"{tag}_bgr_of_bgra"] = pre.make_bgr(bgra)
+        assert pre.make_gray(gray) is gray and pre.make_bgr(bgr) is bgr
+    h, w = 192, 256
+    K = np.array([[210.0, 0, 126.3], [0, 205.0, 97.7], [0, 0, 1]]); D = np.array([-0.28, 0.09, 0.0012, -0.0007, -0.01])
+    img = smooth_img(rng, h, w); g1 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    out["K"] = K; out["D"] = D; out["und_img"] = img; out["und_gray"] = g1
+    for inv in (False, True):
+        dm = pre.DistortionMapper(K, D, inverse=inv)
+        t = "inv" if inv else "fwd"
+        out[f"und_{t}_bgr"] = dm.apply(img); out[f"und_{t}_gray"] = dm.apply(g1)
+        if not inv:
+            xmap, ymap = cv2.initUndistortRectifyMap(K, D, None, K, (w, h), cv2.CV_32FC1)
+        else:
+            xmap, ymap = cv2.initInverseRectificationMap(K, D, np.eye(3), K, (w, h), cv2.CV_32FC1)
+        out[f"und_{t}_xmap"] = xmap; out[f"und_{t}_ymap"] = ymap
+        out[f"und_{t}_linear"] = cv2.remap(img, xmap, ymap, cv2.INTER_LINEAR)
+    np.savez_compressed(OUT / "preproc.npz", **out)
+    print("preproc.npz", {k: v.shape for k, v in out.items() if k.startswith("und_")})
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     reg, mos = ref_shim.import_reference()
     cv2.setRNGSeed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "preproc":
+        gen_preproc()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "matchfeatures":      # add this fixture without regenerating the others
         gen_matchfeatures(reg, mos)
         return
@@ -368,6 +402,7 @@ def main():
     gen_routing(reg, mos)
     gen_pipeline(reg, mos)
     gen_matchfeatures(reg, mos)
+    gen_preproc()
     (OUT / "PROVENANCE.txt").write_text(
         f"generated by oracle/make_golden.py\ncv2 {cv2.__version__}, numpy {np.__version__}\n"
         f"reference: DTUAqua-ObsTek/mosaic-library checkout at {ref_shim.REFERENCE_SRC.parent}\n")

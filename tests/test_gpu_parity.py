@@ -783,3 +783,60 @@ def test_peer_frames_single_process_and_update_pointer():
         b.step_planned(k, None, peers=peers)
     peers.close()
     assert np.array_equal(a.gather(0), b.gather(0)) and a.frames_applied == b.frames_applied >= 4
+
+
+# ------------------------------------------------------------------------------------------------
+# row N4: pre-processing on the device (preprocessing.py:68-98, 314-346)
+# ------------------------------------------------------------------------------------------------
+def test_preproc_golden_on_gpu(golden):
+    """make_gray / make_bgr / DistortionMapper of the drop-in against what the real reference produced (fixtures of
+    oracle/make_golden.py gen_preproc), numpy in -> numpy out and device tensor in -> device tensor out.  Bit-exact."""
+    from mosaicking_b200 import preprocessing as pre
+    g = golden.preproc
+    for tag in ("a", "b"):
+        for name, fn, src in (("gray_of_bgr", pre.make_gray, "bgr"), ("gray_of_bgra", pre.make_gray, "bgra"), ("bgr_of_gray", pre.make_bgr, "gray"),
+                              ("bgr_of_bgra", pre.make_bgr, "bgra")):
+            want = g[f"{tag}_{name}"]
+            got = fn(g[f"{tag}_{src}"])
+            assert isinstance(got, np.ndarray) and np.array_equal(got, want), (tag, name)
+            got_d = fn(torch.from_numpy(g[f"{tag}_{src}"]).cuda())
+            assert got_d.is_cuda and np.array_equal(got_d.cpu().numpy(), want), (tag, name)
+        gray = g[f"{tag}_gray"]; bgr = g[f"{tag}_bgr"]
+        assert pre.make_gray(gray) is gray and pre.make_bgr(bgr) is bgr              # pass-through like the reference
+    for t, inv in (("fwd", False), ("inv", True)):
+        dm = pre.DistortionMapper(g["K"], g["D"], inverse=inv)
+        assert np.array_equal(dm.apply(g["und_img"]), g[f"und_{t}_bgr"])
+        assert np.array_equal(dm.apply(g["und_gray"]), g[f"und_{t}_gray"])
+        assert np.array_equal(dm.apply(torch.from_numpy(g["und_img"]).cuda()).cpu().numpy(), g[f"und_{t}_bgr"])
+        assert np.array_equal(pre.remap(g["und_img"], g[f"und_{t}_xmap"], g[f"und_{t}_ymap"], "linear"), g[f"und_{t}_linear"])
+    chain = pre.Pipeline([pre.DistortionMapper(g["K"], g["D"]), pre.Crop((16, 8, 200, 150))])
+    assert np.array_equal(chain.apply(g["und_img"]), g["und_fwd_bgr"][8:158, 16:216])
+
+
+def test_preproc_4k_vs_oracle_and_identity():
+    """3840x2160: gray of a random frame equals the oracle; the four conversions through the raw C ABI with pitched rows; a remap
+    through the identity map returns the frame (INTER_LINEAR and INTER_CUBIC: integer coordinates have weight 1 on one tap)."""
+    import ctypes  # noqa: F401
+    from mosaicking_b200 import preprocessing as pre
+    rng = np.random.default_rng(5)
+    h, w = 2160, 3840
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    d = torch.from_numpy(img).cuda()
+    gray = pre.make_gray(d)
+    assert np.array_equal(gray.cpu().numpy(), orc.cvt_color(img, orc.CVT_BGR2GRAY))
+    assert torch.equal(pre.make_bgr(gray)[..., 1], gray)
+    bgra = torch.cat([d, torch.full((h, w, 1), 9, dtype=torch.uint8, device="cuda")], 2).contiguous()
+    assert torch.equal(pre.make_bgr(bgra), d) and torch.equal(pre.make_gray(bgra), gray)
+    # odd width + unaligned pitch through the C ABI: the scalar path
+    sub = img[:37, :333].copy()
+    src = torch.zeros((37, 333 * 3 + 5), dtype=torch.uint8, device="cuda"); src[:, :999] = torch.from_numpy(sub.reshape(37, 999)).cuda()
+    dst = torch.zeros((37, 340), dtype=torch.uint8, device="cuda")
+    mb._lib.check(mb._lib.lib().mk_cvt_color_u8(src.data_ptr(), 37, 333, src.stride(0), 0, dst.data_ptr(), dst.stride(0), None))
+    assert np.array_equal(dst[:, :333].cpu().numpy(), orc.cvt_color(sub, orc.CVT_BGR2GRAY)) and int(dst[:, 333:].sum()) == 0
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    for interp in ("linear", "cubic"):
+        assert torch.equal(pre.remap(d, xs, ys, interp), d)
+    # a shifted, slightly scaled map on a window: equals the oracle, borders included
+    xm = (xs[:300, :400] * 1.013 - 7.3).astype(np.float32); ym = (ys[:300, :400] * 0.991 - 4.6).astype(np.float32)
+    for interp, code in (("linear", orc.INTER_LINEAR), ("cubic", orc.INTER_CUBIC)):
+        assert np.array_equal(pre.remap(img[:320, :420], xm, ym, interp), orc.remap(img[:320, :420], xm, ym, code))

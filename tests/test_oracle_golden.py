@@ -123,3 +123,28 @@ def test_window_oracle_equals_full_canvas_crop():
             orc.mapper_update_window(w2, wm2, (Hc, Wc), (wx, wy), img, H, 0.4, interp)
             assert np.array_equal(f2[wy:wy + wh, wx:wx + ww], w2) and np.array_equal(m2[wy:wy + wh, wx:wx + ww], wm2)
         orc.mapper_update(canvas, cm, img, H, 0.4, orc.INTER_LINEAR)
+
+
+def test_preproc_golden(golden):
+    """preprocessing.make_gray / make_bgr and DistortionMapper.apply of the real reference (preprocessing.py:68-98,314-346):
+    the oracle's cvtColor / remap restatements equal them bit for bit (uint8)."""
+    g = golden.preproc
+    for tag in ("a", "b"):
+        assert np.array_equal(orc.cvt_color(g[f"{tag}_bgr"], orc.CVT_BGR2GRAY), g[f"{tag}_gray_of_bgr"])
+        assert np.array_equal(orc.cvt_color(g[f"{tag}_bgra"], orc.CVT_BGRA2GRAY), g[f"{tag}_gray_of_bgra"])
+        assert np.array_equal(orc.cvt_color(g[f"{tag}_gray"], orc.CVT_GRAY2BGR), g[f"{tag}_bgr_of_gray"])
+        assert np.array_equal(orc.cvt_color(g[f"{tag}_bgra"], orc.CVT_BGRA2BGR), g[f"{tag}_bgr_of_bgra"])
+    for t in ("fwd", "inv"):
+        xm, ym = g[f"und_{t}_xmap"], g[f"und_{t}_ymap"]
+        assert np.array_equal(orc.remap(g["und_img"], xm, ym, orc.INTER_CUBIC), g[f"und_{t}_bgr"])
+        assert np.array_equal(orc.remap(g["und_gray"], xm, ym, orc.INTER_CUBIC), g[f"und_{t}_gray"])
+        assert np.array_equal(orc.remap(g["und_img"], xm, ym, orc.INTER_LINEAR), g[f"und_{t}_linear"])
+
+
+def test_cvt_gray_all_triples_live_cv2():
+    """The 15-bit gray coefficients against cv2 itself on every BGR triple (2^24 pixels)."""
+    cv2 = pytest.importorskip("cv2")
+    v = np.arange(256, dtype=np.uint8)
+    B, G, R = np.meshgrid(v, v, v, indexing="ij")
+    img = np.stack([B.ravel(), G.ravel(), R.ravel()], 1).reshape(4096, 4096, 3)
+    assert np.array_equal(orc.cvt_color(img, orc.CVT_BGR2GRAY), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
