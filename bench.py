@@ -453,6 +453,7 @@ def single_gpu(ctx) -> dict:
     out["batched_compositing"] = batched_compositing(torch, mb, factory, frames, Hs, W, min(K, 64), fh, fw, flush)
     out["alpha_one_compositing"] = alpha_one_compositing(torch, mb, dev, frames, Hs, W, min(K, 64), iso)
     out["warp_only"] = warp_only(torch, mb, dev, iso)
+    out["preproc_4k"] = preproc_record(torch, mb, dev, iso)
     out["other_kernels"] = other_kernels(torch, mb, dev, iso)
     mapper.release()
     del frames, desc_d
@@ -666,9 +667,33 @@ def warp_only(torch, mb, dev, iso) -> dict:
         ts = iso([(lambda i=i: mb.warp_perspective(imgs[i % 4], H, (w, h), "linear", device=dev)) for i in range(12)])
         nbytes = 2.0 * w * h * 3
         med = float(np.median(ts))
-        res[name] = {"kernel": "mk::warp_kernel<1,3>", "bound": "hbm", "achieved": nbytes / (med * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        res[name] = {"kernel": "mk::warp_staged_kernel<1>", "bound": "hbm", "achieved": nbytes / (med * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": nbytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_us": med * 1e3, "launch_us_stats": stats_us(ts),
                      "algorithmic_bytes_per_launch": nbytes, "note": "includes the output allocation of mb.warp_perspective"}
+    return res
+
+
+def preproc_record(torch, mb, dev, iso) -> dict:
+    """Row N4, pre-processing on the device at 3840x2160 (preprocessing.py:68-98,314-346): make_gray, make_bgr of a BGRA frame and
+    the INTER_CUBIC undistortion, each against the HBM copy peak.  Algorithmic bytes = pixels read + written (+ 8 B of map per
+    pixel for the remap); isolated calls, L2 flushed, median of 10."""
+    from mosaicking_b200 import preprocessing as pre
+    pk = peaks()
+    rng = np.random.default_rng(4)
+    h, w = 2160, 3840
+    bgr = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).to(dev) for _ in range(3)]
+    bgra = [torch.from_numpy(rng.integers(0, 256, (h, w, 4), dtype=np.uint8)).to(dev) for _ in range(3)]
+    dm = pre.DistortionMapper(np.array([[2900.0, 0, 1915.5], [0, 2890.0, 1082.5], [0, 0, 1]]), np.array([-0.21, 0.06, 0.0008, -0.0005, -0.004]), device=dev)
+    dm.maps(w, h)
+    res = {}
+    for name, kernel, fn, nbytes in (("make_gray_bgr", "mk::cvt_color_kernel<BGR2GRAY>", lambda i: pre.make_gray(bgr[i % 3]), w * h * 4.0),
+                                     ("make_bgr_bgra", "mk::cvt_color_kernel<BGRA2BGR>", lambda i: pre.make_bgr(bgra[i % 3]), w * h * 7.0),
+                                     ("undistort_cubic", "mk::remap_kernel<CUBIC,3>", lambda i: dm.apply(bgr[i % 3]), w * h * 14.0)):
+        ts = iso([(lambda i=i: fn(i)) for i in range(10)])
+        med = float(np.median(ts))
+        res[name] = {"kernel": kernel, "bound": "hbm", "achieved": nbytes / (med * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": nbytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_us": med * 1e3, "launch_us_stats": stats_us(ts),
+                     "algorithmic_bytes_per_launch": nbytes}
     return res
 
 

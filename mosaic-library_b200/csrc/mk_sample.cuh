@@ -148,6 +148,20 @@ __device__ __forceinline__ uint32_t sample_linear_c1(const uint8_t *__restrict__
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int clamp_u8(int v) { return min(255, max(0, v)); }
 
+// signed 16-bit weight pairs x unsigned bytes: d = a.lo * b.byte[0|2] + a.hi * b.byte[1|3] + c   (SASS IDP.2A)
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t sample_cubic_c3(const uint8_t *__restrict__ src, size_t pitch, int h, int w,
                                                     int X, int Y, const short *__restrict__ tab)
 {
@@ -156,6 +170,11 @@ __device__ __forceinline__ uint32_t sample_cubic_c3(const uint8_t *__restrict__ 
     const short *wt = tab + (ay * 32 + ax) * 16;
     int acc0 = 0, acc1 = 0, acc2 = 0;
     if (sx >= 1 && sx <= w - 5 && sy >= 1 && sy <= h - 3) {
+        // interior: 16 int16 weights = two 16-byte loads (word k of row ky = the pair w[2k], w[2k+1]); every row of the 4x4
+        // footprint is 12 bytes = four aligned words funnel-shifted, channels gathered by PRMT, two IDP.2A per channel and row
+        const uint4 *wq = reinterpret_cast<const uint4 *>(wt);
+        const uint4 wa = __ldg(wq), wb = __ldg(wq + 1);
+        const uint32_t wp[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
         const uint8_t *a = src + (size_t)(sy - 1) * pitch + (size_t)(sx - 1) * 3;
         const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
         const unsigned sh = (unsigned)(ai & 3) * 8;
@@ -165,11 +184,14 @@ __device__ __forceinline__ uint32_t sample_cubic_c3(const uint8_t *__restrict__ 
             const uint32_t *q = reinterpret_cast<const uint32_t *>(base + (size_t)ky * pitch);
             const uint32_t r0 = ldg32(q), r1 = ldg32(q + 1), r2 = ldg32(q + 2), r3 = ldg32(q + 3);
             const uint32_t d0 = __funnelshift_r(r0, r1, sh), d1 = __funnelshift_r(r1, r2, sh),
-                           d2 = __funnelshift_r(r2, r3, sh);  // 12 bytes: 4 BGR pixels
-            const int w0 = wt[ky * 4 + 0], w1 = wt[ky * 4 + 1], w2 = wt[ky * 4 + 2], w3 = wt[ky * 4 + 3];
-            acc0 += (int)(d0 & 255u) * w0 + (int)(d0 >> 24) * w1 + (int)((d1 >> 16) & 255u) * w2 + (int)((d2 >> 8) & 255u) * w3;
-            acc1 += (int)((d0 >> 8) & 255u) * w0 + (int)(d1 & 255u) * w1 + (int)(d1 >> 24) * w2 + (int)((d2 >> 16) & 255u) * w3;
-            acc2 += (int)((d0 >> 16) & 255u) * w0 + (int)((d1 >> 8) & 255u) * w1 + (int)(d2 & 255u) * w2 + (int)(d2 >> 24) * w3;
+                           d2 = __funnelshift_r(r2, r3, sh);  // 12 bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            const uint32_t vb = __byte_perm(__byte_perm(d0, d1, 0x0630), d2, 0x5210);   // B0 B1 B2 B3
+            const uint32_t vg = __byte_perm(__byte_perm(d0, d1, 0x0741), d2, 0x6210);   // G0 G1 G2 G3
+            const uint32_t vr = __byte_perm(__byte_perm(d0, d1, 0x0052), d2, 0x7410);   // R0 R1 R2 R3
+            const uint32_t w01 = wp[2 * ky], w23 = wp[2 * ky + 1];
+            acc0 = dp2a_hi_su(w23, vb, dp2a_lo_su(w01, vb, acc0));
+            acc1 = dp2a_hi_su(w23, vg, dp2a_lo_su(w01, vg, acc1));
+            acc2 = dp2a_hi_su(w23, vr, dp2a_lo_su(w01, vr, acc2));
         }
     } else {
 #pragma unroll
@@ -213,20 +235,6 @@ struct SrcTile {
     const uint8_t *s;   // shared memory
     int sy0, bx0, R, rowbytes;
 };
-
-// signed 16-bit weight pairs x unsigned bytes: d = a.lo * b.byte[0|2] + a.hi * b.byte[1|3] + c   (SASS IDP.2A)
-__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
 // Bilinear weights as two int16 pairs: lut[ay * 32 + ax] = ((w00 | w01 << 16), (w10 | w11 << 16)), weights (32-ax)(32-ay) ...
 // <= 1024.  Per channel the 2x2 quad sits in one register as bytes (v00, v01, v10, v11), so
