@@ -213,11 +213,14 @@ class Iso:
 
     def back_to_back(self, fns, reps: int = 5) -> float:
         """Average duration of one call when the calls are issued back to back (no flush in between; the caller makes
-        the working set of the group larger than L2): ms per call, median over `reps` groups."""
+        the working set of the group larger than L2): ms per call, median over `reps` groups.  A few flushes are queued in
+        front (about 1 ms of GPU work) so that the host is ahead of the GPU for the whole group: the span is device time, not the
+        host's issue rate (a Python call into the library costs about as much as a 1080p launch)."""
         torch = self.torch
         per = []
         for _ in range(reps):
-            self.flush.zero_()
+            for _ in range(6):
+                self.flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for f in fns:
@@ -616,8 +619,8 @@ def pipeline_no_flush(torch, mb, matcher, mapper, desc_d, frames, Hs, W, K) -> d
 
 def batched_compositing(torch, mb, factory, frames, Hs, W, n, fh, fw, flush) -> dict:
     """The offline form of the same work (SequentialMosaic.generate knows every frame of a tile up front): ONE
-    mk_mapper_update_batch launch composites n frames in order, every canvas tile is read and written once.  Timed with CUDA
-    events; a few queued L2 flushes in front keep the GPU busy while the host builds the tile -> frame table."""
+    mk_mapper_update_batch call composites n frames in order -- for alpha blending a back-to-back train of strip-kernel launches.
+    Timed with CUDA events; a few queued L2 flushes in front keep the GPU busy while the host queues the launches."""
     mp = factory(CANVAS, CANVAS)
     fr, hs = frames[W:W + n], Hs[W:W + n]
     mp.update_batch(fr[:2], hs[:2])                       # warm-up (stream-ordered allocator pool, module load)
@@ -637,9 +640,9 @@ def batched_compositing(torch, mb, factory, frames, Hs, W, n, fh, fw, flush) -> 
     pk = peaks()
     achieved = nbytes / (ms * 1e-3) / 1e9
     mp.release()
-    return {"frames_per_launch": n, "us_per_frame": ms * 1e3 / n, "frames_per_s": n / (ms * 1e-3),
-            "roofline": {"kernel": "mk::mapper_update_kernel<batch>", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "note": "per-frame algorithmic byte count; the batch form reads/writes each canvas tile once"}}
+    return {"frames_per_call": n, "us_per_frame": ms * 1e3 / n, "frames_per_s": n / (ms * 1e-3),
+            "roofline": {"kernel": "mk::mapper_strip_kernel (train of launches)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "note": "per-frame algorithmic byte count, frames composited in sequence order by one mk_mapper_update_batch call"}}
 
 
 def alpha_one_compositing(torch, mb, dev, frames, Hs, W, n, iso) -> dict:

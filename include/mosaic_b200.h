@@ -146,9 +146,10 @@ int mk_mapper_update(uint8_t *canvas, size_t canvas_pitch, uint8_t *cmask, size_
                      const double *H_host, double alpha, int interp, int blend, float feather_ramp,
                      int32_t *region_host, void *stream);
 
-/* Batched form ("gather" formulation): `nframes` device-resident frames are composited in sequence order by ONE
- * launch; every canvas tile is read once, updated by all the frames that reach it and written once.  The result is
- * identical to nframes successive mk_mapper_update calls -- what SequentialMosaic.generate does for a tile
+/* Batched form: `nframes` device-resident frames are composited in sequence order by ONE call -- a back-to-back train of
+ * strip-kernel launches for MK_BLEND_ALPHA (that kernel is not HBM bound, so the train is the faster form), one "gather"
+ * launch for MK_BLEND_FEATHER (every canvas tile is read once, updated by all the frames that reach it and written once).
+ * The result is identical to nframes successive mk_mapper_update calls -- what SequentialMosaic.generate does for a tile
  * (src/mosaicking/mosaic.py:678-686).  Arrays with the _host suffix live in HOST memory: src_host[k] is the device
  * pointer of frame k, H_host holds nframes row-major 3x3 float64 matrices.  No ROI masks in this form. */
 int mk_mapper_update_batch(uint8_t *canvas, size_t canvas_pitch, uint8_t *cmask, size_t cmask_pitch,

@@ -778,7 +778,19 @@ extern "C" int mk_mapper_update_batch(uint8_t *canvas, size_t canvas_pitch, uint
         set_error("mk_mapper_update_batch: alignment (canvas/cmask/wacc 16 B + pitch %% 16)");
         return MK_ERR_ALIGN;
     }
-    // per-frame descriptors + the (tile -> ordered frame list) table
+    if (blend == MK_BLEND_ALPHA) {
+        // alpha blending: a train of strip-kernel launches in sequence order.  The persistent strip kernel (mk_strip.cu) is not
+        // HBM bound, so reading every canvas tile once (the gather launch below) buys nothing, and back to back its launches
+        // cost less per frame (18.6 us vs 23.2 us for 1080p frames, bench `batched_compositing`); frames it cannot take
+        // fall back to the tile kernel one by one inside mk_mapper_update.
+        for (int k = 0; k < nframes; ++k) {
+            const int rc = mk_mapper_update(canvas, canvas_pitch, cmask, cmask_pitch, nullptr, 0, canvas_h, canvas_w, src_host[k], src_h_host[k], src_w_host[k],
+                                            src_pitch_host[k], nullptr, 0, H_host + 9 * (size_t)k, alpha, interp, blend, feather_ramp, nullptr, stream);
+            if (rc != MK_OK) return rc;
+        }
+        return MK_OK;
+    }
+    // feather: per-frame descriptors + the (tile -> ordered frame list) table
     const int ntx = (canvas_w + TW - 1) / TW, nty = (canvas_h + TH - 1) / TH;
     std::vector<FrameDesc> frames((size_t)nframes);
     std::vector<std::array<int, 4>> rects((size_t)nframes);

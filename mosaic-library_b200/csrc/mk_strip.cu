@@ -33,8 +33,14 @@ constexpr int BR = CH + 2 * HALO;    // rows of the first phase-1 block of a seg
 constexpr int RING = 64;             // ring of warped rows / bit rows, indexed by a running row counter of the CTA (three chunks in flight)
 constexpr int STHREADS = 256;
 constexpr int MAX_STRIPS = 200;
-constexpr int MAX_CHUNKS = 64;      // chunks one CTA may own
-constexpr int NSRC = 3;             // source boxes in flight per CTA (three: the box of chunk j+3 is requested while chunk j is computed --
+#ifndef MK_MAX_CHUNKS
+#define MK_MAX_CHUNKS 64
+#endif
+constexpr int MAX_CHUNKS = MK_MAX_CHUNKS;      // chunks one CTA may own
+#ifndef MK_NSRC
+#define MK_NSRC 3
+#endif
+constexpr int NSRC = MK_NSRC;             // source boxes in flight per CTA (three: the box of chunk j+3 is requested while chunk j is computed --
                                     // enough lead for a frame that lives in another GPU's memory and arrives over NVLink)
 constexpr int NCV = 4;              // canvas / mask tile buffers: tile i+1 is loading, i-1 is blended, i-2 is being stored, i-3 has left
 constexpr int NROWB = 4;            // coordinate-base buffers (bases of chunk i+2 are written while chunk i-1 may still be read)
@@ -181,6 +187,15 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     uint8_t *const sp = s_dyn + (sb - smem_u32(s_dyn));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // A launch costs about 6 us before and after its work (measured on 64 x 32 px frames): let the next launch of a train be
+    // scheduled now (programmatic dependent launch: its CTAs move in as ours leave and run their prologue; they touch global memory
+    // only after griddepcontrol.wait below, i.e. after this grid has completed), and start fetching the three tensor maps.
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_src) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_cv) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&map_mk) : "memory");
+    }
     const FrameDesc &F = p.f;
     const int boxbytes = p.boxW * p.boxR;                 // bytes one TMA box delivers
     const int boxstride = (boxbytes + 127) & ~127;        // TMA destinations are 128-byte aligned
@@ -209,6 +224,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");      // everything the previous grid of the stream wrote (the canvas!) is visible from here on
 
     // ---- source boxes of ALL chunks of this CTA, four lanes per chunk: the quantised images of the four corners of the haloed
     //      block (columns tileX-2 .. tileX+65) bound every tap of the block as long as W keeps its sign; and the ring offset of the
@@ -529,7 +545,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             mbar_arrive_addr(sb + BAR_V + 8 * (i & 1));
         }
     }
-    if (tid == 224) bulk_wait_all0();      // the last stores must have left shared memory before the CTA exits
+    if (tid == 224) bulk_wait_read0();     // the last stores must have read their tiles out of shared memory before the CTA exits
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -861,8 +877,15 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
     if (rc == MK_OK) rc = encode_image_map(&map_cv, P.canvas, 1, (long)P.Wc * 3, P.Hc, (size_t)P.cpitch, ROWB, CH);
     if (rc == MK_OK) rc = encode_image_map(&map_mk, P.cmask, 1, (long)P.Wc, P.Hc, (size_t)P.mpitch, TW, CH);
     if (rc != MK_OK) return rc;
-    if (interp == MK_INTER_LINEAR) mapper_strip_kernel<MK_INTER_LINEAR><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
-    else mapper_strip_kernel<MK_INTER_CUBIC><<<(unsigned)grid, STHREADS, (size_t)dyn, st>>>(map_src, map_cv, map_mk, S);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(STHREADS); cfg.dynamicSmemBytes = (size_t)dyn; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("MK_NO_PDL") != nullptr;          // diagnosis switch: plain stream-ordered launch
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (interp == MK_INTER_LINEAR) MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, mapper_strip_kernel<MK_INTER_LINEAR>, map_src, map_cv, map_mk, S));
+    else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, mapper_strip_kernel<MK_INTER_CUBIC>, map_src, map_cv, map_mk, S));
     MK_LAUNCH_CHECK("mapper_strip_kernel");
     *done = true;
     return MK_OK;

@@ -250,9 +250,10 @@ class Mapper:
         self.last_region = (region[0], region[1], region[2], region[3])
 
     def update_batch(self, frames: Sequence, Hs: Sequence[np.ndarray]) -> None:
-        """Composite many frames in sequence order with ONE launch (gather formulation: every canvas tile is read once,
-        updated by all the frames that reach it, written once).  Same result as calling update() frame by frame -- the
-        loop SequentialMosaic.generate runs per tile (mosaic.py:678-686).  Frames: uint8 [h, w, 3] arrays / tensors;
+        """Composite many frames in sequence order with ONE call: a back-to-back train of strip-kernel launches (alpha
+        blending), or one gather launch (feather: every canvas tile is read once, updated by all the frames that reach it,
+        written once).  Same result as calling update() frame by frame -- the loop SequentialMosaic.generate runs per tile
+        (mosaic.py:678-686).  Frames: uint8 [h, w, 3] arrays / tensors;
         host frames are uploaded first (they all have to be resident during the launch)."""
         n = len(frames)
         if n != len(Hs):

@@ -55,7 +55,8 @@ def timing(h, w, n=24):
         iso.append(a.elapsed_time(b) * 1e3)
     grp = []
     for rep in range(5):
-        flush.zero_()
+        for _ in range(6):
+            flush.zero_()          # ~1 ms of queued GPU work: the host gets ahead of the GPU, the span below is GPU time only
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for k in range(n):
