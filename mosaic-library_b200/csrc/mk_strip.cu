@@ -155,18 +155,21 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
 
-// INTER_LINEAR from the staged box, no containment test (see sample_linear_c3_smem_fast); `base` = shared address of the box
-__device__ __forceinline__ uint32_t sample_linear_box(uint32_t base, int pitch, int sy0, int bx0, int X, int Y, const uint2 *__restrict__ lut)
+// INTER_LINEAR from the staged box, no containment test (see sample_linear_c3_smem_fast).  `boxrel` = shared address of the box
+// minus bx0, the byte column its first byte stands for (both multiples of 16), so the first tap lives at
+// t = boxrel + r * pitch + 3 * sx: three aligned words from t & ~3 per row, funnel-shifted by 8 * (t & 3) (the shift wraps mod 32).
+__device__ __forceinline__ uint32_t sample_linear_box(uint32_t boxrel, int pitch, int sy0, int X, int Y)
 {
-    const int r = (Y >> 5) - sy0, cb = (X >> 5) * 3 - bx0;
+    const int r = (Y >> 5) - sy0;
     // the four integer weights as two int16 pairs, (w00 | w01 << 16, w10 | w11 << 16) = ((32-ay) * u, ay * u) with
     // u = (32-ax) | ax << 16: three IMADs on the FMA pipe instead of a 32-way divergent table read (8.5 L1 wavefronts per warp)
     const uint32_t ax = (uint32_t)X & 31u, ay = (uint32_t)Y & 31u;
     const uint32_t u = ax * 65535u + 32u;
-    const uint2 wt = make_uint2((32u - ay) * u, ay * u);
-    (void)lut;
-    const uint32_t a = base + r * pitch + (cb & ~3), b = a + pitch;
-    const unsigned sh = (unsigned)(cb & 3) * 8;
+    const uint32_t wbot = ay * u, wtop = (u << 5) - wbot;
+    const uint2 wt = make_uint2(wtop, wbot);
+    const uint32_t t = (uint32_t)(r * pitch) + ((uint32_t)(X >> 5) * 3u + boxrel);
+    const uint32_t a = t & ~3u, b = a + (uint32_t)pitch;
+    const unsigned sh = t << 3;
     const uint32_t a0 = lds32(a), a1 = lds32(a + 4), a2 = lds32(a + 8), b0 = lds32(b), b1 = lds32(b + 4), b2 = lds32(b + 8);
     return lerp3_dp2a(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(b0, b1, sh),
                       __funnelshift_r(b1, b2, sh), wt);
@@ -322,7 +325,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             if (rc.z != 0 && INTERP == 1) {        // staged: the box holds the halo columns' taps too (its corners are columns tileX-2 / tileX+65)
                 if (F.M.affine) quantize_fast_t<true>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
                 else quantize_fast_t<false>(F.M, F.M.wr, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
-                mv = sample_linear_box(src_base + (uint32_t)((j % NSRC) * boxstride), p.boxW, rc.x, rc.y, X, Y, p.lut) ? 255u : 0u;
+                mv = sample_linear_box(src_base + (uint32_t)((j % NSRC) * boxstride) - (uint32_t)rc.y, p.boxW, rc.x, X, Y) ? 255u : 0u;
             } else {
                 quantize(F.M, rb[0], rb[1], rb[2], sx, sy, sw, X, Y);
                 mv = sample_c3_tile<INTERP>(rc.z != 0, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut) ? 255u : 0u;
@@ -356,7 +359,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             const bool staged = rc.z != 0;
             const int rbase = first + rc.w;                 // ring slot of block row r = (rbase + r) & 63
             const int sbuf = i % NSRC;
-            const uint32_t box = src_base + (uint32_t)(sbuf * boxstride);
+            const uint32_t boxrel = src_base + (uint32_t)(sbuf * boxstride) - (uint32_t)bx0;
             // the ring slots of chunk i were last used by chunk i-4 (or later): everybody must have blended chunk i-3
             if (i >= 3) mbar_wait_addr(sb + BAR_P2 + 8 * ((i - 3) & 1), (uint32_t)((i - 3) >> 1) & 1u, 600 + i);
             mbar_wait_addr(sb + BAR_SRC + 8 * sbuf, (uint32_t)(i / NSRC) & 1u, 100 + i);
@@ -391,7 +394,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                     int X, Y;
                     if constexpr (FAST) quantize_fast_t<AFF>(F.M, wr, X0, Y0, W0, mx, my, mw, X, Y);
                     else quantize(F.M, X0, Y0, W0, mx, my, mw, X, Y);
-                    if constexpr (FAST && INTERP == 1) return sample_linear_box(box, p.boxW, sy0, bx0, X, Y, p.lut);
+                    if constexpr (FAST && INTERP == 1) return sample_linear_box(boxrel, p.boxW, sy0, X, Y);
                     else return sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
                 };
                 int r = r_lo + (warp >> 1);
@@ -628,6 +631,7 @@ __global__ void __launch_bounds__(256, 4) warp_staged_kernel(const __grid_consta
         auto body = [&](auto fast_tag, auto affine_tag) {
             constexpr bool FAST = decltype(fast_tag)::value, AFF = decltype(affine_tag)::value;
             const double wr = p.M.wr;
+            const uint32_t boxrel = box - (uint32_t)bx0;
             SrcTile T;
             T.s = s_dyn + (box - smem_u32(s_dyn)); T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
             auto one = [&](int r) -> uint32_t {
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(256, 4) warp_staged_kernel(const __grid_consta
                 int X, Y;
                 if constexpr (FAST) quantize_fast_t<AFF>(p.M, wr, X0, Y0, W0, mx, my, mw, X, Y);
                 else quantize(p.M, X0, Y0, W0, mx, my, mw, X, Y);
-                if constexpr (FAST && INTERP == 1) return sample_linear_box(box, p.boxW, sy0, bx0, X, Y, p.lut);
+                if constexpr (FAST && INTERP == 1) return sample_linear_box(boxrel, p.boxW, sy0, X, Y);
                 else return sample_c3_tile<INTERP>(FAST, T, p.src, p.spitch, p.h, p.w, X, Y, p.cubic, p.lut);
             };
             int r = warp >> 1;
