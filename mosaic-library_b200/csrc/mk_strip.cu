@@ -51,6 +51,31 @@ constexpr int NROWB = 4;            // coordinate-base buffers (bases of chunk i
 #define MK_STRIP_ILP 4
 #endif
 constexpr int STRIP_OCC = MK_STRIP_OCC;   // CTAs per SM the register budget is set for (four rows per warp in flight need ~76 registers)
+#ifndef MK_SVC_WARP
+#define MK_SVC_WARP 0
+#endif
+// Build knob (A/B measured, off): a ninth "service" warp erodes the validity rows and requests the source boxes instead of warp 1.
+// In the ncu source view the other warps poll the "bit rows ready" barrier 13 times per chunk (12 % of all issued instructions), which
+// looked like a critical chain on warp 1 -- but neither this warp, nor MK_P1_BALANCE, nor MK_WAIT_BACKOFF changes the launch time
+// (16.0-16.4 us back to back at 1080p, 50-51.5 us at 4K): the polls only fill issue slots nobody else wants.  What does move the
+// time is the number of USEFUL instructions (MK_EXP_SKIP_* below: phase-1 arithmetic -30 %, phase-2 arithmetic -15 %, side halo -3 %).
+constexpr int SVC = MK_SVC_WARP;
+#ifndef MK_P1_BALANCE
+#define MK_P1_BALANCE 0
+#endif
+// Phase-1 rows of a chunk per warp (warp & 1 = which 32-column half, the four warps of a half split its rows): first row | rows << 8
+// for a 16-row chunk, the same << 16 for the 20-row first chunk of a segment.  The warps with a side job (4-6: side-halo columns,
+// ~150 instructions per chunk; 2-3: coordinate bases; 7: TMA) take fewer rows than warps 0 and 1, so that all eight finish a chunk
+// at about the same time -- the pipeline runs at the pace of its slowest warp, and the others spend their slack polling.
+#define MK_SH(a16, n16, a20, n20) ((uint32_t)(a16) | (uint32_t)(n16) << 8 | (uint32_t)(a20) << 16 | (uint32_t)(n20) << 24)
+__constant__ uint32_t c_p1_share[8] = {
+    MK_SH(0, 5, 0, 6),  MK_SH(0, 5, 0, 6),      // warps 0, 1
+    MK_SH(5, 5, 6, 6),  MK_SH(5, 4, 6, 5),      // warps 2, 3
+    MK_SH(10, 3, 12, 4), MK_SH(9, 3, 11, 4),    // warps 4, 5
+    MK_SH(13, 3, 16, 4), MK_SH(12, 4, 15, 5),   // warps 6, 7
+};
+constexpr int NTHR = STHREADS + 32 * SVC;  // threads per CTA
+constexpr int ERODE_WARP = SVC ? 8 : 1;
 
 // shared-memory layout of the strip kernel: ONE dynamic block, every array at a constant offset from its 128-byte aligned base, so
 // every shared address is `base register + immediate` (static __shared__ arrays cost an S2R / LEA pair per address on sm_100)
@@ -126,6 +151,30 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t a, uint32_t parity, int 
 #endif
     __trap();
 }
+// The same for waits that are expected to be long (a warp that is ahead of the pipeline): the hardware wakes a suspended try_wait on
+// every barrier event of the CTA (13 polls of 7 instructions per wait in the ncu source view), so sleep blind between the polls.
+#ifndef MK_WAIT_BACKOFF
+#define MK_WAIT_BACKOFF 0          // build knob (A/B measured, off): blind sleep in ns between polls of the long waits
+#endif
+__device__ __forceinline__ void mbar_wait_slack(uint32_t a, uint32_t parity, int what = 0)
+{
+#if MK_WAIT_BACKOFF > 0
+    uint32_t ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
+        __nanosleep(MK_WAIT_BACKOFF);
+        asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+#else
+    mbar_wait_addr(a, parity, what);
+#endif
+}
 __device__ __forceinline__ void mbar_wait_or_trap(unsigned long long *bar, uint32_t parity, int what = 0) { mbar_wait_addr(smem_u32(bar), parity, what); }
 __device__ __forceinline__ void mbar_init_addr(uint32_t a, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t a) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory"); }
@@ -181,7 +230,7 @@ __device__ __forceinline__ uint32_t sample_linear_box(uint32_t boxrel, int pitch
 // waits a warp meets are on things produced an iteration earlier.  Side jobs: warp 1 erodes chunk i and requests source box i+3,
 // warps 2-3 the coordinate bases of chunk i+2, warps 4-6 the side-halo columns of chunk i+1, warp 7 stores tile i-2 and loads tile i+1.
 template <int INTERP>
-__global__ void __launch_bounds__(STHREADS, STRIP_OCC)
+__global__ void __launch_bounds__(NTHR, STRIP_OCC)
 mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_cv,
                     const __grid_constant__ CUtensorMap map_mk, const __grid_constant__ StripParams p)
 {
@@ -310,6 +359,9 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
         const int tileX = blk.x, first = blk.z, nr = blk.w;
         if (t >= nr * 4) return;
+#ifdef MK_EXP_SKIP_SIDE        // timing experiment only (wrong at frame edges): how much do the side-halo columns cost?
+        { const int4 rq = lds128i(sb + OFF_RECT + 16 * j); sts8(sb + OFF_SIDE + (uint32_t)((first + (t >> 2) + rq.w) & (RING - 1)) * 4u + (uint32_t)(t & 3), 255u); return; }
+#endif
         const int4 rc = lds128i(sb + OFF_RECT + 16 * j);
         SrcTile T;
         T.s = sp + OFF_SRC + (j % NSRC) * boxstride; T.sy0 = rc.x; T.bx0 = rc.y; T.R = p.boxR; T.rowbytes = p.boxW;
@@ -339,6 +391,41 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
         side_halo(0, tid);
     }
 
+    // erosion of chunk i (everybody's rows are in) and the request for source box i+NSRC: one warp
+    auto erode_chunk = [&](int i) {
+            mbar_wait_slack(sb + BAR_RR + 8 * (i & 1), (uint32_t)(i >> 1) & 1u, 400 + i);
+            if (lane == 0 && i + NSRC < n) issue_src(i + NSRC);      // into the buffer phase 1 of this chunk has finished reading
+            const int4 blk = lds128i(sb + OFF_BLK + 16 * i);
+            const int fy = blk.y, first = blk.z, nr = blk.w;
+            const int roff = (int)lds32(sb + OFF_RECT + 16 * i + 12);
+            if (lane < nr) {
+                const uint32_t ri = (uint32_t)(first + lane + roff) & (RING - 1);
+                const unsigned long long m = lds64(sb + OFF_M0 + ri * 8u);
+                const uint32_t sd = lds32(sb + OFF_SIDE + ri * 4u);
+                const unsigned long long l2 = (sd & 0xFFu) ? 1ull : 0ull, l1 = (sd & 0xFF00u) ? 1ull : 0ull;
+                const unsigned long long r1 = (sd & 0xFF0000u) ? 1ull : 0ull, r2 = (sd & 0xFF000000u) ? 1ull : 0ull;
+                const unsigned long long sl1 = (m << 1) | l1, sl2 = (m << 2) | (l1 << 1) | l2;
+                const unsigned long long sr1 = (m >> 1) | (r1 << 63), sr2 = (m >> 2) | (r1 << 62) | (r2 << 63);
+                sts64(sb + OFF_H + ri * 8u, m & sl1 & sl2 & sr1 & sr2);
+            }
+            __syncwarp();
+            unsigned long long ev = 0;
+            if (lane < CH) {
+                const int y = fy + lane + roff;
+                ev = lds64(sb + OFF_H + (uint32_t)((y - 2) & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y - 1) & (RING - 1)) * 8u) &
+                     lds64(sb + OFF_H + (uint32_t)(y & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y + 1) & (RING - 1)) * 8u) &
+                     lds64(sb + OFF_H + (uint32_t)((y + 2) & (RING - 1)) * 8u);
+                sts64(sb + OFF_V + (uint32_t)((i & 1) * CH + lane) * 8u, ev);
+            }
+            const int any = __any_sync(0xffffffffu, ev != 0ull);
+            if (lane == 0) sts32(sb + OFF_ANY + 4 * (i & 3), (uint32_t)any);
+            mbar_arrive_addr(sb + BAR_V + 8 * (i & 1));
+    };
+    if (SVC && warp == ERODE_WARP) {
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) erode_chunk(i);
+        return;
+    }
     const int half = warp & 1, cx = half * 32 + lane;
     // lanes whose column lies outside the canvas (last strip only) sample column 0 of the strip instead and discard the result:
     // no divergence in the row loop, and every tap stays inside the staged box
@@ -347,6 +434,9 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
     double mx = dmul(F.M.m[0], dx1), my = dmul(F.M.m[3], dx1), mw = dmul(F.M.m[6], dx1);
     const uint32_t warp_base = sb + OFF_WARP + (uint32_t)cx * 4u;
     const uint32_t m0_base = sb + OFF_M0 + (uint32_t)half * 4u;
+#if MK_P1_BALANCE
+    const uint32_t share = c_p1_share[warp];
+#endif
 
 #pragma unroll 1
     for (int i = 0; i <= n + 1; ++i) {
@@ -388,6 +478,9 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                 SrcTile T;
                 T.s = sp + OFF_SRC + sbuf * boxstride; T.sy0 = sy0; T.bx0 = bx0; T.R = p.boxR; T.rowbytes = p.boxW;
                 auto one = [&](int r) -> uint32_t {
+#ifdef MK_EXP_SKIP_P1          // timing experiment only (wrong results): how much of the launch is phase-1 arithmetic?
+                    return 0x00010101u + (uint32_t)r;
+#endif
                     double X0, Y0, W0 = 0.0;
                     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(X0), "=d"(Y0) : "r"(rowb + (uint32_t)r * 32u));
                     if constexpr (!AFF) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(W0) : "r"(rowb + (uint32_t)r * 32u + 16u));
@@ -397,6 +490,24 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                     if constexpr (FAST && INTERP == 1) return sample_linear_box(boxrel, p.boxW, sy0, X, Y);
                     else return sample_c3_tile<INTERP>(FAST, T, F.src, F.spitch, F.h, F.w, X, Y, p.cubic, p.lut);
                 };
+#if MK_P1_BALANCE
+                // this warp's contiguous rows of its half: fewer for the warps that carry a side job (see c_p1_share)
+                const uint32_t shr = share >> (nr == BR ? 16 : 0);
+                int r = max(r_lo, (int)(shr & 0xFFu));
+                const int re = min(r_hi, (int)((shr & 0xFFu) + ((shr >> 8) & 0xFFu)));
+#pragma unroll 1
+                for (; r + 3 <= re; r += 3) {     // three independent rows in flight
+                    const uint32_t pa = one(r), pb = one(r + 1), pc = one(r + 2);
+                    finish_row(r, xvalid ? pa : 0u); finish_row(r + 1, xvalid ? pb : 0u); finish_row(r + 2, xvalid ? pc : 0u);
+                }
+                if (r + 2 <= re) {
+                    const uint32_t pa = one(r), pb = one(r + 1);
+                    finish_row(r, xvalid ? pa : 0u); finish_row(r + 1, xvalid ? pb : 0u);
+                } else if (r < re) {
+                    const uint32_t pa = one(r);
+                    finish_row(r, xvalid ? pa : 0u);
+                }
+#else
                 int r = r_lo + (warp >> 1);
 #if MK_STRIP_ILP == 4
                 if (r + 12 < r_hi) {              // the usual case (16 or 20 rows inside the canvas): four independent rows in flight
@@ -417,6 +528,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
                     const uint32_t pa = one(r);
                     finish_row(r, xvalid ? pa : 0u);
                 }
+#endif
             };
             if (staged) {
                 if (F.M.affine) body(std::true_type{}, std::true_type{});
@@ -463,13 +575,17 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             const int4 blk = lds128i(sb + OFF_BLK + 16 * j);
             const int fy = blk.y;
             const int roff = (int)lds32(sb + OFF_RECT + 16 * j + 12);
-            mbar_wait_addr(sb + BAR_V + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 500 + i);
+            mbar_wait_slack(sb + BAR_V + 8 * (j & 1), (uint32_t)(j >> 1) & 1u, 500 + i);
             const int r = tid >> 4, g = tid & 15;
             const unsigned long long v = lds64(sb + OFF_V + (uint32_t)((j & 1) * CH + r) * 8u);
             const uint32_t vw = (g & 8) ? (uint32_t)(v >> 32) : (uint32_t)v;
             const unsigned mb = (vw >> (4 * (g & 7))) & 15u;
             mbar_wait_addr(sb + BAR_CV + 8 * cbuf, (uint32_t)(j / NCV) & 1u, 200 + i);
+#ifdef MK_EXP_SKIP_P2          // timing experiment only (wrong results): how much of the launch is phase-2 arithmetic?
+            if (false) {
+#else
             if (mb) {
+#endif
                 uint32_t *cw = reinterpret_cast<uint32_t *>(sp + OFF_CANVAS + cbuf * (CH * ROWB) + r * ROWB + 12 * g);
                 uint32_t *ms = reinterpret_cast<uint32_t *>(sp + OFF_MASK + cbuf * (CH * TW) + r * TW + 4 * g);
                 const uint32_t c0w = cw[0], c1w = cw[1], c2w = cw[2], mk4 = *ms;
@@ -517,36 +633,7 @@ mapper_strip_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_co
             mbar_arrive_addr(sb + BAR_P2 + 8 * (j & 1));
         }
 
-        // =========================== warp 1: erosion of chunk i (everybody's rows are in), source box of chunk i+3 ===========================
-        if (warp == 1 && i < n) {
-            mbar_wait_addr(sb + BAR_RR + 8 * (i & 1), (uint32_t)(i >> 1) & 1u, 400 + i);
-            if (lane == 0 && i + NSRC < n) issue_src(i + NSRC);      // into the buffer phase 1 of this chunk has finished reading
-            const int4 blk = lds128i(sb + OFF_BLK + 16 * i);
-            const int fy = blk.y, first = blk.z, nr = blk.w;
-            const int roff = (int)lds32(sb + OFF_RECT + 16 * i + 12);
-            if (lane < nr) {
-                const uint32_t ri = (uint32_t)(first + lane + roff) & (RING - 1);
-                const unsigned long long m = lds64(sb + OFF_M0 + ri * 8u);
-                const uint32_t sd = lds32(sb + OFF_SIDE + ri * 4u);
-                const unsigned long long l2 = (sd & 0xFFu) ? 1ull : 0ull, l1 = (sd & 0xFF00u) ? 1ull : 0ull;
-                const unsigned long long r1 = (sd & 0xFF0000u) ? 1ull : 0ull, r2 = (sd & 0xFF000000u) ? 1ull : 0ull;
-                const unsigned long long sl1 = (m << 1) | l1, sl2 = (m << 2) | (l1 << 1) | l2;
-                const unsigned long long sr1 = (m >> 1) | (r1 << 63), sr2 = (m >> 2) | (r1 << 62) | (r2 << 63);
-                sts64(sb + OFF_H + ri * 8u, m & sl1 & sl2 & sr1 & sr2);
-            }
-            __syncwarp();
-            unsigned long long ev = 0;
-            if (lane < CH) {
-                const int y = fy + lane + roff;
-                ev = lds64(sb + OFF_H + (uint32_t)((y - 2) & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y - 1) & (RING - 1)) * 8u) &
-                     lds64(sb + OFF_H + (uint32_t)(y & (RING - 1)) * 8u) & lds64(sb + OFF_H + (uint32_t)((y + 1) & (RING - 1)) * 8u) &
-                     lds64(sb + OFF_H + (uint32_t)((y + 2) & (RING - 1)) * 8u);
-                sts64(sb + OFF_V + (uint32_t)((i & 1) * CH + lane) * 8u, ev);
-            }
-            const int any = __any_sync(0xffffffffu, ev != 0ull);
-            if (lane == 0) sts32(sb + OFF_ANY + 4 * (i & 3), (uint32_t)any);
-            mbar_arrive_addr(sb + BAR_V + 8 * (i & 1));
-        }
+        if (!SVC && warp == 1 && i < n) erode_chunk(i);
     }
     if (tid == 224) bulk_wait_read0();     // the last stores must have read their tiles out of shared memory before the CTA exits
 }
@@ -762,7 +849,7 @@ static int strip_occupancy(int dyn_smem, int *occ)
     }
     static int cached_dev = -1, cached_smem = -1, cached_occ = 0;       // the query costs microseconds: once per (device, shared-memory size)
     if (cached_dev != dev || cached_smem != dyn_smem) {
-        MK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_occ, mapper_strip_kernel<INTERP>, STHREADS, (size_t)dyn_smem));
+        MK_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_occ, mapper_strip_kernel<INTERP>, NTHR, (size_t)dyn_smem));
         cached_dev = dev; cached_smem = dyn_smem;
     }
     *occ = cached_occ;
@@ -882,7 +969,7 @@ int launch_strip_update(const MapperParams &P, const double *H, int interp, cons
     if (rc == MK_OK) rc = encode_image_map(&map_mk, P.cmask, 1, (long)P.Wc, P.Hc, (size_t)P.mpitch, TW, CH);
     if (rc != MK_OK) return rc;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(STHREADS); cfg.dynamicSmemBytes = (size_t)dyn; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = (size_t)dyn; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -326,25 +326,41 @@ class Mapper:
         return h * w * 3 + area * (8 + (8 if self._blend == _lib.BLEND_FEATHER else 0))
 
 
-def warp_perspective(image, H: np.ndarray, dsize: tuple[int, int], interp="linear", device=None) -> torch.Tensor:
+def warp_perspective(image, H: np.ndarray, dsize: tuple[int, int], interp="linear", device=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """cv2.warpPerspective(image, H, dsize, None, interp, BORDER_CONSTANT, 0) on the GPU
-    (mosaic.py:114 / transformations.py:116).  uint8, 1 or 3 channels; returns a device tensor."""
+    (mosaic.py:114 / transformations.py:116).  uint8, 1 or 3 channels; returns a device tensor.
+
+    A contiguous device tensor whose rows are a multiple of 16 bytes (1920 or 3840 px x 3) is read in place; anything else is
+    copied into a pitched staging buffer first.  `out` (device, uint8, contiguous, Hd x Wd[ x cn], rows a multiple of 16 bytes)
+    receives the result without an allocation -- like cv2's `dst` argument."""
     device = _cuda_device(device)
     t = image if isinstance(image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(image))
     cn = 1 if t.ndim == 2 else int(t.shape[2])
     h, w = int(t.shape[0]), int(t.shape[1])
-    pitch = _round_up(w * cn, 128)
-    src = torch.empty((h, pitch), dtype=torch.uint8, device=device)
-    src[:, : w * cn].copy_(t.reshape(h, w * cn), non_blocking=True)
+    if t.is_cuda and t.device == device and t.dtype == torch.uint8 and t.is_contiguous() and (w * cn) % 16 == 0 and t.data_ptr() % 16 == 0:
+        src, pitch = t.reshape(h, w * cn), w * cn
+    else:
+        pitch = _round_up(w * cn, 128)
+        src = torch.empty((h, pitch), dtype=torch.uint8, device=device)
+        src[:, : w * cn].copy_(t.reshape(h, w * cn), non_blocking=True)
     Wd, Hd = int(dsize[0]), int(dsize[1])
-    dpitch = _round_up(Wd * cn, 128)
-    dst = torch.empty((Hd, dpitch), dtype=torch.uint8, device=device)
+    if out is not None:
+        want = (Hd, Wd) if cn == 1 else (Hd, Wd, cn)
+        if (not out.is_cuda or out.device != device or out.dtype != torch.uint8 or tuple(out.shape) != want or not out.is_contiguous()
+                or (Wd * cn) % 16 or out.data_ptr() % 16):
+            raise ValueError(f"warp_perspective: out must be a contiguous uint8 tensor {want} on {device} with rows of a multiple of 16 bytes")
+        dst, dpitch = out.reshape(Hd, Wd * cn), Wd * cn
+    else:
+        dpitch = _round_up(Wd * cn, 128)
+        dst = torch.empty((Hd, dpitch), dtype=torch.uint8, device=device)
     Hm = np.ascontiguousarray(np.asarray(H, dtype=np.float64).reshape(3, 3))
     with _current_device(device):
         _lib.check(_lib.lib().mk_warp_perspective_u8(src.data_ptr(), h, w, cn, pitch, Hm.ctypes.data, dst.data_ptr(), Hd, Wd,
                                                      dpitch, INTERP[interp], torch.cuda.current_stream(device).cuda_stream))
-    out = dst[:, : Wd * cn]
-    return out.reshape(Hd, Wd) if cn == 1 else out.reshape(Hd, Wd, cn)
+    if out is not None:
+        return out
+    res = dst[:, : Wd * cn]
+    return res.reshape(Hd, Wd) if cn == 1 else res.reshape(Hd, Wd, cn)
 
 
 # ------------------------------------------------------------------------------------------------

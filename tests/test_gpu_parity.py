@@ -341,6 +341,24 @@ def test_warp_full_hd_vs_oracle():
     assert np.array_equal(got, orc.warp_perspective(img, H, (2600, 1800), 1))
 
 
+@pytest.mark.parametrize("interp,code", [("linear", 1), ("cubic", 2)])
+def test_warp_device_in_place_and_out(interp, code):
+    """Device frame read in place (row = 1920 * 3 bytes, no staging copy) into a preallocated, unpadded `out` (cv2's dst argument);
+    a destination whose rows are not a multiple of 16 bytes is refused."""
+    import torch
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    th = 0.1
+    H = np.array([[np.cos(th), -np.sin(th), 90.5], [np.sin(th), np.cos(th), -60.25], [0, 0, 1.0]])
+    dev_img = torch.from_numpy(img).cuda()
+    out = torch.full((1080, 1920, 3), 7, dtype=torch.uint8, device="cuda")
+    res = mb.warp_perspective(dev_img, H, (1920, 1080), interp, out=out)
+    assert res is out
+    assert np.array_equal(out.cpu().numpy(), orc.warp_perspective(img, H, (1920, 1080), code))
+    with pytest.raises(ValueError):
+        mb.warp_perspective(dev_img, H, (1918, 1080), interp, out=torch.empty((1080, 1918, 3), dtype=torch.uint8, device="cuda"))
+
+
 # ------------------------------------------------------------------------------------------------
 # fused warp + blend (Mapper)
 # ------------------------------------------------------------------------------------------------
