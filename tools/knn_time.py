@@ -22,6 +22,19 @@ def timeit(fn, n=20, warm=3):
     return np.median(ts), min(ts)
 
 
+def train(fn, n=20, reps=5):
+    """us per call in a train of n calls (no flush inside; a few memsets first so the host gets ahead of the GPU)"""
+    out = []
+    for _ in range(reps):
+        for _ in range(4): flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n): fn()
+        b.record(); torch.cuda.synchronize()
+        out.append(a.elapsed_time(b) * 1e3 / n)
+    return np.median(out)
+
+
 def same(a, b):
     return all(torch.equal(x, y) for x, y in zip(a, b))
 
@@ -34,10 +47,10 @@ for nq, nt in ((5000, 5000), (4999, 5003), (777, 9001)):
     m = mb.Matcher(norm="hamming", engine="tensor")
     ok = same(ref, m.knn_match_device(q, t, 0.7))
     med, best = timeit(lambda: m.knn_match_device(q, t, 0.7))
-    print(f"hamming tcgen05 {nq}x{nt}: median {med:.1f} best {best:.1f} us  identical to XOR+POPC: {ok}")
+    print(f"hamming tcgen05 {nq}x{nt}: median {med:.1f} best {best:.1f} us, train {train(lambda: m.knn_match_device(q, t, 0.7)):.2f} us/call  identical to XOR+POPC: {ok}")
     m2 = mb.Matcher(norm="l2")
     med, best = timeit(lambda: m2.knn_match_device(q, t, 0.7))
-    print(f"l2-u8 tcgen05 {nq}x{nt}: median {med:.1f} best {best:.1f} us")
+    print(f"l2-u8 tcgen05 {nq}x{nt}: median {med:.1f} best {best:.1f} us, train {train(lambda: m2.knn_match_device(q, t, 0.7)):.2f} us/call")
 for n, nt in ((8000, 8000), (4000, 4000), (8000, 7777)):
     q = torch.from_numpy(rng.integers(0, 200, (n, 128)).astype(np.float32)).to(dev)
     t = torch.from_numpy(rng.integers(0, 200, (nt, 128)).astype(np.float32)).to(dev)
@@ -48,4 +61,5 @@ for n, nt in ((8000, 8000), (4000, 4000), (8000, 7777)):
     ref = m.knn_match_device(q2, t, 0.7)
     ok = all(torch.equal(x[1:], y[1:]) for x, y in zip(out, ref))
     med, best = timeit(lambda: m.knn_match_device(q, t, 0.7), n=10, warm=2)
-    print(f"l2 f32 tcgen05 {n}x{nt}x128: median {med:.1f} best {best:.1f} us -> {2.0*n*nt*128/med/1e6:.0f} TFLOP/s  identical to SIMT: {ok}")
+    tr = train(lambda: m.knn_match_device(q, t, 0.7), n=10)
+    print(f"l2 f32 tcgen05 {n}x{nt}x128: median {med:.1f} best {best:.1f} us, train {tr:.2f} us/call -> {2.0*n*nt*128/tr/1e6:.0f} TFLOP/s  identical to SIMT: {ok}")
