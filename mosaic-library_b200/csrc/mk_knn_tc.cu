@@ -768,7 +768,9 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
     const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
     const int wpb = 8, rows = rows_q + rows_t;
-    if (norm == MK_NORM_HAMMING_TC)
+    static const bool exp_skip_prep = getenv("MK_EXP_SKIP_PREP") != nullptr;   // timing experiment only: operands of the previous call
+    if (exp_skip_prep) { /* nothing */ }
+    else if (norm == MK_NORM_HAMMING_TC)
         knn_tc_prep_bits_kernel<<<(int)(((long)rows * (pl.kp >> 4) + 255) / 256), 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t, stride,
                                                                         dim, pl.kp, static_cast<uint8_t *>(qb), static_cast<uint8_t *>(tb), qn, tn,
                                                                         batched ? nullptr : n_keep, flags, (int)(zero_bytes / 4));

@@ -12,6 +12,7 @@ dev = torch.device("cuda:0")
 flush = torch.empty(1024 << 20, dtype=torch.uint8, device=dev)
 rng = np.random.default_rng(0)
 tag = "strip" if os.environ.get("MK_STRIP", "1") != "0" else "tile"
+INTERP = os.environ.get("K4_INTERP", "linear")        # K4_INTERP=cubic times the reference Mapper's default interpolation
 
 
 def parity():
@@ -44,7 +45,7 @@ def timing(h, w, n=24):
     C = 16384
     frames = [torch.from_numpy(rng.integers(1, 256, (h, w, 3), dtype=np.uint8)).to(dev) for _ in range(n)]
     Hs = [trajectory(k + 5, w, h, C) for k in range(n)]
-    mp = mb.Mapper(C, C, alpha_blend=0.5, interp="linear")
+    mp = mb.Mapper(C, C, alpha_blend=0.5, interp=INTERP)
     for k in range(3):
         mp.update_device(frames[k], Hs[k])
     iso = []
@@ -65,7 +66,7 @@ def timing(h, w, n=24):
         grp.append(a.elapsed_time(b) * 1e3 / n)
     nbytes = np.mean([mp.footprint_bytes(h, w, H) for H in Hs])
     iso = np.array(iso)
-    print(f"[{tag}] {w}x{h}: isolated min/med/max {iso.min():.1f}/{np.median(iso):.1f}/{iso.max():.1f} us -> {nbytes / np.median(iso) / 1e3:.0f} GB/s; "
+    print(f"[{tag}] {INTERP} {w}x{h}: isolated min/med/max {iso.min():.1f}/{np.median(iso):.1f}/{iso.max():.1f} us -> {nbytes / np.median(iso) / 1e3:.0f} GB/s; "
           f"back-to-back {np.median(grp):.1f} us/launch -> {nbytes / np.median(grp) / 1e3:.0f} GB/s ({nbytes / 1e6:.1f} MB algorithmic)")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
