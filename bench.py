@@ -896,35 +896,44 @@ def multi_gpu(ctx) -> dict:
         barrier()
         return max_over_ranks(float(sum(e[0].elapsed_time(e[1]) for e in evs_)))
 
+    def measured_pass(mode):
+        """W untimed + K timed steps with this frame transport -> everything the JSON line needs from the pass."""
+        transport["mode"] = mode
+        mosaic._posted.clear()
+        for k in range(W):
+            one_step(k, last=(k == W - 1))
+        barrier()
+        clocks = ClockSampler(local)
+        clocks.start()
+        time.sleep(0.25)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+        n0 = mb.launch_count()
+        sent0, applied0 = mosaic.bytes_sent, mosaic.frames_applied
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            flush.zero_()
+            one_step(W + k, evs[k], last=(k == K - 1))
+        barrier()
+        t1 = time.perf_counter()
+        launches = mb.launch_count() - n0
+        ck = clocks.stop(t0, t1)
+        step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+        total_ms = max_over_ranks(float(step_ms.sum()))
+        routed, applied, launches_all = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - applied0, launches])
+        return {"mode": mode, "total_ms": total_ms, "routed": routed, "applied": applied, "launches_all": launches_all, "clocks": ck}
+
+    # Both frame transports get the same full pass; the faster one (same answer on every rank: the times are maxima over ranks) is
+    # the headline and the other one is reported next to it.  --transport only decides which runs last.  NCCL's send/recv of a
+    # whole frame wins at N = 2 (it hides under the kernels); from N = 4 on its per-peer bandwidth drops and the zero-copy peer
+    # reads win.
     other = "nccl" if args.transport == "peer" else "peer"
-    transport["mode"] = other                        # the other transport first (untimed warm-up + one timed pass), then the headline
-    for k in range(W):
-        one_step(k, last=(k == W - 1))
-    other_ms = timed_steps()
-    mosaic._posted.clear()
-    transport["mode"] = args.transport
-    for k in range(W):
-        one_step(k, last=(k == W - 1))
-    barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    time.sleep(0.25)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
-    n0 = mb.launch_count()
-    sent0, applied0 = mosaic.bytes_sent, mosaic.frames_applied
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        flush.zero_()
-        one_step(W + k, evs[k], last=(k == K - 1))
-    barrier()
-    t1 = time.perf_counter()
-    launches = mb.launch_count() - n0
-    ck = clocks.stop(t0, t1)
-    step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
-    total_ms = max_over_ranks(float(step_ms.sum()))
+    passes = [measured_pass(other), measured_pass(args.transport)]
+    best = min(passes, key=lambda r: r["total_ms"])
+    rest = [r for r in passes if r is not best][0]
+    total_ms, routed, applied, launches_all, ck = best["total_ms"], best["routed"], best["applied"], best["launches_all"], best["clocks"]
+    chosen, other, other_ms = best["mode"], rest["mode"], rest["total_ms"]
     value = world * K / (total_ms * 1e-3)
-    routed, applied, launches_all = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - applied0, launches])
     assert routed > 0, "no frame crossed a tile seam: the sharded path was not exercised"
 
     # ---- limiter breakdown on this rank: the pieces of a step, each alone ----
@@ -965,9 +974,9 @@ def multi_gpu(ctx) -> dict:
             "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching on its own (ordinary) stream, same policy as N=1",
             "blend": "alpha", "interp": "linear", "canvas": [BIG_GRID[0] * CANVAS, BIG_GRID[1] * CANVAS], "tile": [CANVAS, CANVAS], "frame": [fw, fh],
             "tile_updates_total": int(applied), "frame_bytes_routed_total": int(routed), "frame_bytes_routed_per_step": routed / K,
-            "transport": (args.transport + (": no frame copies -- the owner of the neighbouring tile composites straight out of the ingest GPU's memory (cudaIpc mapping, the "
-                                            "kernel's 2-D TMA source boxes cross NVLink); routed bytes are counted as whole frames (upper bound)" if args.transport == "peer"
-                                            else ": ncclSend/Recv of the whole frame, posted one step ahead")),
+            "transport": (chosen + (": no frame copies -- the owner of the neighbouring tile composites straight out of the ingest GPU's memory (cudaIpc mapping, the "
+                                    "kernel's 2-D TMA source boxes cross NVLink); routed bytes are counted as whole frames (upper bound)" if chosen == "peer"
+                                    else ": ncclSend/Recv of the whole frame, posted one step ahead") + "; the faster of the two transports, both timed the same way"),
         },
         "other_transport": {"mode": other, "value": world * K / (other_ms * 1e-3), "ms_per_step": other_ms / K},
         "gpu_launches": int(launches_all), "clocks": ck,
@@ -1305,7 +1314,8 @@ def main():
                     help="N=1 only: ALSO time the step with matching in its own group of at least this many SMs (green contexts), reported "
                          "under sm_partition_variant; the headline always uses two ordinary streams; 0 = skip the variant")
     ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: how a frame reaches the other ranks whose tiles its footprint overlaps (the other one is timed too, as other_transport)")
+                    help="N > 1: how a frame reaches the other ranks whose tiles its footprint overlaps; both are timed the same way, the faster one is the headline, "
+                         "this flag only decides which one runs last")
     ap.add_argument("--no-feather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)

@@ -14,6 +14,7 @@ Two things the reference does not have, both optional:
 from __future__ import annotations
 
 import warnings
+from itertools import repeat
 from typing import Sequence
 
 import numpy as np
@@ -510,6 +511,14 @@ class Matcher:
         if len(query) == 0:
             return ()
         idx, dist, _ = self.knn_match_arrays(query, train, ratio=0.0)
+        if idx.shape[1] == 2 and idx.min() >= 0:
+            # every row has its two neighbours (Nt >= 2, the hot path): build the 2 * Nq objects with C-level loops
+            # (map over columns, zip into pairs) -- a third cheaper than nested generator expressions; what is left is
+            # cv2.DMatch's own constructor
+            q = range(idx.shape[0])
+            m0 = map(DMatch, q, idx[:, 0].tolist(), repeat(0), dist[:, 0].tolist())
+            m1 = map(DMatch, q, idx[:, 1].tolist(), repeat(0), dist[:, 1].tolist())
+            return tuple(zip(m0, m1))
         il, dl = idx.tolist(), dist.tolist()      # plain Python numbers: far cheaper than numpy scalar indexing
         return tuple(tuple(DMatch(i, j, 0, d) for j, d in zip(ir, dr) if j >= 0) for i, (ir, dr) in enumerate(zip(il, dl)))
 
