@@ -148,11 +148,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self, t0: float, t1: float) -> dict:
+    def wait_first(self, busy=None, limit_s: float = 4.0) -> None:
+        """Block until nvidia-smi has printed its first sample (up to a second when eight ranks start it at once); `busy()` is
+        called in the meantime (untimed steps of the same workload), so the GPU is under the bench's load when the timed region
+        starts and the sample just before it is a sample under load."""
+        if self.proc is None:
+            return
+        deadline = time.perf_counter() + limit_s
+        while time.perf_counter() < deadline and not self.rows:
+            busy() if busy is not None else time.sleep(0.02)
+
+    def stop(self, t0: float, t1: float, busy=None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        # the timed region (K steps of ~40 us plus the flushes) is shorter than one sampling period: keep the same load running
+        # (`busy`, untimed) until a sample taken after the region has arrived, then use the samples inside the region or, if
+        # there are none, the ones on either side of it
+        deadline = time.perf_counter() + 1.5
+        while time.perf_counter() < deadline and not any(t >= t1 for t, _ in self.rows):
+            busy() if busy is not None else time.sleep(0.02)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        allrows = list(self.rows)
+        rows = [r for t, r in allrows if t0 <= t <= t1]
+        if not rows:
+            before = [r for t, r in allrows if t < t0][-1:]
+            after = [r for t, r in allrows if t > t1][:2]
+            rows = before + after
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -367,7 +388,12 @@ def single_gpu(ctx) -> dict:
         torch.cuda.synchronize()
         clocks = ClockSampler(local)
         clocks.start()
-        time.sleep(0.25)
+
+        def busy():                          # untimed steps of the same workload while the clock sampler catches up
+            for k in range(W):
+                one_step(k, mp)
+            torch.cuda.synchronize()
+        clocks.wait_first(busy)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
         n0 = mb.launch_count()
         torch.cuda.synchronize()
@@ -378,7 +404,7 @@ def single_gpu(ctx) -> dict:
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         launches = mb.launch_count() - n0
-        ck = clocks.stop(t0, t1)
+        ck = clocks.stop(t0, t1, busy)
         step_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
         match_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])      # both measured from the common start: they overlap
         blend_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
@@ -469,7 +495,7 @@ def single_gpu(ctx) -> dict:
 
 
 def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, dbytes=32) -> dict:
-    """End to end through the reference-facing API with HOST buffers (page-locked ndarrays): Matcher.knn_match_arrays_async +
+    """End to end through the reference-facing API with HOST buffers (page-locked ndarrays): Matcher.match_next_async (or knn_match_arrays_async) +
     Mapper.update, software-pipelined by one frame; and the blocking form."""
     torch, mb, dev, args = ctx["torch"], ctx["mb"], ctx["dev"], ctx["args"]
     K, W = args.steps, args.warmup
@@ -496,14 +522,30 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
         mapper.update(img, Hs[k % len(Hs)])
         return int(matcher.knn_match_arrays(q, t, RATIO)[2].sum())
 
-    def loop(k0, n):
-        """Same calls, software-pipelined by one frame: queue frame k's matching, hand frame k to the mapper, then collect
-        frame k-1's matches -- every result is still read on the host inside the timed region."""
+    def loop_two_sets(k0, n):
+        """Software-pipelined by one frame: queue frame k's matching (BOTH descriptor sets uploaded by the call), hand frame k to
+        the mapper, then collect frame k-1's matches -- every result is still read on the host inside the timed region."""
         kept, pending = 0, None
         for k in range(k0, k0 + n):
             img, q, t = inputs(k)
-            nxt = matcher.knn_match_arrays_async(q, t, RATIO)
             amapper.update(img, Hs[k % len(Hs)])
+            nxt = matcher.knn_match_arrays_async(q, t, RATIO)
+            if pending is not None:
+                kept += int(pending.result()[2].sum())
+            pending = nxt
+        return kept + int(pending.result()[2].sum())
+
+    def loop(k0, n):
+        """The same pipeline the way SequentialMosaic.match_features walks a video (knn_match(descriptors, descriptors_prev),
+        mosaic.py:402-438): Matcher.match_next_async keeps the previous frame's descriptors on the device, so every step uploads
+        ITS frame and ITS descriptor set (the sequence's first set goes up before the first step, inside the timed region)."""
+        matcher.reset_sequence()
+        matcher.match_next_async(inputs(k0)[2], RATIO)
+        kept, pending = 0, None
+        for k in range(k0, k0 + n):
+            img, q, _ = inputs(k)
+            amapper.update(img, Hs[k % len(Hs)])      # frame first: its 6 MB copy is what the host link must never wait for
+            nxt = matcher.match_next_async(q, RATIO)  # (queueing the descriptors first costs 25 us per frame, tools/e2e_gap_probe.py)
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
@@ -537,10 +579,12 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
         prev = cur_s
     passes = [timed(lambda: loop(W, K)) for _ in range(5)]     # five passes of K frames, the median counts
     e2e_s = float(np.median(passes))
+    assert loop(W, K) == loop_two_sets(W, K), "match_next and the two-set call disagree"
+    two_s = float(np.median([timed(lambda: loop_two_sets(W, K)) for _ in range(5)]))
     for k in range(W):
         sync_step(k)
     sync_s = float(np.median([timed(lambda: [sync_step(W + k) for k in range(K)]) for _ in range(3)]))
-    h2d = fh * fw * 3 + 2 * ndesc * dbytes
+    h2d = fh * fw * 3 + ndesc * dbytes + (ndesc * dbytes + K - 1) // K     # frame + its descriptor set (+ the sequence's first set, spread over K)
     d2h = ndesc * (2 * 4 + 2 * 4 + 1)
     for _ in range(3):
         wd.copy_(pin_frames[0], non_blocking=True)
@@ -556,12 +600,13 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
     dres = torch.empty(d2h, dtype=torch.uint8, device=dev)
     hres = torch.from_numpy(mb.pinned_empty((d2h,)))
     dfr = [torch.empty((fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
-    s_a, s_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_a, s_b, s_c = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
     def pattern(n):
         for k in range(n):
             with torch.cuda.stream(s_b):
-                dq[0].copy_(pin_desc[k % len(pin_desc)], non_blocking=True); dq[1].copy_(pin_desc[(k + 1) % len(pin_desc)], non_blocking=True)
+                dq[k & 1].copy_(pin_desc[k % len(pin_desc)], non_blocking=True)
+            with torch.cuda.stream(s_c):
                 hres.copy_(dres, non_blocking=True)
             with torch.cuda.stream(s_a):
                 dfr[k % 3].copy_(pin_frames[k % len(pin_frames)], non_blocking=True)
@@ -570,11 +615,15 @@ def e2e_single(ctx, matcher, mapper, frames, Hs, desc_h, fw, fh, ndesc=NDESC, db
     amapper.release()
     return {"value": K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "copies_only_frames_per_s": 1.0 / floor_s,
-            "note": ("host ndarray in pinned memory -> Matcher.knn_match_arrays_async + Mapper.update, matches of frame k-1 read on the host "
+            "note": ("host ndarray in pinned memory -> Matcher.match_next_async (query = this frame's descriptors, train = the previous frame's, "
+                     "still on the device: mosaic.py:402-438 as a stream) + Mapper.update, matches of frame k-1 read on the host "
                      "while frame k is in flight; wall clock incl. Python, median of 5 passes of K frames; untimed frames first until the PCIe path is warm"),
+            "two_set_value": K / two_s,
+            "two_set_note": "same loop through Matcher.knn_match_arrays_async(query, train): both descriptor sets uploaded every step "
+                            f"({fh * fw * 3 + 2 * ndesc * dbytes} bytes per step)",
             "host_link": {"h2d_gbs_achieved": (K / e2e_s) * h2d / 1e9, "h2d_gbs_plain_copy": link_gbs,
                           "note": "plain_copy = back-to-back frame-sized cudaMemcpyAsync from page-locked memory on this box; "
-                                  "copies_only_frames_per_s = this step's four copies (frame, two descriptor sets, packed result) with no kernels: the ceiling of e2e"},
+                                  "copies_only_frames_per_s = this step's three copies (frame, its descriptor set, packed result; each on its own stream) with no kernels: the ceiling of e2e"},
             "passes_frames_per_s": [round(K / t) for t in passes],
             "link_warmup_gbs": [round(x, 1) for x in link_windows],
             "sync_value": K / sync_s,
@@ -905,7 +954,12 @@ def multi_gpu(ctx) -> dict:
         barrier()
         clocks = ClockSampler(local)
         clocks.start()
-        time.sleep(0.25)
+
+        def busy():                          # rank-local load (no collective: the ranks' samplers do not tick together)
+            for _ in range(8):
+                matcher.knn_match_device(desc_d[1], desc_d[0], RATIO)
+            torch.cuda.synchronize()
+        clocks.wait_first(busy)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
         n0 = mb.launch_count()
         sent0, applied0 = mosaic.bytes_sent, mosaic.frames_applied
@@ -917,7 +971,7 @@ def multi_gpu(ctx) -> dict:
         barrier()
         t1 = time.perf_counter()
         launches = mb.launch_count() - n0
-        ck = clocks.stop(t0, t1)
+        ck = clocks.stop(t0, t1, busy)
         step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
         total_ms = max_over_ranks(float(step_ms.sum()))
         routed, applied, launches_all = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - applied0, launches])
@@ -996,7 +1050,7 @@ def multi_gpu(ctx) -> dict:
 
 
 def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
-    """End to end with HOST buffers on every rank at once: page-locked frame + descriptors -> knn_match_arrays_async + the sharded
+    """End to end with HOST buffers on every rank at once: page-locked frame + descriptors -> match_next_async + the sharded
     step (H2D of the frame, routing, compositing), matches read back on the host.  Also what the host link gives every GPU when
     all N copy at the same time (plain frame-sized copies), which is the ceiling of this number."""
     torch, dist, mb, dev, args = ctx["torch"], ctx["dist"], ctx["mb"], ctx["dev"], ctx["args"]
@@ -1029,9 +1083,10 @@ def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
 
     def loop(k0, n):
         kept, pending = 0, None
+        matcher.reset_sequence()
+        matcher.match_next_async(pin_desc[k0 % 8].numpy(), RATIO)      # first set of the sequence (mosaic.py:402-438 as a stream)
         for k in range(k0, k0 + n):
-            q, t = pin_desc[(k + 1) % 8].numpy(), pin_desc[k % 8].numpy()
-            nxt = matcher.knn_match_arrays_async(q, t, RATIO)
+            q = pin_desc[(k + 1) % 8].numpy()
             sl = k % 3
             d = dev_ring[sl]
             with torch.cuda.stream(copy_stream):                       # H2D of frame k on a side stream: it overlaps the step of frame k-1
@@ -1041,6 +1096,7 @@ def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
             main.wait_event(slot_full[sl])
             mosaic.step_planned(k % nfr, d)
             slot_free[sl].record(main)
+            nxt = matcher.match_next_async(q, RATIO)     # after the frame: the host link must never wait for the 6 MB copy
             if pending is not None:
                 kept += int(pending.result()[2].sum())
             pending = nxt
@@ -1066,12 +1122,12 @@ def e2e_multi(ctx, barrier, max_over_ranks, fw, fh) -> dict:
         timed(lambda: loop(0, min(32, nfr)))
     passes = [timed(lambda: loop(W, K)) for _ in range(5)]
     s = float(np.median(passes))
-    h2d = fh * fw * 3 + 2 * NDESC * 32
+    h2d = fh * fw * 3 + NDESC * 32 + (NDESC * 32 + K - 1) // K
     res = {"value": world * K / s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": NDESC * 17,
            "host_link": {"h2d_gbs_achieved_per_gpu": (K / s) * h2d / 1e9, "h2d_gbs_plain_copy_concurrent_per_gpu": link_gbs,
                          "note": f"plain copy = all {world} ranks streaming page-locked frames at the same time; it is the ceiling of the per-GPU e2e rate"},
            "passes_frames_per_s": [round(world * K / t) for t in passes],
-           "note": "every rank: page-locked host frame + descriptors -> knn_match_arrays_async + sharded step, matches read on the host; wall clock, max over ranks"}
+           "note": "every rank: page-locked host frame -> sharded step, its descriptors -> Matcher.match_next_async (train = the previous frame's set, still on the device), matches read on the host; wall clock, max over ranks"}
     mosaic.mappers.clear()
     torch.cuda.empty_cache()
     return res

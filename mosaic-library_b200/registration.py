@@ -351,6 +351,28 @@ class Matcher:
             raise TypeError("knn_match_arrays_async takes host ndarrays")
         return self._knn_host_submit(query, train, ratio)
 
+    def match_next_async(self, desc: np.ndarray, ratio: float = 0.7) -> "PendingMatch":
+        """Sequential matching the way SequentialMosaic.match_features walks a video (mosaic.py:402-438:
+        knn_match(descriptors, descriptors_prev) for consecutive frames): match `desc` (query) against the set passed to the
+        PREVIOUS match_next call (train), which is still in device memory -- every descriptor set crosses the host link once
+        instead of twice.  Same results as knn_match_arrays_async(desc, previous_desc, ratio).  The first call of a sequence has
+        nothing to match against: its handle resolves to idx = -1, dist = FLT_MAX, keep = False (what an empty train set gives).
+        `desc` must stay alive and unmodified until the handle's result() (or the next call's) has returned.
+        reset_sequence() starts a new sequence; any knn_match_arrays* call in between does so too."""
+        if not isinstance(desc, np.ndarray):
+            raise TypeError("match_next_async takes a host ndarray")
+        return self._knn_host_submit(desc, None, ratio, seq=True)
+
+    def match_next(self, desc: np.ndarray, ratio: float = 0.7):
+        """Blocking form of match_next_async -> (idx, dist, keep)."""
+        return self.match_next_async(desc, ratio).result()
+
+    def reset_sequence(self) -> None:
+        """Forget the descriptor set kept on the device by match_next: the next match_next call starts a new sequence."""
+        hp = self._matcher.get("host_plan")
+        if hp is not None:
+            hp["seq"] = None
+
     def _host_plan(self, device, dtype, dim: int, nq: int, nt: int) -> dict:
         """Everything the host path reuses call after call: private stream, device row buffers (rows padded to 16 bytes,
         padding zero), packed output buffer, the ring of page-locked result buffers.  Rebuilt only when the descriptor
@@ -372,37 +394,61 @@ class Matcher:
         cap = max(nq, nt, 1)
         cap = 1 << (cap - 1).bit_length()
         total_cap = (cap * 17 + 3 & ~3) + 4
+        dstream = self._matcher.get("dstream")
+        if dstream is None or dstream.device != device:
+            dstream = torch.cuda.Stream(device=device)
+            self._matcher["dstream"] = dstream
         with torch.cuda.stream(stream):          # allocations and fills happen on the private stream
-            qd = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
-            td = torch.zeros(cap * stride, dtype=torch.uint8, device=device)
-            out = torch.empty(total_cap, dtype=torch.uint8, device=device)
-        ring = [{"host": torch.from_numpy(pinned_empty((total_cap,))), "event": torch.cuda.Event(), "owner": None}
-                for _ in range(PendingMatch.DEPTH)]
+            bufs = [torch.zeros(cap * stride, dtype=torch.uint8, device=device) for _ in range(2)]
+            outs = [torch.empty(total_cap, dtype=torch.uint8, device=device) for _ in range(PendingMatch.DEPTH)]
+        # every slot: page-locked result buffer + its own device output buffer (the packed result leaves on the DOWNLOAD stream,
+        # so the next call's uploads and kernels never queue behind a device->host copy: 140 -> 130 us per frame of copy-engine
+        # time in the frame loop, tools/copy_mix_probe2.py)
+        ring = [{"host": torch.from_numpy(pinned_empty((total_cap,))), "event": torch.cuda.Event(), "kdone": torch.cuda.Event(),
+                 "out": outs[i], "out_ptr": outs[i].data_ptr(), "owner": None} for i in range(PendingMatch.DEPTH)]
         for slot in ring:
             slot["host_ptr"] = slot["host"].data_ptr()
-        hp = {"key": (device, dtype.char, dim), "cap": cap, "stream": stream, "sptr": stream.cuda_stream, "row": row, "stride": stride,
-              "q": qd, "t": td, "out": out, "q_ptr": qd.data_ptr(), "t_ptr": td.data_ptr(), "out_ptr": out.data_ptr(),
-              "ring": ring, "pos": 0, "code": _norm_code(self._norm, dtype, self._engine), "ws": {}, "device": device}
+        seq = None
+        if hp is not None and hp["seq"] is not None and hp["key"] == (device, dtype.char, dim):
+            # a set outgrew the buffers in the middle of a match_next sequence: the resident set moves into the new buffers
+            seq = hp["seq"]
+            with torch.cuda.stream(stream):
+                nb = seq[1] * stride
+                bufs[seq[0]][:nb].copy_(hp["bufs"][seq[0]][:nb])
+        hp = {"key": (device, dtype.char, dim), "cap": cap, "stream": stream, "sptr": stream.cuda_stream, "dstream": dstream,
+              "dsptr": dstream.cuda_stream, "row": row, "stride": stride, "bufs": bufs, "buf_ptr": [b.data_ptr() for b in bufs],
+              "seq": seq, "ring": ring, "pos": 0, "code": _norm_code(self._norm, dtype, self._engine), "ws": {}, "device": device}
         self._matcher["host_plan"] = hp
         return hp
 
-    def _knn_host_submit(self, q: np.ndarray, t: np.ndarray, ratio: float) -> "PendingMatch":
-        if q.dtype != t.dtype:
-            raise _bad_input("query and train descriptors must have the same type")
-        if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1]:
+    def _knn_host_submit(self, q: np.ndarray, t, ratio: float, seq: bool = False) -> "PendingMatch":
+        """t: the train descriptors (host), or with seq=True nothing: the train set is then the query set of the previous
+        seq call, which is still in device memory (match_next_async)."""
+        if q.ndim != 2 or (not seq and (t.ndim != 2 or q.shape[1] != t.shape[1])):
             raise _bad_input("query and train descriptors must have the same width")
+        if not seq and q.dtype != t.dtype:
+            raise _bad_input("query and train descriptors must have the same type")
         if q.dtype not in (np.uint8, np.float32):
             raise _bad_input(f"unsupported descriptor dtype {q.dtype} (cv2 accepts CV_8U and CV_32F)")
         if not q.flags.c_contiguous:
             q = np.ascontiguousarray(q)
-        if not t.flags.c_contiguous:
+        if not seq and not t.flags.c_contiguous:
             t = np.ascontiguousarray(t)          # both stay referenced by the handle until the copies are done
-        (nq, dim), nt = q.shape, t.shape[0]
-        if nq == 0:
+        nq, dim = q.shape
+        prev = None
+        if seq:
+            hp0 = self._matcher.get("host_plan")
+            prev = hp0["seq"] if hp0 is not None else None
+            if prev is not None and hp0["key"] != (_cuda_device(self._device), q.dtype.char, dim):
+                raise _bad_input("match_next: descriptor type or width changed inside a sequence; call reset_sequence() first")
+            nt = prev[1] if prev is not None else 0
+        else:
+            nt = t.shape[0]
+        if nq == 0 and not seq:
             return PendingMatch.done(np.empty((0, 2), np.int32), np.empty((0, 2), np.float32), np.empty((0,), bool))
         # host in, host out: nothing depends on the caller's stream, so the call runs on a private stream and
         # overlaps whatever the caller has in flight (e.g. Mapper's frame upload + fused kernel)
-        hp = self._host_plan(_cuda_device(self._device), q.dtype, dim, nq, nt)
+        hp = self._host_plan(_cuda_device(self._device), q.dtype, dim, max(nq, 1), nt)
         L, sptr, row, stride, code = self._matcher["lib"], hp["sptr"], hp["row"], hp["stride"], hp["code"]
         ws = hp["ws"].get((nq, nt))
         if ws is None:
@@ -423,15 +469,33 @@ class Matcher:
         slot = hp["ring"][k]
         if slot["owner"] is not None:
             slot["owner"]._resolve()             # an uncollected older call still points at this slot
-        base = hp["out_ptr"]
+        base = slot["out_ptr"]
+        if seq:      # the previous query set stays where it is and becomes the train set; the new set goes into the other buffer
+            qi = 1 - prev[0] if prev is not None else 0
+            q_ptr, t_ptr = hp["buf_ptr"][qi], hp["buf_ptr"][1 - qi]
+            hp["seq"] = (qi, nq)
+        else:
+            q_ptr, t_ptr = hp["buf_ptr"]
+            hp["seq"] = None
         with _current_device(hp["device"]):
-            _lib.check(L.mk_upload_2d(hp["q_ptr"], stride, q.__array_interface__["data"][0], row, row, nq, sptr))
-            if nt:
-                _lib.check(L.mk_upload_2d(hp["t_ptr"], stride, t.__array_interface__["data"][0], row, row, nt, sptr))
-            _lib.check(L.mk_knn2(code, hp["q_ptr"], nq, hp["t_ptr"] if nt else None, nt, dim, stride, base, base + nq * 8,
+            if nq:
+                _lib.check(L.mk_upload_2d(q_ptr, stride, q.__array_interface__["data"][0], row, row, nq, sptr))
+            if seq and (prev is None or nq == 0):
+                # first set of a sequence (nothing to match against yet) or an empty set: the upload is all there is to do
+                if nq:
+                    slot["event"].record(hp["stream"])
+                    slot["event"].synchronize()      # once per sequence: the caller may reuse `q` as soon as this returns
+                pending = PendingMatch.done(np.full((nq, 2), -1, np.int32), np.full((nq, 2), np.finfo(np.float32).max, np.float32),
+                                            np.zeros((nq,), bool))
+                return pending
+            if nt and not seq:
+                _lib.check(L.mk_upload_2d(t_ptr, stride, t.__array_interface__["data"][0], row, row, nt, sptr))
+            _lib.check(L.mk_knn2(code, q_ptr, nq, t_ptr if nt else None, nt, dim, stride, base, base + nq * 8,
                                  float(ratio), base + off_keep, base + off_n, ws[0], ws[1], sptr))
-            _lib.check(L.mk_download_2d(slot["host_ptr"], total, base, total, total, 1, sptr))
-        slot["event"].record(hp["stream"])
+            slot["kdone"].record(hp["stream"])
+            hp["dstream"].wait_event(slot["kdone"])
+            _lib.check(L.mk_download_2d(slot["host_ptr"], total, base, total, total, 1, hp["dsptr"]))
+        slot["event"].record(hp["dstream"])
         pending = PendingMatch(slot, nq, off_keep, (q, t))
         slot["owner"] = pending
         return pending

@@ -151,6 +151,37 @@ def test_knn_match_arrays_async_ring():
     assert e[0].shape == (0, 2) and e[2].shape == (0,)
 
 
+@pytest.mark.parametrize("norm,dtype,dim", [("hamming", np.uint8, 32), ("l2", np.float32, 128), ("l2", np.uint8, 61)])
+def test_match_next_sequence_equals_pairwise(norm, dtype, dim):
+    """Matcher.match_next (mosaic.py:402-438 walked as a stream: the previous frame's descriptors stay on the device and become
+    the train set) returns exactly what knn_match(descriptors, descriptors_prev) returns for every consecutive pair -- sets of
+    different sizes, an empty set in the middle, more calls in flight than the result ring holds, an interleaved two-set call
+    (which ends the sequence) and reset_sequence()."""
+    rng = np.random.default_rng(15)
+    sizes = [700, 3100, 1, 900, 0, 450, 2048, 2049, 300]
+    sets = [rng.integers(0, 256, (n, dim)).astype(dtype) for n in sizes]
+    m = mb.Matcher(norm=norm)
+    handles = [m.match_next_async(s, 0.7) for s in sets]
+    first = handles[0].result()
+    assert first[0].shape == (sizes[0], 2) and (first[0] == -1).all() and not first[2].any()
+    for k in range(len(sets) - 1, 0, -1):
+        idx, dist, keep = handles[k].result()
+        oi, od = orc.knn2(sets[k], sets[k - 1], norm)
+        assert idx.shape == (sizes[k], 2)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od) and np.array_equal(keep, orc.ratio_test(oi, od, 0.7)), k
+    # a two-set call in between ends the sequence; so does reset_sequence()
+    a = m.knn_match_arrays(sets[1], sets[3], 0.7)
+    oi, od = orc.knn2(sets[1], sets[3], norm)
+    assert np.array_equal(a[0], oi)
+    r = m.match_next(sets[5], 0.7)
+    assert (r[0] == -1).all()
+    r = m.match_next(sets[6], 0.7)
+    oi, od = orc.knn2(sets[6], sets[5], norm)
+    assert np.array_equal(r[0], oi) and np.array_equal(r[1], od)
+    m.reset_sequence()
+    assert (m.match_next(sets[3], 0.7)[0] == -1).all()
+
+
 def test_knn_match_device_async_own_stream():
     """The matcher's own-stream form: same tensors as the blocking device call, usable from the caller's stream after
     result(); several calls in flight, descriptors produced on the caller's stream right before the call."""
