@@ -46,6 +46,7 @@ constexpr int TC_TEAM_THREADS = TC_EPI_THREADS / TC_TEAMS;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;    // warps: 0 TMA, 1 MMA, 2.. epilogue
 constexpr int TC_MAX_KP = 128;     // padded K supported (SIFT 128)
 constexpr int TC_TABS = 4;         // ring of per-tile column tables (written two tiles ahead by the epilogue threads)
+constexpr int TC_MAX_CLUSTER = 8;  // train splits merged inside one thread-block cluster (portable cluster size); more splits merge through global memory
 
 struct TcParams {
     const void *qb, *tb;            // operand copies: bf16 [n][kp] (L2) or fp8-e4m3 0/1 bytes [n][kp] (Hamming on bit-expanded rows)
@@ -56,6 +57,7 @@ struct TcParams {
     int hamming;                    // 1: scores are Hamming counts (distance = count), 0: squared L2 (distance = sqrtf)
     const int32_t *set_off, *pairs, *out_off;   // batched tables (device) or null: rows of qb == rows of tb == all sets
     int splits, nqb;
+    int cluster_merge;              // 1: the CTAs of one query block (blockIdx.y = split) form a thread-block cluster and merge through rank 0's shared memory
     unsigned long long *part;
     int *tickets;
     int32_t *idx;
@@ -286,7 +288,8 @@ struct TcSmem {
     static __host__ __device__ constexpr int tn_off(int slot) { return 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + slot * TC_N * 4; }   // TC_TABS slots
     static constexpr int keys_off = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES + TC_TABS * TC_N * 4;      // [TC_GROUPS][128][2] u64
     static constexpr int bar_off = keys_off + TC_GROUPS * TC_M * 2 * 8;
-    static constexpr int total = bar_off + 256;
+    static constexpr int part_off = bar_off + 256;              // [TC_MAX_CLUSTER - 1][128][2] u64: best two of the other splits of the cluster (written remotely)
+    static constexpr int total = part_off + (TC_MAX_CLUSTER - 1) * TC_M * 2 * 8;
 };
 
 template <int KIND>
@@ -527,7 +530,28 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
         }
     }
-    if (p.splits > 1) {
+    if (p.splits > 1 && p.cluster_merge) {
+        // The splits of this query block are the CTAs of one cluster (cluster dims (1, splits, 1): rank == split).  Everybody but
+        // rank 0 stores its best two per row straight into rank 0's shared memory (st.shared::cluster over the SM-to-SM network),
+        // one cluster barrier publishes them, rank 0 merges and writes the outputs: no global-memory round trip, no fence, no
+        // ticket (the global path below costs store -> __threadfence -> atomic -> load, about 2 us on the critical path).
+        if (split != 0 && is_row_thread) {
+            const uint32_t local = smem_addr(smem + TcSmem::part_off + ((split - 1) * TC_M + tid) * 16);
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local), "r"(0));
+            asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};\n" ::"r"(remote), "l"(k1), "l"(k2) : "memory");
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (split != 0) return;
+        if (is_row_thread) {
+            const unsigned long long *o = reinterpret_cast<const unsigned long long *>(smem + TcSmem::part_off) + tid * 2;
+            for (int s = 1; s < p.splits; ++s, o += TC_M * 2) {
+                const unsigned long long a = o[0], b = o[1];
+                if (a != TcKey::NONE) { const unsigned long long mx = a > k1 ? a : k1; k1 = a < k1 ? a : k1; k2 = mx < k2 ? mx : k2; }
+                if (b != TcKey::NONE) { const unsigned long long mx = b > k1 ? b : k1; k1 = b < k1 ? b : k1; k2 = mx < k2 ? mx : k2; }
+            }
+        }
+    } else if (p.splits > 1) {
         const size_t blk = (size_t)z * p.nqb + qblk;
         unsigned long long *base = p.part + (blk * p.splits) * TC_M * 2;
         if (is_row_thread) {
@@ -791,6 +815,8 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     P.nq = nq; P.nt = nt; P.kp = pl.kp; P.dim = dim;
     P.row_bytes = pl.kp * pl.esz; P.atom_elems = 128 / pl.esz; P.hamming = norm == MK_NORM_HAMMING_TC;
     P.splits = pl.splits; P.nqb = pl.nqb;
+    static const bool no_cluster = getenv("MK_NO_CLUSTER_MERGE") != nullptr;   // diagnosis / A-B switch: merge the splits through global memory
+    P.cluster_merge = (pl.splits > 1 && pl.splits <= TC_MAX_CLUSTER && !no_cluster) ? 1 : 0;
     P.set_off = set_off; P.pairs = pairs; P.out_off = out_off;
     P.part = reinterpret_cast<unsigned long long *>(ws + pl.off_part); P.tickets = tickets;
     P.idx = idx; P.dist = dist; P.keep = keep; P.n_keep = cnt ? cnt : n_keep; P.ratio = ratio;
@@ -807,11 +833,20 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     // programmatic dependent launch: the GEMM kernel's prologue (barriers, TMEM allocation) runs under the prep kernel
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     static const bool no_pdl = getenv("MK_NO_PDL") != nullptr;   // diagnosis switch: plain stream-ordered launch
-    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (!no_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (P.cluster_merge) {                   // the splits of a query block = one cluster (see the merge in the kernel)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)pl.splits; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     if (P.hamming) MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P));
     else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P));
     MK_LAUNCH_CHECK("knn2_tc_kernel");
