@@ -44,13 +44,14 @@ bool invert3x3(const double *S, double *D);
 int stream_sm_count(cudaStream_t stream);
 
 // Tensor-core kNN flags, written on the DEVICE (prep pass + TC kernel) and read by the guarded SIMT fallback:
-//   flags[0] != 0  some value is not an integer in [0,255]: bf16 operands would round it, the TC kernel does nothing;
+//   flags[0] == flags[1]  some value is not an integer in [0,255]: bf16 operands would round it, the TC kernel does nothing
+//                  (flags[1] = this call's epoch, flags[0] is set to it by the prep pass: nothing to zero before the call);
 //   flags[3] != 0  some row's best-two squared distance reached 2^22: the TC path ranks by the integer d^2, which equals
 //                  cv2's ranking by sqrtf((float)d^2) only while sqrtf is injective (d^2 < 2^22), so the whole call is
 //                  recomputed by the bit-exact SIMT kernel.  (Never happens for uint8 rows <= 64 bytes or SIFT.)
 #ifdef __CUDACC__
-__device__ __forceinline__ bool knn_tc_inputs_ok(const int *flags) { return flags[0] == 0; }
-__device__ __forceinline__ bool knn_tc_result_ok(const int *flags) { return flags[0] == 0 && flags[3] == 0; }
+__device__ __forceinline__ bool knn_tc_inputs_ok(const int *flags) { return flags[0] != flags[1]; }
+__device__ __forceinline__ bool knn_tc_result_ok(const int *flags) { return flags[0] != flags[1] && flags[3] == 0; }
 #endif
 
 }  // namespace mk

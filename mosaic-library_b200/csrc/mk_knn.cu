@@ -63,7 +63,7 @@ bool knn_tc_supported(int norm, int nq, int nt, int dim);
 int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
                const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out,
-               const int32_t **tc_count_out);
+               const int32_t **tc_count_out, int *simt_tickets, size_t simt_ticket_bytes);
 
 struct Problem {
     const uint8_t *q, *t;
@@ -465,7 +465,7 @@ static void launch_reg(dim3 grid, cudaStream_t st, const KnnParams &P)
 }
 
 static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, void *workspace, size_t workspace_bytes,
-                   cudaStream_t st, bool zero_n_keep = true)
+                   cudaStream_t st, bool zero_n_keep = true, bool tickets_zeroed = false)
 {
     const KnnPlan pl = make_plan(norm, npairs, max_nq, max_nt);
     if (workspace_bytes < pl.ticket_bytes + pl.part_bytes || !workspace) { set_error("mk_knn2: workspace too small (%zu < %zu)", workspace_bytes, pl.ticket_bytes + pl.part_bytes); return MK_ERR_WORKSPACE; }
@@ -476,7 +476,7 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
     P.splits = pl.splits; P.nqb = pl.nqb;
     if (P.n_keep && zero_n_keep) MK_CUDA_TRY(cudaMemsetAsync(P.n_keep, 0, sizeof(int32_t) * npairs, st));
     if (pl.nqb == 0 || npairs == 0) return MK_OK;
-    if (pl.splits > 1) MK_CUDA_TRY(cudaMemsetAsync(P.tickets, 0, pl.ticket_bytes, st));
+    if (pl.splits > 1 && !tickets_zeroed) MK_CUDA_TRY(cudaMemsetAsync(P.tickets, 0, pl.ticket_bytes, st));
     dim3 grid(pl.nqb, pl.splits, npairs);
     if (norm == MK_NORM_L2_F32) {
         const size_t smem = (size_t)2 * FT * P.dim * sizeof(float);
@@ -570,12 +570,15 @@ extern "C" int mk_knn2(int norm, const void *q, int nq, const void *t, int nt, i
         if (workspace_bytes < simt_bytes || !workspace) { set_error("mk_knn2: workspace too small"); return MK_ERR_WORKSPACE; }
         const int *flags = nullptr;
         const int32_t *tc_count = nullptr;
+        // the guarded SIMT pass needs zeroed tickets at the front of the workspace: the TC prep kernel zeroes them (no memset node)
+        const bool guarded = !(norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64));
         rc = knn_tc_run(norm, q, nq, t, nt, dim, row_stride, nullptr, nullptr, 1, nullptr, 0, idx, dist, ratio, keep, n_keep,
-                        static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags, &tc_count);
+                        static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes, (cudaStream_t)stream, &flags, &tc_count,
+                        static_cast<int *>(workspace), guarded && pl.splits > 1 ? pl.ticket_bytes : 0);
         // uint8 rows: dim*255^2 < 2^22, bit counts <= 256: the TC result always stands
         if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
         P.guard = flags; P.tc_count = tc_count;
-        return run_knn(bn, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+        return run_knn(bn, P, 1, nq, nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false, /*tickets_zeroed=*/true);
     }
     return run_knn(bn, P, 1, nq, nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -607,10 +610,11 @@ extern "C" int mk_knn2_batched(int norm, const void *desc, int total_rows, int d
         const int32_t *tc_count = nullptr;
         rc = knn_tc_run(norm, desc, max_nq, nullptr, max_nt, dim, row_stride, set_off, pairs, npairs, out_off, total_rows, idx, dist,
                         ratio, keep, n_keep, static_cast<uint8_t *>(workspace) + simt_bytes, workspace_bytes - simt_bytes,
-                        (cudaStream_t)stream, &flags, &tc_count);
+                        (cudaStream_t)stream, &flags, &tc_count, static_cast<int *>(workspace),
+                        !(norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) && pl.splits > 1 ? pl.ticket_bytes : 0);
         if (rc != MK_OK || norm == MK_NORM_HAMMING_TC || (norm == MK_NORM_L2_U8 && dim <= 64)) return rc;
         P.guard = flags; P.tc_count = tc_count;
-        return run_knn(bn, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false);
+        return run_knn(bn, P, npairs, max_nq, max_nt, workspace, simt_bytes, (cudaStream_t)stream, /*zero_n_keep=*/false, /*tickets_zeroed=*/true);
     }
     return run_knn(bn, P, npairs, max_nq, max_nt, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -604,12 +604,21 @@ template <typename T>
 __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ q, int nq, const T *__restrict__ t, int nt,
                                                           size_t stride_bytes, int dim, int kp, __nv_bfloat16 *__restrict__ qb,
                                                           __nv_bfloat16 *__restrict__ tb, float *__restrict__ qn,
-                                                          float *__restrict__ tn, int *flags, int32_t *n_keep)
+                                                          float *__restrict__ tn, int *flags, int32_t *n_keep, int epoch, int nzero,
+                                                          int *zero2, int nzero2)
 {
     asm volatile("griddepcontrol.launch_dependents;\n");     // the GEMM kernel may start its prologue now (it waits before reading)
-    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = gid >> 5;
     const int lane = threadIdx.x & 31;
     if (row == 0 && lane == 0 && n_keep) *n_keep = 0;
+    // No memset node in front of this kernel: flags[0] is only ever SET to this call's epoch (below, by whoever finds a bad value),
+    // flags[1] = the epoch, so "inputs not exact" reads flags[0] == flags[1] (mk_common.cuh) and nothing has to be zeroed before
+    // it can be set; flags[2..] (flags[3] is raised by the TC kernel), the TC tickets / counters behind them and the SIMT
+    // fallback's tickets are zeroed here, grid-wide.
+    if (gid == 0) flags[1] = epoch;
+    for (int i = 2 + gid; i < nzero; i += gridDim.x * blockDim.x) flags[i] = 0;
+    for (int i = gid; i < nzero2; i += gridDim.x * blockDim.x) zero2[i] = 0;
     if (row >= nq + nt) return;
     const bool is_q = row < nq;
     if (!is_q) row -= nq;
@@ -626,7 +635,7 @@ __global__ void __launch_bounds__(256) knn_tc_prep_kernel(const T *__restrict__ 
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) (is_q ? qn : tn)[row] = acc;
-    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(flags, epoch);
 }
 
 // ---- prep for Hamming: bits -> e4m3 bytes (1.0 = 0x38 / 0), popcounts as "norms" -----------------------------------------
@@ -646,7 +655,8 @@ __global__ void __launch_bounds__(256) knn_tc_prep_bits_kernel(const uint8_t *__
     int row = gid / tpr;
     const int part = gid % tpr;
     if (gid == 0 && n_keep) *n_keep = 0;
-    for (int i = gid; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;   // flags + tickets of the TC kernel (no memset node)
+    if (gid == 0) { zero[0] = 0; zero[1] = 1; }              // flags[0] != flags[1]: bit rows are always exact (mk_common.cuh)
+    for (int i = 2 + gid; i < nzero; i += gridDim.x * blockDim.x) zero[i] = 0;   // flags + tickets of the TC kernel (no memset node)
     const bool live = row < nq + nt;
     const bool is_q = row < nq;
     if (!is_q) row -= nq;
@@ -770,7 +780,7 @@ bool knn_tc_supported(int norm, int nq, int nt, int dim)
 int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, size_t stride, const int32_t *set_off,
                const int32_t *pairs, int npairs, const int32_t *out_off, int total_rows, int32_t *idx, float *dist, double ratio,
                uint8_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, cudaStream_t st, const int **flags_out,
-               const int32_t **tc_count_out)
+               const int32_t **tc_count_out, int *simt_tickets, size_t simt_ticket_bytes)
 {
     const bool batched = pairs != nullptr;
     const int sms = stream_sm_count(st);     // splits (hence the partial-result scratch) never exceed what 148 SMs ask for
@@ -788,7 +798,10 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
     // float rows may be recomputed by the guarded SIMT kernel: the TC kernel then counts survivors into `cnt`, not n_keep
     int32_t *cnt = (norm == MK_NORM_L2_F32 && n_keep) ? reinterpret_cast<int32_t *>(ws + pl.off_cnt) : nullptr;
     const size_t zero_bytes = cnt ? (pl.off_cnt - pl.off_flags) + (size_t)np * 4 : (size_t)((uint8_t *)tickets - (uint8_t *)flags) + (size_t)np * pl.nqb * 4;
-    if (norm != MK_NORM_HAMMING_TC) MK_CUDA_TRY(cudaMemsetAsync(flags, 0, zero_bytes, st));
+    static std::atomic<int> epoch_counter{0};
+    int epoch = epoch_counter.fetch_add(1) + 1;
+    if (epoch == 0) epoch = epoch_counter.fetch_add(1) + 1;
+    const int nzero2 = (int)(simt_ticket_bytes / 4);
     if (n_keep && batched) MK_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * np, st));
     const int rows_q = batched ? total_rows : nq, rows_t = batched ? 0 : nt;
     const int wpb = 8, rows = rows_q + rows_t;
@@ -800,10 +813,12 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
                                                                         batched ? nullptr : n_keep, flags, (int)(zero_bytes / 4));
     else if (norm == MK_NORM_L2_F32)
         knn_tc_prep_kernel<float><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const float *>(q), rows_q, static_cast<const float *>(t), rows_t,
-                                                                          stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep);
+                                                                          stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep,
+                                                                          epoch, (int)(zero_bytes / 4), simt_tickets, nzero2);
     else
         knn_tc_prep_kernel<uint8_t><<<(rows + wpb - 1) / wpb, 256, 0, st>>>(static_cast<const uint8_t *>(q), rows_q, static_cast<const uint8_t *>(t), rows_t,
-                                                                            stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep);
+                                                                            stride, dim, pl.kp, static_cast<__nv_bfloat16 *>(qb), static_cast<__nv_bfloat16 *>(tb), qn, tn, flags, batched ? nullptr : n_keep,
+                                                                            epoch, (int)(zero_bytes / 4), simt_tickets, nzero2);
     MK_LAUNCH_CHECK("knn_tc_prep_kernel");
     alignas(64) CUtensorMap map_q, map_t;
     int rc = make_map(&map_q, qb, rows_q, pl.kp, TC_M, pl.esz);
