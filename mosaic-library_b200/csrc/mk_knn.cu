@@ -51,7 +51,11 @@ struct KnnParams {
 // is over; otherwise n_keep is still zero and this pass counts the survivors of the recomputed call itself.
 __device__ __forceinline__ bool knn_guard_skip(const KnnParams &p)
 {
-    if (!p.guard || !knn_tc_result_ok(p.guard)) return false;
+    if (!p.guard) return false;
+    // guarded passes are launched with programmatic stream serialization: their CTAs may be resident before the tensor-core
+    // kernel has finished, and may read its verdict only after this wait (a no-op under a plain launch)
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (!knn_tc_result_ok(p.guard)) return false;
     if (p.tc_count && p.n_keep && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.n_keep[blockIdx.z] = p.tc_count[blockIdx.z];
     return true;
 }
@@ -489,7 +493,17 @@ static int run_knn(int norm, KnnParams &P, int npairs, int max_nq, int max_nt, v
                 configured.store(dev, std::memory_order_release);
             }
         }
-        knn2_f32_kernel<<<grid, KNN_THREADS, smem, st>>>(P);
+        if (P.guard) {       // guarded pass behind the tensor-core kernel: launch latency hidden under that kernel's tail
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(KNN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_f32_kernel, P));
+        } else {
+            knn2_f32_kernel<<<grid, KNN_THREADS, smem, st>>>(P);
+        }
     } else {
         const int nv = (P.dim + 15) / 16;
         if (norm == MK_NORM_HAMMING) {

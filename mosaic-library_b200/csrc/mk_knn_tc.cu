@@ -308,6 +308,9 @@ knn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int qblk = blockIdx.x, split = blockIdx.y, z = blockIdx.z;
+    // float rows are followed by the guarded SIMT pass (mk_knn.cu), which only reads this kernel's verdict: let its CTAs be
+    // scheduled as soon as there is room (they wait in griddepcontrol.wait until this grid has completed)
+    if (KIND == 0) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     // problem of this CTA: rows [qrow0, qrow0 + nq) of the query matrix against rows [trow0, trow0 + nt) of the train matrix
     int qrow0 = 0, trow0 = 0, nq = p.nq, nt = p.nt, out0 = 0;
     if (p.pairs) {
