@@ -931,6 +931,8 @@ def multi_gpu(ctx) -> dict:
             matcher.knn_match_device(desc_d[k + 1], desc_d[k], RATIO)
         if transport["mode"] == "peer":
             mosaic.step_planned(k, None, peers=peers)                            # routed frames are composited straight out of the ingest GPU's memory
+        elif transport["mode"] == "peer_copy":
+            mosaic.step_planned(k, None, peers=peers, peer_copy=True)            # routed frames pulled whole by the copy engine, one step ahead
         else:
             mosaic.step_planned(k, frames[k], None if last else frames[k + 1])   # ncclSend/Recv, the exchange of step k+1 posted under step k
         main.wait_stream(s_match)
@@ -949,6 +951,9 @@ def multi_gpu(ctx) -> dict:
         """W untimed + K timed steps with this frame transport -> everything the JSON line needs from the pass."""
         transport["mode"] = mode
         mosaic._posted.clear()
+        if mosaic._pc is not None:
+            torch.cuda.synchronize()
+            mosaic._pc["posted"].clear()
         for k in range(W):
             one_step(k, last=(k == W - 1))
         barrier()
@@ -975,18 +980,25 @@ def multi_gpu(ctx) -> dict:
         step_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
         total_ms = max_over_ranks(float(step_ms.sum()))
         routed, applied, launches_all = sum_over_ranks([mosaic.bytes_sent - sent0, mosaic.frames_applied - applied0, launches])
-        return {"mode": mode, "total_ms": total_ms, "routed": routed, "applied": applied, "launches_all": launches_all, "clocks": ck}
+        # frame W + k straddles the seam when W + k is even (seam_lane): then this rank composites its part of its own frame AND the
+        # neighbouring lane's part that falls into its tile (two launches, together about one frame of pixels); otherwise one
+        # launch of a frame that lies inside its own tile -- the same work as the N = 1 step
+        kind = np.array([(W + k) % 2 == 0 for k in range(K)])
+        by_kind = {"frame_inside_own_tile_us": max_over_ranks(float(step_ms[~kind].mean() * 1e3)) if (~kind).any() else None,
+                   "frame_straddles_seam_us": max_over_ranks(float(step_ms[kind].mean() * 1e3)) if kind.any() else None}
+        return {"mode": mode, "total_ms": total_ms, "routed": routed, "applied": applied, "launches_all": launches_all, "clocks": ck,
+                "by_kind": by_kind}
 
     # Both frame transports get the same full pass; the faster one (same answer on every rank: the times are maxima over ranks) is
     # the headline and the other one is reported next to it.  --transport only decides which runs last.  NCCL's send/recv of a
     # whole frame wins at N = 2 (it hides under the kernels); from N = 4 on its per-peer bandwidth drops and the zero-copy peer
     # reads win.
-    other = "nccl" if args.transport == "peer" else "peer"
-    passes = [measured_pass(other), measured_pass(args.transport)]
+    modes = [m for m in ("nccl", "peer", "peer_copy") if m != args.transport] + [args.transport]
+    passes = [measured_pass(m) for m in modes]
     best = min(passes, key=lambda r: r["total_ms"])
-    rest = [r for r in passes if r is not best][0]
+    rest = [r for r in passes if r is not best]
     total_ms, routed, applied, launches_all, ck = best["total_ms"], best["routed"], best["applied"], best["launches_all"], best["clocks"]
-    chosen, other, other_ms = best["mode"], rest["mode"], rest["total_ms"]
+    chosen = best["mode"]
     value = world * K / (total_ms * 1e-3)
     assert routed > 0, "no frame crossed a tile seam: the sharded path was not exercised"
 
@@ -1028,12 +1040,19 @@ def multi_gpu(ctx) -> dict:
             "timing": "sum of per-step CUDA-event durations (start -> both streams joined), max over ranks; matching on its own (ordinary) stream, same policy as N=1",
             "blend": "alpha", "interp": "linear", "canvas": [BIG_GRID[0] * CANVAS, BIG_GRID[1] * CANVAS], "tile": [CANVAS, CANVAS], "frame": [fw, fh],
             "tile_updates_total": int(applied), "frame_bytes_routed_total": int(routed), "frame_bytes_routed_per_step": routed / K,
-            "transport": (chosen + (": no frame copies -- the owner of the neighbouring tile composites straight out of the ingest GPU's memory (cudaIpc mapping, the "
-                                    "kernel's 2-D TMA source boxes cross NVLink); routed bytes are counted as whole frames (upper bound)" if chosen == "peer"
-                                    else ": ncclSend/Recv of the whole frame, posted one step ahead") + "; the faster of the two transports, both timed the same way"),
+            "transport": (chosen + {"peer": ": no frame copies -- the owner of the neighbouring tile composites straight out of the ingest GPU's memory (cudaIpc mapping, the "
+                                            "kernel's 2-D TMA source boxes cross NVLink); routed bytes are counted as whole frames (upper bound)",
+                                    "peer_copy": ": the owner of the neighbouring tile pulls the whole frame out of the ingest GPU's memory with the copy engine "
+                                                 "(cudaIpc mapping + cudaMemcpyAsync over NVLink on a side stream, one step ahead): no SM is taken from the compositing kernel",
+                                    "nccl": ": ncclSend/Recv of the whole frame, posted one step ahead"}[chosen]
+                          + "; the fastest of the three transports, all timed the same way"),
         },
-        "other_transport": {"mode": other, "value": world * K / (other_ms * 1e-3), "ms_per_step": other_ms / K},
+        "other_transports": [{"mode": r["mode"], "value": world * K / (r["total_ms"] * 1e-3), "ms_per_step": r["total_ms"] / K,
+                              "step_us_by_kind": r["by_kind"]} for r in rest],
         "gpu_launches": int(launches_all), "clocks": ck,
+        "step_us_by_kind": dict(best["by_kind"], note=("max over ranks of the mean step time by kind of frame: a frame inside the rank's own tile is the N = 1 step (one "
+                                                       "launch); a frame that straddles the seam costs this rank two launches (its part of its own frame + the part of the "
+                                                       "neighbouring lane's frame that falls into its tile), about one frame of pixels in total")),
         "limiter": {"match_alone_us": stats_us(match_iso), "k4_own_tile_launch_us": stats_us(k4_iso), "nccl_sendrecv_one_frame_us": sr_us,
                     "nccl_sendrecv_gbs": frames[0].numel() / sr_us / 1e3,
                     "note": ("a step costs max(matching, compositing); compositing = this rank's frame into its own tile plus, every second step, the neighbour's frame "
@@ -1369,7 +1388,7 @@ def main():
     ap.add_argument("--sm-partition", type=int, default=40,
                     help="N=1 only: ALSO time the step with matching in its own group of at least this many SMs (green contexts), reported "
                          "under sm_partition_variant; the headline always uses two ordinary streams; 0 = skip the variant")
-    ap.add_argument("--transport", default="nccl", choices=["peer", "nccl"],
+    ap.add_argument("--transport", default="peer_copy", choices=["peer", "nccl", "peer_copy"],
                     help="N > 1: how a frame reaches the other ranks whose tiles its footprint overlaps; both are timed the same way, the faster one is the headline, "
                          "this flag only decides which one runs last")
     ap.add_argument("--no-feather", action="store_true")

@@ -229,6 +229,9 @@ int mk_chain_homographies(const double *H, int n, double *H_abs, void *stream);
 int mk_ipc_export(const void *dev_ptr, uint8_t *handle_out, uint64_t *offset_out);
 int mk_ipc_open(const uint8_t *handle, void **base_out);
 int mk_ipc_close(void *base);
+/* Whole-frame pull over NVLink by the COPY ENGINE (no SM, no NCCL kernel next to the persistent compositing kernel):
+ * cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream`, src typically a pointer obtained through mk_ipc_open. */
+int mk_copy_peer(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Per-frame pre-processing on the device (row N4): a frame that is already in device memory is

@@ -27,7 +27,7 @@ EXPORTS = (
     "mk_warp_perspective_u8", "mk_mapper_update", "mk_mapper_update_batch", "mk_mapper_footprint", "mk_upload_2d", "mk_download_2d",
     "mk_event_create", "mk_event_destroy", "mk_stream_follow", "mk_sm_partition_create", "mk_sm_partition_destroy",
     "mk_gather_matches", "mk_ransac_workspace_bytes", "mk_ransac_transform", "mk_chain_homographies",
-    "mk_ipc_export", "mk_ipc_open", "mk_ipc_close", "mk_cvt_color_u8", "mk_remap_u8",
+    "mk_ipc_export", "mk_ipc_open", "mk_ipc_close", "mk_copy_peer", "mk_cvt_color_u8", "mk_remap_u8",
 )
 MODEL_AFFINE, MODEL_PERSPECTIVE = 0, 1
 
@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
     L.mk_ipc_open.argtypes = [vp, C.POINTER(vp)]
     L.mk_ipc_close.restype = i32
     L.mk_ipc_close.argtypes = [vp]
+    L.mk_copy_peer.restype = i32
+    L.mk_copy_peer.argtypes = [vp, vp, sz, vp]
     if L.mk_abi_version() != 1:
         raise MosaicB200Error("libmosaic_b200 ABI version mismatch")
     _lib = L

@@ -50,6 +50,14 @@ extern "C" int mk_download_2d(void *dst_host, size_t dst_pitch, const void *src_
     return MK_OK;
 }
 
+extern "C" int mk_copy_peer(void *dst_dev, const void *src_dev, size_t bytes, void *stream)
+{
+    if (!dst_dev || !src_dev) { mk::set_error("mk_copy_peer: null pointer"); return MK_ERR_ARG; }
+    if (bytes == 0) return MK_OK;
+    MK_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return MK_OK;
+}
+
 extern "C" void *mk_event_create(void)
 {
     cudaEvent_t e = nullptr;

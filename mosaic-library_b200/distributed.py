@@ -128,6 +128,7 @@ class ShardedMosaic:
         self.mappers: dict[tuple[int, int], object] = {}
         self._recv = {}          # (source rank, step parity) -> receive buffer
         self._posted = {}        # step -> exchange posted ahead of time (step_planned with next_frame)
+        self._pc = None          # state of the copy-engine pulls (step_planned with peers and peer_copy=True)
         self.frames_applied = 0
         self.bytes_sent = 0
         self._host_group = None   # gloo group for the host-side pose exchange of the unplanned step()
@@ -211,15 +212,22 @@ class ShardedMosaic:
         self._plan_H = allH.reshape(self.world, -1, 3, 3)
         self._plan_table = [self.routing([self._plan_H[s, k] for s in range(self.world)]) for k in range(self._plan_H.shape[1])]
 
-    def step_planned(self, k: int, frame: torch.Tensor | None, next_frame: torch.Tensor | None = None, peers: "PeerFrames | None" = None) -> int:
+    def step_planned(self, k: int, frame: torch.Tensor | None, next_frame: torch.Tensor | None = None, peers: "PeerFrames | None" = None,
+                     peer_copy: bool = False) -> int:
         """Step k of a planned sequence: no collective, only the frame send/recv the routing asks for.
         With `next_frame` (this rank's frame of step k+1, already on the device) the exchange of step k+1 is posted BEFORE
         step k is composited, so the NVLink transfer runs under the kernels of step k (receive buffers alternate by step
         parity).  Every rank must then pass next_frame for the same steps, and the next call must be step k+1.
         With `peers` (PeerFrames over every rank's frames of the planned sequence) nothing is sent at all: a frame that another
         rank ingested is composited straight out of that GPU's memory (the kernel's TMA loads cross NVLink), frame k of rank s
-        being peers.ptr[s][k]."""
+        being peers.ptr[s][k].
+        With `peers` and peer_copy=True the frames other ranks ingested are PULLED whole by the copy engine instead
+        (mk_copy_peer: cudaMemcpyAsync out of the mapped peer memory on a side stream, the pulls of step k+1 queued before step k
+        is composited): no SM is taken from the persistent compositing kernel -- an NCCL send/recv kernel running next to it
+        costs the step ~10 us -- and the kernel reads local memory.  The next call must then be step k+1."""
         H_all = [self._plan_H[s, k] for s in range(self.world)]
+        if peers is not None and peer_copy:
+            return self._composite_peer_copy(k, H_all, peers)
         if peers is not None:
             return self._composite_peer(k, H_all, self._plan_table[k], peers)
         posted = self._posted.pop(k, None)
@@ -298,6 +306,63 @@ class ShardedMosaic:
                 done += 1
                 if s != self.rank:
                     self.bytes_sent += fh * fw * 3        # upper bound of what crosses NVLink: only the footprint's source rectangles do
+        self.frames_applied += done
+        return done
+
+    def _peer_pull(self, k: int, peers: "PeerFrames") -> dict:
+        """Queue the copy-engine pulls of the frames other ranks ingested and this rank composites at step k
+        -> {source rank: (local buffer, event 'landed')}.  Two buffers per source rank, by step parity."""
+        pc = self._pc
+        if pc is None:
+            from . import _lib
+            st = torch.cuda.Stream(device=self.device)
+            pc = self._pc = {"lib": _lib.lib(), "check": _lib.check, "stream": st, "sptr": st.cuda_stream, "bufs": {}, "landed": {}, "free": {},
+                             "posted": {}}
+        got = {}
+        for s, dests in enumerate(self._plan_table[k]):
+            if s == self.rank or self.rank not in dests:
+                continue
+            key = (s, k & 1)
+            buf = pc["bufs"].get(key)
+            if buf is None:
+                buf = pc["bufs"][key] = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device)
+                pc["landed"][key] = torch.cuda.Event()
+            free = pc["free"].get(k & 1)
+            if free is not None:
+                pc["stream"].wait_event(free)          # the kernels of step k-2 have read this buffer
+            ptr, fh, fw = peers.ptr[s][k]
+            with torch.cuda.device(self.device):
+                pc["check"](pc["lib"].mk_copy_peer(buf.data_ptr(), ptr, fh * fw * 3, pc["sptr"]))
+            pc["landed"][key].record(pc["stream"])
+            got[s] = (buf, pc["landed"][key])
+            self.bytes_sent += fh * fw * 3
+        return got
+
+    def _composite_peer_copy(self, k: int, H_all, peers: "PeerFrames") -> int:
+        pulled = self._pc["posted"].pop(k, None) if self._pc is not None else None
+        if pulled is None:
+            pulled = self._peer_pull(k, peers)
+        if k + 1 < len(self._plan_table):
+            self._pc["posted"][k + 1] = self._peer_pull(k + 1, peers)      # runs under the kernels of step k
+        main = torch.cuda.current_stream(self.device)
+        done = 0
+        for s, dests in enumerate(self._plan_table[k]):
+            if self.rank not in dests:
+                continue
+            if s != self.rank:
+                main.wait_event(pulled[s][1])
+            for (xi, yi) in dests[self.rank]:
+                H_tile = homogeneous_translation(-xi * self.tile_size[0], -yi * self.tile_size[1]) @ H_all[s]   # mosaic.py:617
+                if s == self.rank:
+                    ptr, fh, fw = peers.ptr[s][k]
+                    self._mapper((xi, yi)).update_pointer(ptr, fh, fw, fw * 3, H_tile)
+                else:
+                    self._mapper((xi, yi)).update_device(pulled[s][0], H_tile)
+                done += 1
+        ev = self._pc["free"].get(k & 1)
+        if ev is None:
+            ev = self._pc["free"][k & 1] = torch.cuda.Event()
+        ev.record(main)
         self.frames_applied += done
         return done
 

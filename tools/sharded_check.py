@@ -1,6 +1,7 @@
 """N-GPU numerical check of ShardedMosaic: planned steps, real Mapper kernels, gather -> compare bit for bit with rendering every
 tile sequentially on one GPU (reference-tile semantics).  Two transports: "nccl" (frames sent with ncclSend/Recv, the exchange of
-step k+1 posted ahead) and "peer" (no copy: the compositing kernel reads the other GPU's frame over NVLink, distributed.PeerFrames).
+step k+1 posted ahead), "peer" (no copy: the compositing kernel reads the other GPU's frame over NVLink, distributed.PeerFrames)
+and "peer_copy" (the frame is pulled whole out of the other GPU's memory by the copy engine, one step ahead).
 torchrun --nproc-per-node N tools/sharded_check.py"""
 import os, sys
 from pathlib import Path
@@ -25,15 +26,15 @@ for k in range(STEPS):
 factory = lambda w, h: mb.Mapper(w, h, alpha_blend=0.5, interp="linear", device=dev)
 fr = [torch.from_numpy(frames[k, rank]).to(dev) for k in range(STEPS)]
 want = None
-for mode in ("nccl", "peer"):
+for mode in ("nccl", "peer", "peer_copy"):
     sm = ShardedMosaic(GRID, TILE, factory, FRAME, dev)
     sm.connect(); sm.plan(Hs[:, rank])
-    peers = PeerFrames(fr, dev) if mode == "peer" else None
+    peers = PeerFrames(fr, dev) if mode != "nccl" else None
     for k in range(STEPS):
         if peers is None:
             sm.step_planned(k, fr[k], fr[k + 1] if k + 1 < STEPS else None)
         else:
-            sm.step_planned(k, None, peers=peers)
+            sm.step_planned(k, None, peers=peers, peer_copy=(mode == "peer_copy"))
     torch.cuda.synchronize()
     if peers is not None:
         peers.close()
