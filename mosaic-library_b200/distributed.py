@@ -222,8 +222,8 @@ class ShardedMosaic:
         rank ingested is composited straight out of that GPU's memory (the kernel's TMA loads cross NVLink), frame k of rank s
         being peers.ptr[s][k].
         With `peers` and peer_copy=True the frames other ranks ingested are PULLED whole by the copy engine instead
-        (mk_copy_peer: cudaMemcpyAsync out of the mapped peer memory on a side stream, the pulls of step k+1 queued before step k
-        is composited): no SM is taken from the persistent compositing kernel -- an NCCL send/recv kernel running next to it
+        (mk_copy_peer: cudaMemcpyAsync out of the mapped peer memory on a side stream, the pulls of steps k+1 and k+2 queued before
+        step k is composited): no SM is taken from the persistent compositing kernel -- an NCCL send/recv kernel running next to it
         costs the step ~10 us -- and the kernel reads local memory.  The next call must then be step k+1."""
         H_all = [self._plan_H[s, k] for s in range(self.world)]
         if peers is not None and peer_copy:
@@ -309,9 +309,12 @@ class ShardedMosaic:
         self.frames_applied += done
         return done
 
+    PULL_AHEAD = 2           # peer_copy: the pulls of step k + 2 are queued before step k is composited (a 6 MB pull over NVSwitch
+                             # takes longer than one ~35 us step when all eight GPUs pull at once)
+
     def _peer_pull(self, k: int, peers: "PeerFrames") -> dict:
         """Queue the copy-engine pulls of the frames other ranks ingested and this rank composites at step k
-        -> {source rank: (local buffer, event 'landed')}.  Two buffers per source rank, by step parity."""
+        -> {source rank: (local buffer, event 'landed')}.  PULL_AHEAD + 1 buffers per source rank, by step modulo."""
         pc = self._pc
         if pc is None:
             from . import _lib
@@ -322,14 +325,15 @@ class ShardedMosaic:
         for s, dests in enumerate(self._plan_table[k]):
             if s == self.rank or self.rank not in dests:
                 continue
-            key = (s, k & 1)
+            slot = k % (self.PULL_AHEAD + 1)
+            key = (s, slot)
             buf = pc["bufs"].get(key)
             if buf is None:
                 buf = pc["bufs"][key] = torch.empty((self.h, self.w, 3), dtype=torch.uint8, device=self.device)
                 pc["landed"][key] = torch.cuda.Event()
-            free = pc["free"].get(k & 1)
+            free = pc["free"].get(slot)
             if free is not None:
-                pc["stream"].wait_event(free)          # the kernels of step k-2 have read this buffer
+                pc["stream"].wait_event(free)          # the kernels of step k - (PULL_AHEAD + 1) have read this buffer
             ptr, fh, fw = peers.ptr[s][k]
             with torch.cuda.device(self.device):
                 pc["check"](pc["lib"].mk_copy_peer(buf.data_ptr(), ptr, fh * fw * 3, pc["sptr"]))
@@ -339,11 +343,13 @@ class ShardedMosaic:
         return got
 
     def _composite_peer_copy(self, k: int, H_all, peers: "PeerFrames") -> int:
-        pulled = self._pc["posted"].pop(k, None) if self._pc is not None else None
-        if pulled is None:
-            pulled = self._peer_pull(k, peers)
-        if k + 1 < len(self._plan_table):
-            self._pc["posted"][k + 1] = self._peer_pull(k + 1, peers)      # runs under the kernels of step k
+        if self._pc is None or k not in self._pc["posted"]:
+            first = self._peer_pull(k, peers)
+            self._pc["posted"][k] = first
+        for j in range(k + 1, min(k + self.PULL_AHEAD, len(self._plan_table) - 1) + 1):
+            if j not in self._pc["posted"]:
+                self._pc["posted"][j] = self._peer_pull(j, peers)          # runs under the kernels of steps k .. j-1
+        pulled = self._pc["posted"].pop(k)
         main = torch.cuda.current_stream(self.device)
         done = 0
         for s, dests in enumerate(self._plan_table[k]):
@@ -359,9 +365,10 @@ class ShardedMosaic:
                 else:
                     self._mapper((xi, yi)).update_device(pulled[s][0], H_tile)
                 done += 1
-        ev = self._pc["free"].get(k & 1)
+        slot = k % (self.PULL_AHEAD + 1)
+        ev = self._pc["free"].get(slot)
         if ev is None:
-            ev = self._pc["free"][k & 1] = torch.cuda.Event()
+            ev = self._pc["free"][slot] = torch.cuda.Event()
         ev.record(main)
         self.frames_applied += done
         return done
