@@ -1165,7 +1165,7 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
     rng = np.random.default_rng(200 + rank)
     ring = [torch.from_numpy(rng.integers(1, 256, (fh, fw, 3), dtype=np.uint8)).to(dev) for _ in range(4)]
     factory = lambda w_, h_: mb.Mapper(w_, h_, alpha_blend=ALPHA, interp="linear", device=dev)  # noqa: E731
-    res = {"workload": "BASELINE configs[3]: 3840x2160 frames, 65536x65536 canvas = 4x4 tiles of 16384^2 sharded over the ranks, footprint routing (ncclSend/Recv), compositing only"}
+    res = {"workload": "BASELINE configs[3]: 3840x2160 frames, 65536x65536 canvas = 4x4 tiles of 16384^2 sharded over the ranks, footprint routing (three transports: ncclSend/Recv, in-place peer reads, copy-engine pulls), compositing only"}
 
     def run(lanes, nper, tag, transport="nccl"):
         """this rank ingests `lanes` (list of lane ids), nper frames each, lane after lane; transport "nccl" sends a routed frame to
@@ -1182,15 +1182,18 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
             for s, dests in enumerate(mosaic._plan_table[k]):
                 for t in dests.get(rank, []):
                     mosaic._mapper(t)
-        peers = PeerFrames([ring[k % 4] for k in range(n)], dev, rank=rank, world=world) if transport == "peer" else None
+        peers = PeerFrames([ring[k % 4] for k in range(n)], dev, rank=rank, world=world) if transport != "nccl" else None
         def step(k, last):
             if peers is not None:
-                mosaic.step_planned(k, None, peers=peers)
+                mosaic.step_planned(k, None, peers=peers, peer_copy=(transport == "peer_copy"))
             else:
                 mosaic.step_planned(k, ring[k % 4], None if last else ring[(k + 1) % 4])
         for k in range(min(2, n)):                       # warm-up (first launches, NCCL buffers)
             step(k, k + 1 >= min(2, n))
         mosaic._posted.clear()
+        if mosaic._pc is not None:
+            torch.cuda.synchronize()
+            mosaic._pc["posted"].clear()
         barrier()
         sent0, app0 = mosaic.bytes_sent, mosaic.frames_applied
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1220,6 +1223,10 @@ def config3_record(ctx, barrier, max_over_ranks, sum_over_ranks) -> dict:
         res["strong_peer"]["note"] = ("same sets, no frame copies: the owner of the neighbouring tile composites straight out of the ingest GPU's memory "
                                       "(cudaIpc mapping, the kernel's TMA source boxes cross NVLink); frame_bytes_routed is the upper bound (whole frames), "
                                       "only the footprint's source rectangles move")
+        res["weak_peer_copy"] = run([rank], kw, "weak", "peer_copy")
+        res["strong_peer_copy"] = run([l for l in range(8) if l % world == rank], 8, "strong", "peer_copy")
+        res["strong_peer_copy"]["note"] = ("same sets, routed frames pulled whole out of the ingest GPU's memory by the copy engine, two steps ahead "
+                                           "(the headline's transport; at 4K the in-place reads of `peer` move less data)")
     return res
 
 
