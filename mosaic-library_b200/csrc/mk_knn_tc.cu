@@ -865,8 +865,16 @@ int knn_tc_run(int norm, const void *q, int nq, const void *t, int nt, int dim, 
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    if (P.hamming) MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P));
-    else MK_CUDA_TRY(cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P));
+    cudaError_t le = P.hamming ? cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P) : cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P);
+    if (le != cudaSuccess && P.cluster_merge) {
+        // a cluster of `splits` one-CTA-per-SM blocks does not fit this stream's SMs (a small green-context partition, MIG):
+        // same kernel without the cluster, the splits merge through global memory
+        cudaGetLastError();
+        P.cluster_merge = 0;
+        cfg.numAttrs = na - 1;
+        le = P.hamming ? cudaLaunchKernelEx(&cfg, knn2_tc_kernel<1>, map_q, map_t, P) : cudaLaunchKernelEx(&cfg, knn2_tc_kernel<0>, map_q, map_t, P);
+    }
+    MK_CUDA_TRY(le);
     MK_LAUNCH_CHECK("knn2_tc_kernel");
     *flags_out = flags;
     if (tc_count_out) *tc_count_out = cnt;
