@@ -19,6 +19,8 @@ Each rank ingests its own frame stream ("camera"), so per-GPU work is constant a
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Sequence
 
 import numpy as np
@@ -309,7 +311,7 @@ class ShardedMosaic:
         self.frames_applied += done
         return done
 
-    PULL_AHEAD = 2           # peer_copy: the pulls of step k + 2 are queued before step k is composited (a 6 MB pull over NVSwitch
+    PULL_AHEAD = int(os.environ.get("MK_PULL_AHEAD", "2"))   # peer_copy: the pulls of step k + 2 are queued before step k is composited (a 6 MB pull over NVSwitch
                              # takes longer than one ~35 us step when all eight GPUs pull at once)
 
     def _peer_pull(self, k: int, peers: "PeerFrames") -> dict:
