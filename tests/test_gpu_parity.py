@@ -834,6 +834,51 @@ def test_peer_frames_single_process_and_update_pointer():
     assert np.array_equal(a.gather(0), b.gather(0)) and a.frames_applied == b.frames_applied >= 4
 
 
+def test_peer_copy_transport_two_ranks_in_one_process():
+    """The copy-engine transport (ShardedMosaic.step_planned(..., peers=, peer_copy=True): frames other ranks ingested are pulled
+    whole with mk_copy_peer on a side stream, two steps ahead, into a ring of staging buffers) with BOTH ranks of a world of 2
+    emulated in this process on one GPU: every owned tile equals the oracle rendering of the frames routed to it, applied in
+    source-rank order (mosaic.py:595-622 per tile).  The cross-process mapping itself is checked by tools/sharded_check.py."""
+    from types import SimpleNamespace
+    from mosaicking_b200.distributed import ShardedMosaic, tiles_of_footprint
+    dev = torch.device("cuda", 0)
+    TILE, GRID, FRAME, STEPS, WORLD = (400, 360), (2, 1), (240, 320), 9, 2
+    rng = np.random.default_rng(33)
+    host = [[_img(rng, FRAME[0], FRAME[1]) for _ in range(STEPS)] for _ in range(WORLD)]
+    frames = [[torch.from_numpy(f).to(dev) for f in row] for row in host]
+    Hs = np.zeros((WORLD, STEPS, 3, 3))
+    for k in range(STEPS):
+        for r in range(WORLD):
+            th = 0.04 * k - 0.1 * r
+            Hs[r, k] = [[np.cos(th), -np.sin(th), 60.0 + 45 * k + 150 * r], [np.sin(th), np.cos(th), 40.0 + 8 * k + 30 * r], [0, 0, 1.0]]
+    peers = SimpleNamespace(ptr=[[(f.data_ptr(), FRAME[0], FRAME[1]) for f in row] for row in frames])
+    ranks = []
+    for r in range(WORLD):
+        sm = ShardedMosaic(GRID, TILE, lambda w, h: mb.Mapper(w, h, alpha_blend=0.5, interp="linear", device=dev), FRAME, dev, rank=r, world=WORLD)
+        sm._plan_H = Hs
+        sm._plan_table = [sm.routing([Hs[s, k] for s in range(WORLD)]) for k in range(STEPS)]
+        ranks.append(sm)
+    for k in range(STEPS):
+        for sm in ranks:
+            sm.step_planned(k, None, peers=peers, peer_copy=True)
+    torch.cuda.synchronize()
+    pulled = 0
+    for r, sm in enumerate(ranks):
+        want = {}
+        for k in range(STEPS):
+            for s in range(WORLD):
+                for (xi, yi) in tiles_of_footprint(Hs[s, k], FRAME[1], FRAME[0], TILE, GRID):
+                    if sm.owner((xi, yi)) != r:
+                        continue
+                    pulled += s != r
+                    cv, cm = want.setdefault((xi, yi), (np.zeros((TILE[1], TILE[0], 3), np.uint8), np.zeros((TILE[1], TILE[0]), np.uint8)))
+                    orc.mapper_update(cv, cm, host[s][k], mb.homogeneous_translation(-xi * TILE[0], -yi * TILE[1]) @ Hs[s, k], 0.5, 1)
+        assert set(want) == set(sm.mappers)
+        for t, (cv, cm) in want.items():
+            assert np.array_equal(sm.mappers[t].output, cv) and np.array_equal(sm.mappers[t].mask, cm), (r, t)
+    assert pulled >= 6 and sum(sm.bytes_sent for sm in ranks) == pulled * FRAME[0] * FRAME[1] * 3
+
+
 # ------------------------------------------------------------------------------------------------
 # row N4: pre-processing on the device (preprocessing.py:68-98, 314-346)
 # ------------------------------------------------------------------------------------------------
